@@ -1,0 +1,367 @@
+"""oracle/gen_golden.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Generates tests/golden/*.npz by running the UNMODIFIED reference Python code
+(/root/reference/src/{Mapper,Tracker,common}.py, src/utils/Renderer.py,
+src/networks/decoders.py) on CPU through oracle/shims, recording every RNG draw, the inputs
+and outputs of the hot-path seams (get_samples / get_samples_all / render_batch_ray), the loss
+and the gradients Adam sees.  Run in the build container only (needs /root/reference):
+
+    python -m oracle.gen_golden
+
+The fixtures pin oracle/path_ref.py (tests/test_oracle_golden.py) and are compared directly with
+the CUDA path in the -m gpu tests.  Grid tables and decoder weights are filled with the
+platform-independent integer-hash generator grid_ref.lcg_params, so fixtures carry no tables.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = "/root/reference"
+OUT = os.path.join(REPO, "tests", "golden")
+
+CASES = {
+    # name: (yaml, decoder variant implied by yaml, H, W, intrinsics scale, n_keyframes, joint_opt)
+    "map_replica_k1": dict(yaml="configs/Replica/room0.yaml", H=60, W=80, s=1 / 15.0, n_kf=0, pixels=240, lr_factor=5),
+    "map_replica_k7": dict(yaml="configs/Replica/room0.yaml", H=60, W=80, s=1 / 15.0, n_kf=6, pixels=280, lr_factor=1),
+    "map_scannet_k23": dict(yaml="configs/ScanNet/scene0000.yaml", H=46, W=62, s=0.1, n_kf=22, pixels=230, lr_factor=1),
+    "track_replica": dict(yaml="configs/Replica/room0.yaml", H=60, W=80, s=1 / 15.0, pixels=200, edge=6),
+    "track_scannet": dict(yaml="configs/ScanNet/scene0000.yaml", H=46, W=62, s=0.1, pixels=200, edge=5),
+}
+
+
+def _setup_paths():
+    sys.path[:0] = [os.path.join(HERE, "shims"), REF, REPO]
+    os.chdir(REF)   # the yaml files use repo-relative inherit_from paths (src/config.py:38-43)
+
+
+class Recorder:
+    def __init__(self):
+        self.draws = []       # (kind, tensor)
+        self.samples = []     # get_samples / get_samples_all calls
+        self.renders = []
+        self.losses = []
+        self.steps = []       # list of list-of-grads per optimizer.step()
+
+    def install(self):
+        import src.Mapper as M
+        import src.Tracker as T
+        rec = self
+        self._orig = dict(rand=torch.rand, randint=torch.randint, randperm=torch.randperm,
+                          backward=torch.Tensor.backward, step=torch.optim.Adam.step,
+                          gsa=M.get_samples_all, gs=T.get_samples)
+
+        def rand(*a, **k):
+            t = rec._orig["rand"](*a, **k); rec.draws.append(("rand", t.clone())); return t
+
+        def randint(*a, **k):
+            t = rec._orig["randint"](*a, **k); rec.draws.append(("randint", t.clone())); return t
+
+        def randperm(*a, **k):
+            t = rec._orig["randperm"](*a, **k); rec.draws.append(("randperm", t.clone())); return t
+
+        def backward(self_t, *a, **k):
+            rec.losses.append(self_t.detach().clone()); return rec._orig["backward"](self_t, *a, **k)
+
+        def step(opt, *a, **k):
+            rec.steps.append([[None if p.grad is None else p.grad.detach().clone() for p in g["params"]]
+                              for g in opt.param_groups])
+            rec.params_at_step = [[p.detach().clone() for p in g["params"]] for g in opt.param_groups]
+            return rec._orig["step"](opt, *a, **k)
+
+        def gsa(*a, **k):
+            out = rec._orig["gsa"](*a, **k)
+            rec.samples.append(dict(kind="all", args=[x.detach().clone() if torch.is_tensor(x) else x for x in a],
+                                    out=[o.detach().clone() for o in out]))
+            return out
+
+        def gs(*a, **k):
+            out = rec._orig["gs"](*a, **k)
+            rec.samples.append(dict(kind="win", args=[x.detach().clone() if torch.is_tensor(x) else x for x in a],
+                                    out=[o.detach().clone() for o in out]))
+            return out
+
+        torch.rand, torch.randint, torch.randperm = rand, randint, randperm
+        torch.Tensor.backward = backward
+        torch.optim.Adam.step = step
+        M.get_samples_all = gsa
+        T.get_samples = gs
+
+    def uninstall(self):
+        import src.Mapper as M
+        import src.Tracker as T
+        torch.rand, torch.randint, torch.randperm = self._orig["rand"], self._orig["randint"], self._orig["randperm"]
+        torch.Tensor.backward = self._orig["backward"]
+        torch.optim.Adam.step = self._orig["step"]
+        M.get_samples_all = self._orig["gsa"]
+        T.get_samples = self._orig["gs"]
+
+
+def _load_cfg(case):
+    from src import config
+    cfg = config.load_config(case["yaml"], "configs/UNISLAM.yaml")
+    cfg["device"] = "cpu"; cfg["keyframe_device"] = "cpu"
+    s = case["s"]
+    cam = cfg["cam"]
+    # the reference applies crop_edge in UNISLAM.update_cam; here we directly give the post-crop camera, scaled
+    edge = cam["crop_edge"]
+    cam.update(H=case["H"], W=case["W"], fx=cam["fx"] * s, fy=cam["fy"] * s, cx=(cam["cx"] - edge) * s,
+               cy=(cam["cy"] - edge) * s, crop_edge=0)
+    return cfg
+
+
+def _build_world(cfg, seed_salt):
+    """Grids (via the reference's own get_encoder arithmetic), decoders (reference class), bound."""
+    import tinycudann as tcnn
+    from src.networks.decoders import Decoders
+    from oracle import grid_ref, path_ref
+    bound = path_ref.load_bound(cfg["mapping"]["bound"], cfg["scale"], cfg["planes_res"]["bound_dividable"])
+    dim_max = (bound[:, 1] - bound[:, 0]).max()
+    grids = []
+    for key_hash, key_vox, salt in (("hash_size_sdf", "voxel_sdf", 1), ("hash_size_color", "voxel_color", 2)):
+        res = int(dim_max / cfg["grid"][key_vox])                                   # UNISLAM.py:196-199
+        pls = np.exp2(np.log2(res / 16) / (16 - 1))                                  # UNISLAM.py:241
+        enc = tcnn.Encoding(n_input_dims=3, encoding_config={
+            "otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2,
+            "log2_hashmap_size": cfg["grid"][key_hash], "base_resolution": 16, "per_level_scale": pls}, dtype=torch.float)
+        with torch.no_grad():
+            enc.params.copy_(torch.from_numpy(grid_ref.lcg_params(enc.params.numel(), 0.05, salt + seed_salt)))
+        grids.append(enc)
+    dec = Decoders(cfg, c_dim=cfg["model"]["c_dim"], truncation=cfg["model"]["truncation"],
+                   learnable_beta=cfg["rendering"]["learnable_beta"])
+    dec.bound = bound
+    with torch.no_grad():
+        for k, (name, p) in enumerate(sorted(dec.named_parameters())):
+            if name == "beta":
+                continue
+            fan_in = p.shape[-1] if p.dim() > 1 else 16
+            sc = 1.0 / np.sqrt(fan_in) if p.numel() != 768 else 0.35
+            p.copy_(torch.from_numpy(grid_ref.lcg_params(p.numel(), sc, 100 + k + seed_salt)).reshape(p.shape))
+    return bound, grids, dec
+
+
+def _frames(cfg, case, n, seed):
+    """Tiny synthetic frames (stored in the fixture, so generation need not be reproducible)."""
+    import importlib
+    syn = importlib.import_module("uni-slam_b200.synthetic")
+    cam = syn.CameraCfg(case["H"], case["W"], cfg["cam"]["fx"], cfg["cam"]["fy"], cfg["cam"]["cx"], cfg["cam"]["cy"])
+    room = syn.AnalyticRoom(cfg["mapping"]["bound"])
+    poses = syn.trajectory(room, 200)
+    dirs = syn.camera_dirs(cam)
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for k in range(n):
+        c2w = poses[(k * 4) % 200]
+        d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
+        t, p = room.trace(c2w[:3, 3].expand(d.shape), d)
+        col = torch.where((t > 0)[..., None], room.albedo(p), torch.zeros(3))
+        hole = torch.rand(t.shape, generator=g) < 0.05
+        t = torch.where(hole, torch.zeros_like(t), t)
+        out.append((col.float().contiguous(), t.float().contiguous(), c2w.clone()))
+    return out, dirs
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+
+
+def _grad_summary(prefix, g, spec, out):
+    g64 = g.double().reshape(-1, 2)
+    lv_sum, lv_norm = [], []
+    for lv in spec.levels:
+        seg = g64[lv.offset: lv.offset + lv.size]
+        lv_sum.append(seg.sum().item()); lv_norm.append(seg.norm().item())
+    nz = torch.nonzero(g.reshape(-1)).reshape(-1)
+    pick = nz[torch.linspace(0, nz.numel() - 1, min(4096, nz.numel())).long()] if nz.numel() else nz
+    out[prefix + "_level_sum"] = np.array(lv_sum); out[prefix + "_level_norm"] = np.array(lv_norm)
+    out[prefix + "_nnz"] = np.array(nz.numel()); out[prefix + "_idx"] = _np(pick); out[prefix + "_val"] = _np(g.reshape(-1)[pick])
+
+
+def gen_mapping(name, case):
+    from src.Mapper import Mapper
+    from src.utils.Renderer import Renderer
+    from src.common import get_camera_rays
+    cfg = _load_cfg(case)
+    cfg["mapping"]["pixels"] = case["pixels"]
+    bound, grids, dec = _build_world(cfg, 0)
+    H, W = case["H"], case["W"]
+    cam = cfg["cam"]
+    n_kf = case["n_kf"]
+    frames, dirs = _frames(cfg, case, n_kf + 1, seed=7)
+    fake = types.SimpleNamespace(bound=bound, device="cpu", H=H, W=W, fx=cam["fx"], fy=cam["fy"], cx=cam["cx"], cy=cam["cy"])
+    renderer = Renderer(cfg, fake)
+    m = object.__new__(Mapper)
+    m.cfg = cfg; m.device = "cpu"; m.truncation = cfg["model"]["truncation"]; m.bound = bound
+    m.renderer = renderer; m.decoders = dec
+    m.hash_grids_xyz = [grids[0]]; m.c_hash_grids_xyz = [grids[1]]
+    m.H, m.W, m.fx, m.fy, m.cx, m.cy = H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"]
+    for k in ("w_sdf_fs", "w_sdf_center", "w_sdf_tail", "w_depth", "w_color"):
+        setattr(m, k, cfg["mapping"][k])
+    m.mapping_pixels = cfg["mapping"]["pixels"]; m.mapping_window_size = cfg["mapping"]["mapping_window_size"]
+    m.keyframe_selection_method = cfg["mapping"]["keyframe_selection_method"]
+    m.m_mask_mode = cfg["m_mask_mode"]; m.no_vis_on_first_frame = True
+    m.joint_opt_cam_lr = cfg["mapping"]["joint_opt_cam_lr"]; m.LC = cfg["mapping"]["LC"]
+    m.LC_cnt = torch.zeros(1).int(); m.tracking_back = torch.tensor([0])
+    m.activated_mapping_mode = cfg["tracking"].get("activated_mapping_mode", False)
+    m.visualizer = types.SimpleNamespace(save_imgs=lambda *a, **k: None)
+    rays_d_cam = get_camera_rays(H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+    assert torch.equal(rays_d_cam, dirs)
+    # keyframe store exactly as Mapper.run builds it (Mapper.py:528-541)
+    torch.manual_seed(11)
+    m.keyframe_dict, m.keyframe_list = [], []
+    est = torch.zeros(4 * (n_kf + 1) + 1, 4, 4)
+    for k in range(n_kf):
+        col, dep, c2w = frames[k]
+        idx = 4 * k
+        ind = torch.randperm(H * W)[: int(H * W * 0.1)]
+        noisy = c2w.clone(); noisy[:3, 3] += 0.01 * torch.randn(3)
+        est[idx] = noisy
+        m.keyframe_list.append(idx)
+        m.keyframe_dict.append({"gt_c2w": c2w, "idx": idx, "color": col.reshape(-1, 3)[ind], "depth": dep.reshape(-1)[ind],
+                                "est_c2w": noisy.clone(), "rays_d": rays_d_cam.reshape(-1, 3)[ind]})
+    m.estimate_c2w_list = est
+    m.joint_opt = (len(m.keyframe_list) > 4) and cfg["mapping"]["joint_opt"]           # Mapper.py:519
+    col, dep, c2w = frames[n_kf]
+    cur_idx = 4 * n_kf
+    cur_c2w = c2w.clone(); cur_c2w[:3, 3] += 0.01
+    rec = Recorder(); rec.install()
+    orig_render = renderer.render_batch_ray
+
+    def render(*a, **k):
+        out = orig_render(*a, **k)
+        rec.renders.append(dict(rays_d=a[2].detach().clone(), rays_o=a[3].detach().clone(),
+                                gt_depth=k["gt_depth"].detach().clone(), out=[o.detach().clone() for o in out]))
+        return out
+    renderer.render_batch_ray = render
+    try:
+        torch.manual_seed(2)
+        m.optimize_mapping(1, case["lr_factor"], cur_idx, col, dep, c2w, m.keyframe_dict, m.keyframe_list, cur_c2w, rays_d_cam)
+    finally:
+        rec.uninstall()
+    out = {}
+    out["meta_H_W_fx_fy_cx_cy"] = np.array([H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"]], dtype=np.float64)
+    out["bound"] = _np(bound); out["truncation"] = np.array(m.truncation)
+    out["n_stratified"] = np.array(cfg["rendering"]["n_stratified"]); out["n_importance"] = np.array(cfg["rendering"]["n_importance"])
+    out["log2_hash"] = np.array([cfg["grid"]["hash_size_sdf"], cfg["grid"]["hash_size_color"]])
+    out["per_level_scale"] = np.array([grids[0].spec.per_level_scale, grids[1].spec.per_level_scale])
+    out["variant"] = np.array("B" if cfg["grid"]["tcnn_network"] else "A")
+    out["joint_opt"] = np.array(int(m.joint_opt))
+    # sampling calls (first = main batch; optional second = the 200px x last-10-frames batch)
+    calls = [s for s in rec.samples if s["kind"] == "all"]
+    out["n_sample_calls"] = np.array(len(calls))
+    randints = [t for k, t in rec.draws if k == "randint"]
+    rands = [t for k, t in rec.draws if k == "rand"]
+    for ci, s in enumerate(calls):
+        a = s["args"]
+        out[f"call{ci}_n"] = np.array(a[4]); out[f"call{ci}_c2ws"] = _np(a[11]); out[f"call{ci}_depths"] = _np(a[12])
+        out[f"call{ci}_colors"] = _np(a[13]); out[f"call{ci}_rays_d_cam"] = _np(a[15])
+        out[f"call{ci}_indices"] = _np(randints[len(randints) - len(calls) + ci])
+        for nm, o in zip(("rays_o", "rays_d", "depth", "color"), s["out"]):
+            out[f"call{ci}_out_{nm}"] = _np(o)
+    r = rec.renders[-1]
+    n_valid = int((r["gt_depth"] > 0).sum()); n0 = r["gt_depth"].numel() - n_valid
+    tail = rands[-3:] if n0 > 0 else rands[-1:]
+    out["t_rand"] = _np(tail[0]); assert tail[0].shape[0] == n_valid
+    if n0 > 0:
+        out["t_rand_uni"] = _np(tail[1]); out["u_pdf"] = _np(tail[2])
+    out["render_rays_o"] = _np(r["rays_o"]); out["render_rays_d"] = _np(r["rays_d"]); out["render_gt_depth"] = _np(r["gt_depth"])
+    for nm, o in zip(("term", "pixel_unc", "depth", "rgb", "sdf", "z_vals", "depth_unc"), r["out"]):
+        out["ret_" + nm] = _np(o)
+    out["loss"] = _np(rec.losses[-1])
+    grads = rec.steps[-1]; pvals = rec.params_at_step
+    dec_names = [n for n, _ in dec.named_parameters()]
+    for n_, g in zip(dec_names, grads[0]):
+        out["grad_dec." + n_] = _np(g)
+    _grad_summary("grad_sdf_table", grads[1][0], grids[0].spec, out)
+    _grad_summary("grad_rgb_table", grads[2][0], grids[1].spec, out)
+    if m.joint_opt:
+        out["cam_poses"] = _np(pvals[3][0]); out["grad_cam_poses"] = _np(grads[3][0])
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "rays", r["gt_depth"].numel(), "holes", n0, "loss", float(rec.losses[-1]), "calls", len(calls))
+
+
+def gen_tracking(name, case):
+    from src.Tracker import Tracker
+    from src.utils.Renderer import Renderer
+    from src.common import matrix_to_cam_pose
+    cfg = _load_cfg(case)
+    bound, grids, dec = _build_world(cfg, 50)
+    H, W = case["H"], case["W"]
+    cam = cfg["cam"]
+    frames, dirs = _frames(cfg, case, 2, seed=9)
+    fake = types.SimpleNamespace(bound=bound, device="cpu", H=H, W=W, fx=cam["fx"], fy=cam["fy"], cx=cam["cx"], cy=cam["cy"])
+    renderer = Renderer(cfg, fake)
+    t = object.__new__(Tracker)
+    t.cfg = cfg; t.device = "cpu"; t.truncation = cfg["model"]["truncation"]; t.bound = bound
+    t.renderer = renderer; t.decoders = dec
+    for p in t.decoders.parameters():
+        p.requires_grad_(False)                                                        # Tracker.py:110-111
+    t.hash_grids_xyz = [grids[0]]; t.c_hash_grids_xyz = [grids[1]]
+    t.H, t.W, t.fx, t.fy, t.cx, t.cy = H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"]
+    for k in ("w_sdf_fs", "w_sdf_center", "w_sdf_tail", "w_depth", "w_color"):
+        setattr(t, k, cfg["tracking"][k])
+    t.ignore_edge_H = t.ignore_edge_W = case["edge"]
+    t.t_mask_mode = cfg["t_mask_mode"]
+    col, dep, c2w = frames[1]
+    c2w_init = c2w.clone(); c2w_init[:3, 3] += torch.tensor([0.012, -0.008, 0.005])
+    cam_pose0 = matrix_to_cam_pose(c2w_init.unsqueeze(0))
+    cam_pose0[:, :4] += torch.tensor([0.002, -0.003, 0.001, 0.002])                   # un-normalised quaternion on purpose
+    T = torch.nn.Parameter(cam_pose0[:, -3:].clone()); R = torch.nn.Parameter(cam_pose0[:, :4].clone())
+    opt = torch.optim.Adam([{"params": [T], "lr": cfg["tracking"]["lr_T"], "betas": (0.5, 0.999)},
+                            {"params": [R], "lr": cfg["tracking"]["lr_R"], "betas": (0.5, 0.999)}])   # Tracker.py:324-329
+    rec = Recorder(); rec.install()
+    orig_render = renderer.render_batch_ray
+
+    def render(*a, **k):
+        out = orig_render(*a, **k)
+        rec.renders.append(dict(rays_d=a[2].detach().clone(), rays_o=a[3].detach().clone(),
+                                gt_depth=k["gt_depth"].detach().clone(), out=[o.detach().clone() for o in out]))
+        return out
+    renderer.render_batch_ray = render
+    try:
+        torch.manual_seed(3)
+        cam_pose = torch.cat([R, T], -1)
+        loss, punc = t.optimize_tracking(cam_pose, col.unsqueeze(0), dep.unsqueeze(0), case["pixels"], opt)
+    finally:
+        rec.uninstall()
+    out = {}
+    out["meta_H_W_fx_fy_cx_cy"] = np.array([H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"]], dtype=np.float64)
+    out["bound"] = _np(bound); out["truncation"] = np.array(t.truncation); out["edge"] = np.array(case["edge"])
+    out["n_stratified"] = np.array(cfg["rendering"]["n_stratified"]); out["n_importance"] = np.array(cfg["rendering"]["n_importance"])
+    out["log2_hash"] = np.array([cfg["grid"]["hash_size_sdf"], cfg["grid"]["hash_size_color"]])
+    out["per_level_scale"] = np.array([grids[0].spec.per_level_scale, grids[1].spec.per_level_scale])
+    out["variant"] = np.array("B" if cfg["grid"]["tcnn_network"] else "A")
+    out["color_img"] = _np(col); out["depth_img"] = _np(dep); out["cam_pose"] = _np(cam_pose0)
+    out["indices"] = _np([t_ for k, t_ in rec.draws if k == "randint"][-1])
+    out["t_rand"] = _np([t_ for k, t_ in rec.draws if k == "rand"][-1])
+    s = rec.samples[-1]
+    for nm, o in zip(("rays_o", "rays_d", "depth", "color"), s["out"]):
+        out["sample_out_" + nm] = _np(o)
+    r = rec.renders[-1]
+    out["render_rays_o"] = _np(r["rays_o"]); out["render_rays_d"] = _np(r["rays_d"]); out["render_gt_depth"] = _np(r["gt_depth"])
+    for nm, o in zip(("term", "pixel_unc", "depth", "rgb", "sdf", "z_vals", "depth_unc"), r["out"]):
+        out["ret_" + nm] = _np(o)
+    out["loss"] = np.array(loss); out["pixel_unc"] = _np(punc)
+    out["grad_T"] = _np(rec.steps[-1][0][0]); out["grad_R"] = _np(rec.steps[-1][1][0])
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "rays", r["gt_depth"].numel(), "loss", loss, "gradT", out["grad_T"], "gradR", out["grad_R"])
+
+
+def main():
+    _setup_paths()
+    torch.set_num_threads(8)
+    for name, case in CASES.items():
+        if name.startswith("map"):
+            gen_mapping(name, case)
+        else:
+            gen_tracking(name, case)
+
+
+if __name__ == "__main__":
+    main()

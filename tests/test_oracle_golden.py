@@ -1,0 +1,85 @@
+"""CPU: oracle/path_ref.py (the restatement) against fixtures produced by the UNMODIFIED reference
+(oracle/gen_golden.py). This is what pins the oracle for everything but the tcnn arithmetic."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import path_ref
+from helpers import DrawQueue, golden_field, load_golden, max_rel, rel_err
+
+T = torch.from_numpy
+
+
+def _draws(g):
+    d = [T(g["t_rand"])]
+    if "t_rand_uni" in g:
+        d += [T(g["t_rand_uni"]), T(g["u_pdf"])]
+    return DrawQueue(d)
+
+
+@pytest.mark.parametrize("name", ["map_replica_k1", "map_replica_k7", "map_scannet_k23"])
+def test_mapping_iteration_matches_reference(name):
+    g = load_golden(name)
+    field = golden_field(g, 0)
+    joint = int(g["joint_opt"]) == 1
+    c2ws = T(g["call0_c2ws"])
+    if joint:
+        cam_poses = T(g["cam_poses"]).clone().requires_grad_(True)
+        c2ws = torch.cat([c2ws[0:1], path_ref.cam_pose_to_matrix(cam_poses)], dim=0)
+        assert torch.equal(c2ws.detach(), T(g["call0_c2ws"]))
+    batches = []
+    for ci in range(int(g["n_sample_calls"])):
+        cw = c2ws if ci == 0 else c2ws[-10:]
+        batches.append((cw, T(g[f"call{ci}_depths"]), T(g[f"call{ci}_colors"]), T(g[f"call{ci}_rays_d_cam"]),
+                        T(g[f"call{ci}_indices"])))
+        o = path_ref.sample_mapping_rays(*batches[-1])
+        for nm, t in zip(("rays_o", "rays_d", "depth", "color"), o):
+            assert torch.equal(t.detach(), T(g[f"call{ci}_out_{nm}"])), nm       # bit-exact sampling
+    parts = {}
+    loss = path_ref.mapping_iteration(field, batches, float(g["truncation"]), int(g["n_stratified"]),
+                                      int(g["n_importance"]), _draws(g), parts=parts)
+    assert torch.equal(parts["rays_o"].detach(), T(g["render_rays_o"]))
+    assert torch.equal(parts["gt_depth"], T(g["render_gt_depth"]))
+    ret = parts["ret"]
+    assert torch.equal(ret[5], T(g["ret_z_vals"]))                               # z_vals bit-exact (incl. sample_pdf path)
+    for nm, t in zip(("term", "pixel_unc", "depth", "rgb", "sdf"), ret[:5]):
+        assert max_rel(t.detach(), g["ret_" + nm], 1e-4) < 1e-5, nm
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-6
+    loss.backward()
+    for k in g:
+        if k.startswith("grad_dec."):
+            nm = k[len("grad_dec."):]
+            got = field.beta.grad if nm == "beta" else field.w[nm].grad
+            assert rel_err(got, g[k]) < 1e-5, nm
+    for pre, tab, spec in (("grad_sdf_table", field.sdf_table, field.sdf_spec), ("grad_rgb_table", field.rgb_table, field.rgb_spec)):
+        gr = tab.grad.reshape(-1)
+        assert int((gr != 0).sum()) == int(g[pre + "_nnz"])
+        assert rel_err(gr[T(g[pre + "_idx"])], g[pre + "_val"]) < 1e-5
+        norms = [gr.double().reshape(-1, 2)[lv.offset:lv.offset + lv.size].norm().item() for lv in spec.levels]
+        np.testing.assert_allclose(norms, g[pre + "_level_norm"], rtol=1e-5)
+    if joint:
+        assert rel_err(cam_poses.grad, g["grad_cam_poses"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["track_replica", "track_scannet"])
+def test_tracking_iteration_matches_reference(name):
+    g = load_golden(name)
+    field = golden_field(g, 50, requires_grad=False)
+    H, W, fx, fy, cx, cy = [float(v) for v in g["meta_H_W_fx_fy_cx_cy"]]
+    H, W = int(H), int(W)
+    cam_pose = T(g["cam_pose"]).clone().requires_grad_(True)
+    e = int(g["edge"])
+    parts = {}
+    loss, punc = path_ref.tracking_iteration(field, cam_pose, T(g["depth_img"])[None], T(g["color_img"])[None],
+                                             H, W, fx, fy, cx, cy, e, e, T(g["indices"]), float(g["truncation"]),
+                                             int(g["n_stratified"]), int(g["n_importance"]), DrawQueue([T(g["t_rand"])]),
+                                             parts=parts)
+    assert torch.equal(parts["rays_o"].detach(), T(g["render_rays_o"]))
+    assert torch.equal(parts["rays_d"].detach(), T(g["render_rays_d"]))
+    assert torch.equal(parts["ret"][5], T(g["ret_z_vals"]))
+    for nm, t in zip(("term", "pixel_unc", "depth", "rgb", "sdf"), parts["ret"][:5]):
+        assert max_rel(t.detach(), g["ret_" + nm], 1e-4) < 1e-5, nm
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-6
+    loss.backward()
+    assert rel_err(cam_pose.grad[:, 4:], g["grad_T"]) < 1e-5
+    assert rel_err(cam_pose.grad[:, :4], g["grad_R"]) < 1e-5
