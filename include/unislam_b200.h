@@ -1,0 +1,248 @@
+/*
+ * unislam_b200.h -- C-ABI of the B200 (sm_100a) replacement for Uni-SLAM's per-frame
+ * differentiable-rendering hot path.
+ *
+ * The reference has no native code of its own: its operator API for this path is the Python
+ * surface of the tiny-cuda-nn torch binding plus a handful of PyTorch host functions.  Every
+ * entry point below cites the reference interface (file:line under the reference tree) it
+ * replaces.  The thin Python layer in uni-slam_b200/ (ctypes + torch.autograd.Function) is the
+ * only intended caller; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer except the usl_grid_t / usl_mlp_t / usl_field_t /
+ *     usl_points_t / usl_..._args_t structs is a DEVICE pointer; all float tensors are fp32, contiguous, row-major.
+ *   - the caller (PyTorch) owns every buffer; nothing is retained after the call returns.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden global
+ *     state, re-entrant, CUDA-graph capturable (no allocation, no synchronisation inside).
+ *   - return 0 on success, non-zero on error; usl_last_error() gives the message
+ *     (thread-local).  No C++ exception crosses the boundary.
+ *   - "accumulate" outputs (table / decoder / pose gradients) are atomically ADDED into the
+ *     caller's buffer, which the caller zero-fills (tcnn does the same memset).
+ */
+#ifndef UNISLAM_B200_H
+#define UNISLAM_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define USL_API __attribute__((visibility("default")))
+#else
+#define USL_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USL_MAX_LEVELS 16
+#define USL_FEATS 2       /* n_features_per_level, src/UNISLAM.py:226 */
+#define USL_IN 32         /* decoder input width  = 16 levels x 2 (model.c_dim) */
+#define USL_HID 16        /* decoder hidden width, src/networks/decoders.py:35 */
+#define USL_ACT_NONE 0
+#define USL_ACT_TANH 1
+#define USL_ACT_SIGMOID 2
+
+typedef void *usl_stream_t; /* cudaStream_t */
+
+/* One level of the multi-resolution hash grid (tcnn GridEncoding offsets table). */
+typedef struct usl_level {
+    float scale;     /* exp2f(l*log2f(per_level_scale))*base_resolution - 1 */
+    uint32_t res;    /* ceilf(scale)+1 */
+    uint32_t size;   /* entries in this level */
+    uint32_t offset; /* first entry of the level (in entries, x2 floats) */
+    uint32_t hashed; /* 1: CoherentPrime hash, 0: dense linear index */
+} usl_level_t;
+
+/* tcnn.Encoding(n_input_dims=3, {HashGrid, n_levels, 2, log2_hashmap_size, base_resolution,
+ * per_level_scale}, dtype=float) -- src/UNISLAM.py:242-253. Host struct, passed by pointer,
+ * copied by value into kernel arguments. */
+typedef struct usl_grid {
+    int32_t n_levels;
+    uint32_t total_entries;
+    usl_level_t levels[USL_MAX_LEVELS];
+} usl_grid_t;
+
+/* One decoder (src/networks/decoders.py:49-84). Device pointers, row-major (out,in) like
+ * nn.Linear.weight.  Variant A (tcnn_network False): n_hidden=2 with biases.  Variant B
+ * (tcnn.Network FullyFusedMLP restated in fp32): n_hidden=1, b*=NULL, wo = rows of the padded
+ * 16x16 output matrix.  The same struct with writable pointers receives gradients. */
+typedef struct usl_mlp {
+    float *w1, *b1; /* [16,32], [16] or NULL */
+    float *w2, *b2; /* [16,16], [16] or NULL; ignored when n_hidden == 1 */
+    float *wo, *bo; /* [n_out,16], [n_out] or NULL */
+    int32_t n_hidden; /* 1 or 2 */
+    int32_t n_out;    /* 1 (sdf) or 3 (rgb) */
+    int32_t out_act;  /* USL_ACT_* */
+    int32_t _pad;
+} usl_mlp_t;
+
+/* scene_rep + Decoders: (sdf grid, colour grid) and their two decoders, plus the scene bound
+ * (src/UNISLAM.py:205-222) used for point normalisation (src/utils/Renderer.py:136-137). */
+typedef struct usl_field {
+    usl_grid_t grid[2];      /* [0] sdf, [1] colour */
+    const float *table[2];   /* fp32 [total_entries*2] */
+    usl_mlp_t mlp[2];        /* [0] sdf decoder (n_out 1, tanh), [1] colour decoder (n_out 3, sigmoid) */
+    float bound_lo[3], bound_hi[3];
+} usl_field_t;
+
+/* scene bound after UNISLAM.load_bound (host struct) */
+typedef struct usl_bound {
+    float lo[3], hi[3];
+} usl_bound_t;
+
+USL_API const char *usl_last_error(void);
+USL_API int usl_version(void);
+
+/* tcnn GridEncoding constructor (offset table), run once on the host. */
+USL_API int usl_grid_build(int n_levels, int log2_hashmap_size, int base_resolution, double per_level_scale,
+                   usl_grid_t *out);
+
+/* ---- B1: tinycudann.Encoding.forward/backward (src/networks/decoders.py:101-103) ---------- */
+/* y[n,2L] = HashGrid(x[n,3]) */
+USL_API int usl_grid_encode_fwd(const usl_grid_t *g, const float *params, const float *x, int64_t n, float *y,
+                        usl_stream_t stream);
+/* grad_params[total*2] += scatter(w * dy)   (tcnn kernel_grid_backward) */
+USL_API int usl_grid_encode_bwd_params(const usl_grid_t *g, const float *x, const float *dy, int64_t n,
+                               float *grad_params, usl_stream_t stream);
+/* dx[n,3] = dy . d y/d x                    (tcnn kernel_grid_backward_input) */
+USL_API int usl_grid_encode_bwd_input(const usl_grid_t *g, const float *params, const float *x, const float *dy,
+                              int64_t n, float *dx, usl_stream_t stream);
+/* parity inspection: idx[n,L,8] = within-level entry index of every corner (bit-exact gate) */
+USL_API int usl_grid_corner_indices(const usl_grid_t *g, const float *x, int64_t n, uint32_t *idx,
+                            usl_stream_t stream);
+
+/* ---- B2: tinycudann.Network / nn.Linear decoder stacks (decoders.py:107-155) -------------- */
+USL_API int usl_mlp_fwd(const usl_mlp_t *m, const float *h, int64_t n, float *out, usl_stream_t stream);
+/* grads ADDED into gm->*; dh[n,32] may be NULL */
+USL_API int usl_mlp_bwd(const usl_mlp_t *m, const usl_mlp_t *gm, const float *h, const float *out,
+                const float *dout, int64_t n, float *dh, usl_stream_t stream);
+
+/* ---- B5: ray generation (src/common.py:95-180, 210-228) ----------------------------------- */
+/* get_samples_all: gather-then-rotate from K stored keyframe pixel subsets.
+ * c2ws[K,4,4], depths[K,P], colors[K,P,3], dirs_cam[K,P,3], indices[K*n] (int64 torch.randint draw)
+ * -> rays_o/rays_d[K*n,3], gt_depth[K*n], gt_color[K*n,3], dirs_out[K*n,3] (camera-frame dir kept for
+ * the pose gradient), frame_id[K*n] (int32, + frame_base). */
+USL_API int usl_sample_keyframe_rays(const float *c2ws, const float *depths, const float *colors,
+                             const float *dirs_cam, const int64_t *indices, int K, int64_t P, int n,
+                             int frame_base, float *rays_o, float *rays_d, float *gt_depth,
+                             float *gt_color, float *dirs_out, int32_t *frame_id, usl_stream_t stream);
+/* get_samples (tracker): indices[n] into the (H1-H0)x(W1-W0) window of one frame. */
+USL_API int usl_sample_window_rays(const float *c2w, const float *depth, const float *color, int H, int W,
+                           int H0, int H1, int W0, int W1, float fx, float fy, float cx, float cy,
+                           const int64_t *indices, int64_t n, float *rays_o, float *rays_d,
+                           float *gt_depth, float *gt_color, float *dirs_out, usl_stream_t stream);
+/* get_rays: all H*W rays of one camera. */
+USL_API int usl_image_rays(const float *c2w, int H, int W, float fx, float fy, float cx, float cy,
+                   float *rays_o, float *rays_d, usl_stream_t stream);
+
+/* ---- a-4: ray/bbox exit distance (Mapper.py:396-401, Tracker.py:177-183) ------------------- */
+/* t_exit[n]; valid[n] = t_exit >= gt_depth (&& gt_depth > 0 when require_depth) */
+USL_API int usl_bbox_prefilter(const float *rays_o, const float *rays_d, const float *gt_depth, int64_t n,
+                       const usl_bound_t *bound, int require_depth, float *t_exit, uint8_t *valid,
+                       usl_stream_t stream);
+
+/* ---- a-5/a-6: z sampling (src/utils/Renderer.py:42-57,77-130; common.py:49-85) ------------- */
+typedef struct usl_zsample_args {
+    int32_t n_stratified, n_importance;
+    float c_surf_lo;   /* (float)(1.5*truncation) */
+    float c_surf_span; /* (float)(3*truncation)   */
+    const float *t_uni;  /* torch.linspace(0,1,n_stratified) on device */
+    const float *t_surf; /* torch.linspace(0,1,n_importance) on device */
+} usl_zsample_args_t;
+/* rays with gt_depth>0: z[r,:] = perturb(sort(cat(free, surface))). t_rand row = row_map ? row_map[r] : r;
+ * t_rand NULL => perturb off. Rays with valid==0 or gt<=0 are left untouched. */
+USL_API int usl_zsample_depth(const usl_zsample_args_t *a, const float *gt_depth, const uint8_t *valid,
+                      const float *t_rand, const int32_t *row_map, int64_t n_rays, float *z,
+                      usl_stream_t stream);
+/* rays with gt_depth==0: uniform to bbox exit + importance resampling from an SDF-only query
+ * (the [-1,1]-then-clamp normalisation quirk kept). pdf_inds (nullable): searchsorted indices. */
+USL_API int usl_zsample_nodepth(const usl_zsample_args_t *a, const usl_field_t *f, const float *beta,
+                        const float *rays_o, const float *rays_d, const float *gt_depth,
+                        const uint8_t *valid, const float *t_rand_uni, const float *u_pdf,
+                        const int32_t *row_map, int64_t n_rays, float *z, int64_t *pdf_inds,
+                        usl_stream_t stream);
+
+/* ---- B3/B4: field query (Decoders.forward, decoders.py:182-205, with Renderer.py:132-139) -- */
+typedef struct usl_points {
+    const float *x;       /* [n,3] normalised coordinates (un-clamped), or NULL to build from rays */
+    const float *rays_o;  /* [R,3] */
+    const float *rays_d;  /* [R,3] */
+    const float *z;       /* [R,S] */
+    const uint8_t *valid; /* [R] or NULL */
+    int32_t S;
+    int64_t n;            /* number of points (= R*S when built from rays) */
+} usl_points_t;
+/* raw[n,4] = (r,g,b,sdf). feat (nullable): [2][L][n][2] interpolated features kept for the
+ * decoder weight gradient. jac (nullable): [n,12] d raw / d x (rows r,g,b,sdf; clamp-gated). */
+USL_API int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac,
+                  usl_stream_t stream);
+/* d_raw[n,4] -> table gradients (scatter), decoder gradients (gm[2], may be NULL to skip). */
+USL_API int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw, const float *feat,
+                  const float *d_raw, float *grad_table_sdf, float *grad_table_rgb,
+                  const usl_mlp_t *gm, usl_stream_t stream);
+/* SDF channel only, forward only (Renderer.py:121, Mesher.py:134-166). out_of_bound_value used
+ * when mask_bound!=0 and the un-normalised point lies outside the open bound. */
+USL_API int usl_field_sdf(const usl_field_t *f, const usl_points_t *p, float *sdf, usl_stream_t stream);
+
+/* ---- a-8: SDF->weight compositing (Renderer.py:140-158), one warp per ray ------------------ */
+/* outputs: term[R], pixel_unc[R], depth[R], rgb[R,3], depth_unc[R]; weights (nullable) [R,S] */
+USL_API int usl_composite_fwd(const float *raw, const float *z, const float *beta, const uint8_t *valid,
+                      int64_t R, int S, float *term, float *pixel_unc, float *depth, float *rgb,
+                      float *depth_unc, float *weights, usl_stream_t stream);
+/* upstream grads (each nullable = zero): g_term[R], g_punc[R], g_depth[R], g_rgb[R,3], g_dunc[R],
+ * g_sdf[R,S].  Outputs: d_raw[R,S,4]; d_beta[1] (ADDED); and, when jac!=NULL, d_rays_o/d_rays_d[R,3]
+ * = sum_s (d_raw . jac) chained through the normalisation (extent = hi-lo). */
+USL_API int usl_composite_bwd(const float *raw, const float *z, const float *beta, const uint8_t *valid,
+                      int64_t R, int S, const float *g_term, const float *g_punc, const float *g_depth,
+                      const float *g_rgb, const float *g_dunc, const float *g_sdf, const float *jac,
+                      const usl_bound_t *bound, float *d_raw, float *d_beta, float *d_rays_o,
+                      float *d_rays_d, usl_stream_t stream);
+
+/* ---- a-9: masks + losses (Mapper.py:141-175,412-430; Tracker.py:113-147,208-228) ----------- */
+typedef struct usl_loss_args {
+    float truncation;
+    float truncation_center; /* (float)(0.4*truncation), product taken in double by the caller (Mapper.py:160-161) */
+    float w_sdf_fs, w_sdf_center, w_sdf_tail, w_depth, w_color;
+    int32_t mode;      /* 0 mapping ('original'), 1 tracking ('original': 10x-median mask, masked colour) */
+} usl_loss_args_t;
+#define USL_LOSS_SLOTS 16
+/* acc[USL_LOSS_SLOTS] (zeroed by caller; ADDED): 0 fs_sum 1 center_sum 2 tail_sum 3 depth_sum 4 color_sum
+ * 5 n_front 6 n_center 7 n_tail 8 n_mask 9 n_rays(valid) 10 n_color_terms 11 sum_pixel_unc.
+ * tracking mode reads median[0] (device) for the depth-error mask. mask_out[R] (nullable). */
+USL_API int usl_loss_fwd(const usl_loss_args_t *a, const float *raw, const float *z, const float *gt_depth,
+                 const float *gt_color, const uint8_t *valid, const float *pixel_unc, const float *depth,
+                 const float *rgb, const float *median, int64_t R, int S, float *acc, uint8_t *mask_out,
+                 usl_stream_t stream);
+/* loss[0] = weighted sum of means from acc (NaN when a mask is empty, as torch.mean of empty) */
+USL_API int usl_loss_finalize(const usl_loss_args_t *a, const float *acc, float *loss, usl_stream_t stream);
+/* upstream gradients of the loss wrt the render outputs, scaled by g_loss[0] (device, NULL = 1):
+ * g_depth[R], g_rgb[R,3], g_sdf[R,S]. */
+USL_API int usl_loss_bwd(const usl_loss_args_t *a, const float *raw, const float *z, const float *gt_depth,
+                 const float *gt_color, const uint8_t *valid, const uint8_t *mask, const float *depth,
+                 const float *rgb, const float *acc, const float *g_loss, int64_t R, int S,
+                 float *g_depth, float *g_rgb, float *g_sdf, usl_stream_t stream);
+/* torch.median (lower middle) of |gt - depth| over valid rays: median[0]. workspace: >= R floats. */
+USL_API int usl_depth_error_median(const float *gt_depth, const float *depth, const uint8_t *valid, int64_t R,
+                           float *workspace, float *median, usl_stream_t stream);
+
+/* ---- a-10: pose gradient (common.py:196-208 cam_pose_to_matrix; pytorch3d quaternion_to_matrix) */
+/* d_c2w[K,12] (3x4 row-major, ADDED) from per-ray d_rays_o / d_rays_d and the camera-frame dirs. */
+USL_API int usl_pose_reduce(const float *d_rays_o, const float *d_rays_d, const float *dirs_cam,
+                    const int32_t *frame_id, const uint8_t *valid, int64_t n, int K, float *d_c2w,
+                    usl_stream_t stream);
+/* pose[K,7]=[qw,qx,qy,qz,tx,ty,tz] -> c2w[K,16] */
+USL_API int usl_pose_to_matrix(const float *pose, int K, float *c2w, usl_stream_t stream);
+/* d_pose[K,7] = chain of d_c2w[K,12] through quaternion_to_matrix (un-normalised quaternion). */
+USL_API int usl_pose_matrix_bwd(const float *pose, const float *d_c2w, int K, float *d_pose, usl_stream_t stream);
+
+/* ---- a-11: dense SDF query for meshing (src/utils/Mesher.py:134-195) ----------------------- */
+/* points generated in-kernel from the per-axis coordinate arrays ax/ay/az (np.linspace -> fp32),
+ * ordering of torch.meshgrid(indexing='xy') flattened: idx = (iy*nx + ix)*nz + iz for iy in
+ * [y_begin,y_end). SDF = -1 outside the open bound. out[(y_end-y_begin)*nx*nz]. */
+USL_API int usl_sdf_query_grid(const usl_field_t *f, const float *ax, const float *ay, const float *az, int nx,
+                       int ny, int nz, int y_begin, int y_end, float *out, usl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNISLAM_B200_H */

@@ -1,0 +1,254 @@
+"""-m gpu parity tests: the CUDA path (through the C-ABI) against the oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star): hash / sample indices bit-exact; rendered depth / colour and losses
+<= 1e-4 relative (fp32); parameter and pose gradients <= 1e-3 relative.
+"""
+import copy
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import grid_ref, path_ref
+from helpers import DrawQueue, golden_field, load_golden, max_rel, pkg, rel_err
+import gpu_cases
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+DEV = "cuda:0"
+
+GRIDS = {"replica_sdf": (16, 816), "replica_rgb": (19, 816), "scannet": (16, 456)}
+
+
+def _points(n, spec, seed=0):
+    """Random points plus the edge cases the index math must survive: 0, 1, cell boundaries."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, 3, generator=g)
+    x[0] = 0.0; x[1] = 1.0; x[2] = torch.tensor([0.0, 1.0, 0.5])
+    for i, lv in enumerate(spec.levels):          # x = (k - 0.5)/scale sits exactly on a cell boundary
+        x[3 + i] = torch.tensor([(3 - 0.5) / lv.scale, (5 - 0.5) / lv.scale, (7 - 0.5) / lv.scale]).clamp(0, 1)
+    return x
+
+
+@pytest.mark.parametrize("name", list(GRIDS))
+def test_grid_indices_bit_exact_and_features(name):
+    P = pkg()
+    log2T, res = GRIDS[name]
+    pls = grid_ref.per_level_scale_from_resolution(res)
+    spec = grid_ref.make_grid_spec(log2T, pls)
+    enc = P.Encoding(3, {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": log2T,
+                         "base_resolution": 16, "per_level_scale": pls}, dtype=torch.float).to(DEV)
+    assert [(round(a[0], 6), a[1], a[2], a[3], a[4]) for a in enc.level_table()] == \
+           [(round(l.scale, 6), l.res, l.size, l.offset, l.hashed) for l in spec.levels]
+    params = grid_ref.lcg_params(spec.n_params, 0.05, 3)
+    with torch.no_grad():
+        enc.params.copy_(T(params))
+    x = _points(20000, spec)
+    idx_ref, _ = grid_ref.c_corners(spec, x.numpy())
+    idx = P.ops.grid_corner_indices(x.to(DEV), enc.grid).cpu().numpy()
+    assert np.array_equal(idx.astype(np.uint32), idx_ref)                       # bit-exact hash / table indices
+    y_ref = grid_ref.c_encode_fwd(spec, params, x.numpy())
+    y = enc(x.to(DEV)).detach().cpu().numpy()
+    assert np.abs(y - y_ref).max() <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["replica_sdf", "scannet"])
+def test_grid_backward(name):
+    P = pkg()
+    log2T, res = GRIDS[name]
+    pls = grid_ref.per_level_scale_from_resolution(res)
+    spec = grid_ref.make_grid_spec(log2T, pls)
+    enc = P.Encoding(3, {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": log2T,
+                         "base_resolution": 16, "per_level_scale": pls}, dtype=torch.float).to(DEV)
+    params = grid_ref.lcg_params(spec.n_params, 0.05, 4)
+    with torch.no_grad():
+        enc.params.copy_(T(params))
+    x = _points(8192, spec, 1)
+    dy = torch.randn(8192, 32, generator=torch.Generator().manual_seed(2))
+    xg = x.to(DEV).requires_grad_(True)
+    y = enc(xg)
+    y.backward(dy.to(DEV))
+    gp_ref = grid_ref.c_encode_bwd_params(spec, x.numpy(), dy.numpy())            # fp64 accumulation
+    gp = enc.params.grad.cpu().double().numpy()
+    assert np.linalg.norm(gp - gp_ref) / np.linalg.norm(gp_ref) < 1e-5
+    touched = gp_ref != 0
+    assert np.array_equal(gp != 0, touched) or (np.abs(gp[~touched]).max() == 0)
+    assert (np.abs(gp - gp_ref)[touched] / np.maximum(np.abs(gp_ref[touched]), 1e-3)).max() < 1e-3
+    gx_ref = grid_ref.c_encode_bwd_input(spec, params, x.numpy(), dy.numpy())
+    gx = xg.grad.cpu().numpy()
+    assert np.linalg.norm(gx - gx_ref) / np.linalg.norm(gx_ref) < 1e-4
+
+
+def test_grid_properties_full_size():
+    """Size-independent properties at a BASELINE-sized batch (240k points, Replica colour grid)."""
+    P = pkg()
+    pls = grid_ref.per_level_scale_from_resolution(816)
+    enc = P.Encoding(3, {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 19,
+                         "base_resolution": 16, "per_level_scale": pls}, dtype=torch.float).to(DEV)
+    n = 6000 * 40
+    x = torch.rand(n, 3, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0))
+    with torch.no_grad():
+        enc.params.fill_(0.25)                      # constant table -> constant output (partition of unity)
+    y = enc(x)
+    assert (y - 0.25).abs().max() < 1e-6
+    dy = torch.randn(n, 32, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    enc.params.grad = None
+    y.backward(dy)
+    g = enc.params.grad.view(-1, 2).double()
+    # weights of the 8 corners sum to 1 => per level, sum of scattered gradient == sum of dy
+    off = 0
+    for l, (_, _, size, offset, _) in enumerate(enc.level_table()):
+        got = g[offset:offset + size].sum(0)
+        want = dy[:, 2 * l:2 * l + 2].double().sum(0)
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-2), l
+    # linearity: encode(a*T1 + b*T2) == a*encode(T1) + b*encode(T2)
+    t1 = torch.randn_like(enc.params) * 0.05; t2 = torch.randn_like(enc.params) * 0.05
+    with torch.no_grad():
+        enc.params.copy_(t1); y1 = enc(x[:50000]).clone()
+        enc.params.copy_(t2); y2 = enc(x[:50000]).clone()
+        enc.params.copy_(0.5 * t1 - 2.0 * t2); y3 = enc(x[:50000])
+    assert (y3 - (0.5 * y1 - 2.0 * y2)).abs().max() < 1e-5
+
+
+def test_encoding_module_contract():
+    """B1 seam: flat leaf Parameter, deepcopy (Tracker.py:105-108), pickle (mp.spawn, UNISLAM.py:295-298), empty batch."""
+    P = pkg()
+    enc = P.Encoding(3, {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 16,
+                         "base_resolution": 16, "per_level_scale": 1.3}, dtype=torch.float).to(DEV)
+    assert enc.params.is_leaf and enc.params.dim() == 1 and enc.n_output_dims == 32
+    assert float(enc.params.abs().max()) <= 1e-4
+    x = torch.rand(1000, 3, device=DEV)
+    y = enc(x)
+    e2 = copy.deepcopy(enc)
+    e3 = pickle.loads(pickle.dumps(enc))
+    assert torch.equal(e2(x), y) and torch.equal(e3(x), y)
+    assert enc(torch.empty(0, 3, device=DEV)).shape == (0, 32)
+    with pytest.raises(RuntimeError):
+        enc(torch.rand(4, 3))                        # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_network_matches_torch(variant):
+    P = pkg()
+    n = 5000
+    g = torch.Generator().manual_seed(0)
+    h = torch.randn(n, 32, generator=g)
+    if variant == "B":
+        for n_out, act, tact in ((1, "Tanh", torch.tanh), (3, "Sigmoid", torch.sigmoid)):
+            net = P.Network(32, n_out, {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": act,
+                                        "n_neurons": 16, "n_hidden_layers": 1}).to(DEV)
+            hp = h.to(DEV).requires_grad_(True)
+            out = net(hp)
+            dout = torch.randn(n, n_out, generator=g)
+            out.backward(dout.to(DEV))
+            p = net.params.detach().cpu().double().requires_grad_(True)
+            hr = h.double().requires_grad_(True)
+            ref = path_ref.mlp_B(hr, p, n_out, tact)
+            ref.backward(dout.double())
+            assert (out.detach().cpu().double() - ref.detach()).abs().max() < 1e-5      # O(1) activations: absolute fp32 noise
+            assert rel_err(net.params.grad.cpu(), p.grad) < 1e-4
+            assert rel_err(hp.grad.cpu(), hr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["map_replica_k1", "map_replica_k7", "map_scannet_k23"])
+def test_mapping_step_matches_reference(name):
+    r = gpu_cases.run_mapping_case(name, DEV)
+    print(name, r)
+    assert r["rays_o_mismatch"] == 0 and r["rays_d_mismatch"] == 0 and r["valid_mismatch"] == 0
+    assert r["z_depth_mismatch"] == 0                                  # sample positions bit-exact
+    assert r["z_hole_maxabs"] < 1e-4
+    for k in ("term_rel", "pixel_unc_rel", "depth_rel", "rgb_rel", "loss_rel"):
+        assert r[k] < 1e-4, (k, r[k])
+    for k in ("dec_grad_rel", "beta_grad_rel", "table_grad_rel", "pose_grad_rel"):
+        assert r[k] < 1e-3, (k, r[k])
+    for pre in ("grad_sdf_table", "grad_rgb_table"):
+        assert r[pre + "_support_miss"] == 0 and r[pre + "_nnz_excess"] == 0, pre
+
+
+@pytest.mark.parametrize("name", ["track_replica", "track_scannet"])
+def test_tracking_step_matches_reference(name):
+    r = gpu_cases.run_tracking_case(name, DEV)
+    print(name, r)
+    assert r["rays_o_mismatch"] == 0 and r["rays_d_mismatch"] == 0 and r["valid_mismatch"] == 0 and r["z_mismatch"] == 0
+    for k in ("term_rel", "pixel_unc_rel", "depth_rel", "rgb_rel", "loss_rel"):
+        assert r[k] < 1e-4, (k, r[k])
+    assert r["mean_punc_err"] < 1e-3
+    assert r["grad_T_rel"] < 1e-3 and r["grad_R_rel"] < 1e-3
+
+
+@pytest.mark.parametrize("name", ["map_replica_k7", "map_scannet_k23"])
+def test_dropin_renderer_matches_reference(name, monkeypatch):
+    """B3/B4 seams: modules.Decoders + modules.Renderer.render_batch_ray fed the reference's own draws,
+    with the loss assembled by the oracle's restatement of the host code (torch ops on CUDA)."""
+    P = pkg()
+    g = load_golden(name)
+    variant = str(g["variant"])
+    cfg = {"grid_mode": "hash_grid", "grid": {"tcnn_network": variant == "B"}, "scale": 1,
+           "rendering": {"perturb": True, "n_stratified": int(g["n_stratified"]), "n_importance": int(g["n_importance"])}}
+    meta, tabs, dec, beta = gpu_cases.cuda_field(g, 0, DEV)
+    encs = []
+    for i in range(2):
+        e = P.Encoding(3, {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": int(g["log2_hash"][i]),
+                           "base_resolution": 16, "per_level_scale": float(g["per_level_scale"][i])}, dtype=torch.float).to(DEV)
+        with torch.no_grad():
+            e.params.copy_(tabs[i])
+        encs.append(e)
+    decoders = P.Decoders(cfg, c_dim=32, truncation=float(g["truncation"]), learnable_beta=True).to(DEV)
+    with torch.no_grad():
+        for t, src in zip(decoders.decoder_tensors(), dec):
+            t.copy_(src)
+    H, W, fx, fy, cx, cy = [float(v) for v in g["meta_H_W_fx_fy_cx_cy"]]
+    fake = type("U", (), dict(bound=T(g["bound"]), device=DEV, H=int(H), W=int(W), fx=fx, fy=fy, cx=cx, cy=cy))()
+    renderer = P.Renderer(cfg, fake)
+    draws = [T(g["t_rand"]).to(DEV)]
+    if "t_rand_uni" in g:
+        draws += [T(g["t_rand_uni"]).to(DEV), T(g["u_pdf"]).to(DEV)]
+    q = DrawQueue(draws)
+    monkeypatch.setattr(torch, "rand", lambda shape, device=None, **k: q(tuple(shape)))
+    rays_o = T(g["render_rays_o"]).to(DEV).requires_grad_(True)
+    rays_d = T(g["render_rays_d"]).to(DEV).requires_grad_(True)
+    gt_depth = T(g["render_gt_depth"]).to(DEV)
+    scene_rep = ([encs[0]], [encs[1]])
+    ret = renderer.render_batch_ray(scene_rep, decoders, rays_d, rays_o, DEV, float(g["truncation"]), gt_depth=gt_depth)
+    monkeypatch.undo()
+    for nm, t in zip(("term", "pixel_unc", "depth", "rgb", "sdf"), ret[:5]):
+        assert max_rel(t.detach().cpu(), g["ret_" + nm], 1e-3 if nm != "sdf" else 1e-2) < 1e-4, nm
+    has = gt_depth.cpu() > 0
+    assert torch.equal(ret[5].cpu()[has], T(g["ret_z_vals"])[has])
+    # the reference's own loss code (restated) on top of our outputs, then autograd through our backward
+    gt_color = torch.cat([T(g[f"call{ci}_out_color"]) for ci in range(int(g["n_sample_calls"]))])
+    ro_all = torch.cat([T(g[f"call{ci}_out_rays_o"]) for ci in range(int(g["n_sample_calls"]))])
+    rd_all = torch.cat([T(g[f"call{ci}_out_rays_d"]) for ci in range(int(g["n_sample_calls"]))])
+    d_all = torch.cat([T(g[f"call{ci}_out_depth"]) for ci in range(int(g["n_sample_calls"]))])
+    inside = path_ref.bbox_exit(ro_all, rd_all, T(g["bound"])) >= d_all
+    loss = path_ref.mapping_loss(ret, gt_depth, gt_color[inside].to(DEV), float(g["truncation"]))
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-4
+    loss.backward()
+    names = gpu_cases.DEC_ORDER[variant]
+    for nm, t in zip(names, decoders.decoder_tensors()):
+        assert rel_err(t.grad.cpu(), g["grad_dec." + nm]) < 1e-3, nm
+    assert rel_err(decoders.beta.grad.cpu(), g["grad_dec.beta"]) < 1e-3
+    for pre, e in (("grad_sdf_table", encs[0]), ("grad_rgb_table", encs[1])):
+        assert rel_err(e.params.grad.cpu()[T(g[pre + "_idx"])], g[pre + "_val"]) < 1e-3
+    assert rays_o.grad is not None and torch.isfinite(rays_o.grad).all() and torch.isfinite(rays_d.grad).all()
+
+
+def test_dense_sdf_query_matches_oracle():
+    """a-11: in-kernel point generation + SDF-only field query vs the oracle's eval_points, slab-wise."""
+    P = pkg()
+    g = load_golden("map_replica_k7")
+    meta, tabs, dec, beta = gpu_cases.cuda_field(g, 0, DEV)
+    field = golden_field(g, 0, requires_grad=False)
+    mc_bound = [[-1.0, 7.0], [-1.3, 3.7], [-1.7, 1.4]]
+    axes = path_ref.mesh_grid_axes(mc_bound, resolution=0.25)            # coarse grid: seconds on the CPU oracle
+    pts = path_ref.mesh_grid_points(axes)
+    with torch.no_grad():
+        ref = path_ref.eval_points_sdf(field, pts)
+    q = P.DenseSdfQuery(meta, tabs[0], tabs[1], dec, [a.to(DEV) for a in axes])
+    ny = q.ny
+    parts = [q.run(0, ny // 3), q.run(ny // 3, ny)]                      # two slabs == one full query
+    out = torch.cat(parts).cpu()
+    assert out.shape == ref.shape
+    assert torch.equal(out == -1, ref == -1)                              # strict in-bound mask identical
+    assert (out - ref).abs().max() < 2e-5

@@ -1,0 +1,176 @@
+// Stand-alone multi-resolution hash-grid encoding kernels: the tinycudann.Encoding seam (B1).
+// Replaces tcnn kernel_grid / kernel_grid_backward / kernel_grid_backward_input as used at
+// src/networks/decoders.py:101-103 and by loss.backward() (src/Mapper.py:444, src/Tracker.py:241).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "usl_device.cuh"
+
+namespace usl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+// thread per (point, level): blockIdx.y = level keeps a block inside one level's table.
+__global__ void __launch_bounds__(256) encode_fwd_kernel(usl_grid_t g, const float2 *__restrict__ table,
+                                                         const float *__restrict__ x, int64_t n,
+                                                         float2 *__restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = blockIdx.y;
+    const float x0 = x[i * 3 + 0], x1 = x[i * 3 + 1], x2 = x[i * 3 + 2];
+    float2 f, df[3];
+    level_interp<false>(g.levels[l], table, x0, x1, x2, f, df);
+    y[i * g.n_levels + l] = f;
+}
+
+__global__ void __launch_bounds__(256) encode_bwd_params_kernel(usl_grid_t g, const float *__restrict__ x,
+                                                                const float2 *__restrict__ dy, int64_t n,
+                                                                float2 *__restrict__ grad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = blockIdx.y;
+    const usl_level_t &lv = g.levels[l];
+    const Cell c = make_cell(lv, x[i * 3 + 0], x[i * 3 + 1], x[i * 3 + 2]);
+    uint32_t idx[8];
+    float wt[8];
+    corner_indices(lv, c, idx);
+    corner_weights(c, wt);
+    const float2 d = dy[i * g.n_levels + l];
+    float2 *tab = grad + lv.offset;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(tab + idx[k], make_float2(wt[k] * d.x, wt[k] * d.y));
+}
+
+__global__ void __launch_bounds__(256) encode_bwd_input_kernel(usl_grid_t g, const float2 *__restrict__ table,
+                                                               const float *__restrict__ x,
+                                                               const float2 *__restrict__ dy, int64_t n,
+                                                               float *__restrict__ dx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x0 = x[i * 3 + 0], x1 = x[i * 3 + 1], x2 = x[i * 3 + 2];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int l = 0; l < g.n_levels; ++l) {
+        float2 f, df[3];
+        level_interp<true>(g.levels[l], table, x0, x1, x2, f, df);
+        const float2 d = dy[i * g.n_levels + l];
+        a0 += d.x * df[0].x + d.y * df[0].y;
+        a1 += d.x * df[1].x + d.y * df[1].y;
+        a2 += d.x * df[2].x + d.y * df[2].y;
+    }
+    dx[i * 3 + 0] = a0; dx[i * 3 + 1] = a1; dx[i * 3 + 2] = a2;
+}
+
+__global__ void __launch_bounds__(256) corner_indices_kernel(usl_grid_t g, const float *__restrict__ x, int64_t n,
+                                                             uint32_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = blockIdx.y;
+    const Cell c = make_cell(g.levels[l], x[i * 3 + 0], x[i * 3 + 1], x[i * 3 + 2]);
+    uint32_t idx[8];
+    corner_indices(g.levels[l], c, idx);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[(i * g.n_levels + l) * 8 + k] = idx[k];
+}
+
+static int check_grid(const usl_grid_t *g) {
+    if (!g || g->n_levels <= 0 || g->n_levels > USL_MAX_LEVELS) {
+        set_error("invalid usl_grid_t (n_levels out of range)");
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace usl
+
+using namespace usl;
+
+extern "C" {
+
+const char *usl_last_error(void) { return g_err; }
+int usl_version(void) { return 100; }
+
+// tcnn GridEncoding constructor arithmetic, host libm in fp32.
+int usl_grid_build(int n_levels, int log2_hashmap_size, int base_resolution, double per_level_scale,
+                   usl_grid_t *out) {
+    if (!out || n_levels <= 0 || n_levels > USL_MAX_LEVELS || log2_hashmap_size < 3 || log2_hashmap_size > 30) {
+        set_error("usl_grid_build: bad arguments");
+        return 1;
+    }
+    memset(out, 0, sizeof(*out));
+    const float log2_pls = log2f((float)per_level_scale);
+    uint32_t offset = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        const float scale = exp2f((float)l * log2_pls) * (float)base_resolution - 1.0f;
+        const uint32_t res = (uint32_t)ceilf(scale) + 1u;
+        const double dense = (double)res * res * res;
+        const uint32_t max_params = 0xFFFFFFFFu / 2u;
+        uint32_t cnt = dense > (double)max_params ? max_params : (uint32_t)dense;
+        cnt = (cnt + 7u) / 8u * 8u;
+        const uint32_t cap = 1u << log2_hashmap_size;
+        if (cnt > cap) cnt = cap;
+        out->levels[l].scale = scale;
+        out->levels[l].res = res;
+        out->levels[l].size = cnt;
+        out->levels[l].offset = offset;
+        out->levels[l].hashed = dense > (double)cnt ? 1u : 0u;
+        offset += cnt;
+    }
+    out->n_levels = n_levels;
+    out->total_entries = offset;
+    return 0;
+}
+
+int usl_grid_encode_fwd(const usl_grid_t *g, const float *params, const float *x, int64_t n, float *y,
+                        usl_stream_t stream) {
+    if (check_grid(g)) return 1;
+    if (n <= 0) return 0;
+    dim3 grid((unsigned)((n + 255) / 256), g->n_levels);
+    encode_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*g, (const float2 *)params, x, n, (float2 *)y);
+    return check_launch("usl_grid_encode_fwd");
+}
+
+int usl_grid_encode_bwd_params(const usl_grid_t *g, const float *x, const float *dy, int64_t n,
+                               float *grad_params, usl_stream_t stream) {
+    if (check_grid(g)) return 1;
+    if (n <= 0) return 0;
+    dim3 grid((unsigned)((n + 255) / 256), g->n_levels);
+    encode_bwd_params_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*g, x, (const float2 *)dy, n, (float2 *)grad_params);
+    return check_launch("usl_grid_encode_bwd_params");
+}
+
+int usl_grid_encode_bwd_input(const usl_grid_t *g, const float *params, const float *x, const float *dy,
+                              int64_t n, float *dx, usl_stream_t stream) {
+    if (check_grid(g)) return 1;
+    if (n <= 0) return 0;
+    encode_bwd_input_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        *g, (const float2 *)params, x, (const float2 *)dy, n, dx);
+    return check_launch("usl_grid_encode_bwd_input");
+}
+
+int usl_grid_corner_indices(const usl_grid_t *g, const float *x, int64_t n, uint32_t *idx, usl_stream_t stream) {
+    if (check_grid(g)) return 1;
+    if (n <= 0) return 0;
+    dim3 grid((unsigned)((n + 255) / 256), g->n_levels);
+    corner_indices_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*g, x, n, idx);
+    return check_launch("usl_grid_corner_indices");
+}
+
+}  // extern "C"

@@ -1,0 +1,516 @@
+// Fused field query: clamp -> hash-grid gather (16 levels) -> decoder MLP -> activation, per point,
+// and its backward (decoder weight gradients + hash-table gradient scatter).
+// Replaces Decoders.forward / get_raw_sdf / get_raw_rgb (src/networks/decoders.py:91-205), i.e. two
+// tcnn.Encoding calls + two tcnn.Network / nn.Linear stacks, together with the point construction
+// and normalisation of src/utils/Renderer.py:132-137.  blockIdx.y selects the grid (0 sdf, 1 colour)
+// so each thread carries one decoder's registers and the two grids run as independent CTAs.
+#include <cstring>
+
+#include "usl_field.cuh"
+
+namespace usl {
+
+struct FieldArgs {
+    usl_field_t f;
+    usl_points_t p;
+    float *raw;   // [n,4]
+    float *feat;  // [2][L][n][2]
+    float *jac;   // [n,12]
+    float *sdf;   // [n]   (sdf-only mode)
+};
+
+// Loads point i: clamped normalised coordinate xc, clamp gate (1 inside [0,1], else 0).
+__device__ __forceinline__ bool load_point(const usl_points_t &p, const usl_field_t &f, int64_t i, float xc[3],
+                                           float gate[3]) {
+    float x[3];
+    if (p.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x[d] = p.x[i * 3 + d];
+    } else {
+        const int64_t r = i / p.S;
+        if (p.valid && !p.valid[r]) return false;
+        const float z = p.z[i];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x[d] = norm_coord(p.rays_o[r * 3 + d], p.rays_d[r * 3 + d], z, f.bound_lo[d], f.bound_hi[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        xc[d] = fminf(fmaxf(x[d], 0.f), 1.f);                  // torch.clamp(p_nor, 0, 1), decoders.py:101
+        gate[d] = (x[d] >= 0.f && x[d] <= 1.f) ? 1.f : 0.f;   // clamp backward passes grad on the closed interval
+    }
+    return true;
+}
+
+template <bool WITH_JAC, bool SAVE_FEAT>
+__global__ void __launch_bounds__(256) field_fwd_kernel(const __grid_constant__ FieldArgs A) {
+    __shared__ MlpSmem sm;
+    const int gi = blockIdx.y;
+    stage_mlp(A.f.mlp[gi], sm);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.p.n) return;
+    float xc[3], gate[3];
+    if (!load_point(A.p, A.f, i, xc, gate)) return;
+    const usl_grid_t &g = A.f.grid[gi];
+    float out[4], tout[4][3];
+    float2 *fo = SAVE_FEAT ? reinterpret_cast<float2 *>(A.feat) + ((int64_t)gi * g.n_levels) * A.p.n + i : nullptr;
+    decode_point<WITH_JAC, SAVE_FEAT>(g, reinterpret_cast<const float2 *>(A.f.table[gi]), A.f.mlp[gi], sm, xc, fo,
+                                      A.p.n, out, tout);
+    if (gi == 0) {
+        A.raw[i * 4 + 3] = out[0];
+        if (WITH_JAC) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) A.jac[i * 12 + 9 + d] = tout[0][d] * gate[d];
+        }
+    } else {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            A.raw[i * 4 + o] = out[o];
+            if (WITH_JAC) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) A.jac[i * 12 + o * 3 + d] = tout[o][d] * gate[d];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) field_sdf_kernel(const __grid_constant__ FieldArgs A) {
+    __shared__ MlpSmem sm;
+    stage_mlp(A.f.mlp[0], sm);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.p.n) return;
+    float xc[3], gate[3];
+    if (!load_point(A.p, A.f, i, xc, gate)) return;
+    float out[4], tout[4][3];
+    decode_point<false, false>(A.f.grid[0], reinterpret_cast<const float2 *>(A.f.table[0]), A.f.mlp[0], sm, xc,
+                               nullptr, 0, out, tout);
+    A.sdf[i] = out[0];
+}
+
+// ---- dense SDF query for meshing (Mesher.get_grid_uniform + eval_points, Mesher.py:134-195) ----
+struct QueryArgs {
+    usl_field_t f;
+    const float *ax, *ay, *az;
+    int nx, ny, nz, y_begin, y_end;
+    float *out;
+};
+
+__global__ void __launch_bounds__(256) sdf_query_grid_kernel(const __grid_constant__ QueryArgs A) {
+    __shared__ MlpSmem sm;
+    stage_mlp(A.f.mlp[0], sm);
+    __syncthreads();
+    const int64_t total = (int64_t)(A.y_end - A.y_begin) * A.nx * A.nz;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int iz = (int)(i % A.nz);
+        const int64_t t = i / A.nz;
+        const int ix = (int)(t % A.nx);
+        const int iy = (int)(t / A.nx) + A.y_begin;
+        const float p[3] = {A.ax[ix], A.ay[iy], A.az[iz]};
+        bool inside = true;
+        float xc[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            inside = inside && (p[d] < A.f.bound_hi[d]) && (p[d] > A.f.bound_lo[d]);   // strict, Mesher.py:151-154
+            const float x = __fdiv_rn(__fsub_rn(p[d], A.f.bound_lo[d]), __fsub_rn(A.f.bound_hi[d], A.f.bound_lo[d]));
+            xc[d] = fminf(fmaxf(x, 0.f), 1.f);
+        }
+        float v = -1.0f;                                                                // Mesher.py:162
+        if (inside) {
+            float out[4], tout[4][3];
+            decode_point<false, false>(A.f.grid[0], reinterpret_cast<const float2 *>(A.f.table[0]), A.f.mlp[0], sm,
+                                       xc, nullptr, 0, out, tout);
+            v = out[0];
+        }
+        __stcs(A.out + i, v);
+    }
+}
+
+// ---- backward ---------------------------------------------------------------------------------
+#define BWD_THREADS 128
+#define BWD_WARPS (BWD_THREADS / 32)
+#define TILE_STRIDE 52   // floats per point row: 16B-aligned rows, conflict-free 128-bit stores
+
+struct FieldBwdArgs {
+    usl_field_t f;
+    usl_points_t p;
+    const float *raw;     // [n,4] saved outputs
+    const float *feat;    // [2][L][n][2]
+    const float *d_raw;   // [n,4]
+    float *grad_table[2];
+    usl_mlp_t gm[2];
+    int has_gm;
+    float *dh;            // stand-alone decoder mode: [n,32] gradient wrt the input features (nullable)
+};
+
+// STANDALONE: tinycudann.Network seam -- feat is h[n,32] (row-major), raw/d_raw are [n,n_out], no scatter.
+template <int NH, bool STANDALONE>
+__global__ void __launch_bounds__(BWD_THREADS) field_bwd_kernel(const __grid_constant__ FieldBwdArgs A) {
+    __shared__ MlpSmem sm;
+    __shared__ __align__(16) float tiles[BWD_WARPS][32][TILE_STRIDE];
+    const int gi = blockIdx.y;
+    const usl_mlp_t &m = A.f.mlp[gi];
+    stage_mlp(m, sm);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float(*tile)[TILE_STRIDE] = tiles[warp];
+    const usl_grid_t &g = A.f.grid[gi];
+    const int L = g.n_levels;
+    const int64_t n = A.p.n;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+    float xc[3] = {0.f, 0.f, 0.f}, gate[3];
+    bool active = (i < n);
+    if (!STANDALONE) active = active && load_point(A.p, A.f, i, xc, gate);
+
+    // ---- recompute the decoder forward from the saved features ----
+    float f[USL_IN];
+    float h1[USL_HID];
+#pragma unroll
+    for (int j = 0; j < USL_HID; ++j) h1[j] = sm.b1[j];
+    const float2 *fin = STANDALONE ? reinterpret_cast<const float2 *>(A.feat) + (active ? i : 0) * (USL_IN / 2)
+                                   : reinterpret_cast<const float2 *>(A.feat) + ((int64_t)gi * L) * n + (active ? i : 0);
+    const int64_t fstride = STANDALONE ? 1 : n;
+#pragma unroll
+    for (int l = 0; l < USL_IN / 2; ++l) {
+        float2 v = make_float2(0.f, 0.f);
+        if (active && l < L) v = __ldg(fin + (int64_t)l * fstride);
+        f[2 * l] = v.x; f[2 * l + 1] = v.y;
+    }
+#pragma unroll
+    for (int k = 0; k < USL_IN; ++k) {
+        const float4 *w = reinterpret_cast<const float4 *>(sm.w1t[k]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 a = w[q];
+            h1[q * 4 + 0] = fmaf(a.x, f[k], h1[q * 4 + 0]);
+            h1[q * 4 + 1] = fmaf(a.y, f[k], h1[q * 4 + 1]);
+            h1[q * 4 + 2] = fmaf(a.z, f[k], h1[q * 4 + 2]);
+            h1[q * 4 + 3] = fmaf(a.w, f[k], h1[q * 4 + 3]);
+        }
+    }
+    // output-side gradient
+    float du[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+        if (STANDALONE) {
+            for (int o = 0; o < m.n_out; ++o) du[o] = A.d_raw[i * m.n_out + o] * act_bwd(m.out_act, A.raw[i * m.n_out + o]);
+        } else if (gi == 0) {
+            du[0] = A.d_raw[i * 4 + 3] * act_bwd(m.out_act, A.raw[i * 4 + 3]);
+        } else {
+#pragma unroll
+            for (int o = 0; o < 3; ++o) du[o] = A.d_raw[i * 4 + o] * act_bwd(m.out_act, A.raw[i * 4 + o]);
+        }
+    }
+    float dh1[USL_HID];
+    float a2[USL_HID], dh2[USL_HID];
+    if (NH == 2) {
+#pragma unroll
+        for (int j = 0; j < USL_HID; ++j) dh1[j] = 0.f;
+#pragma unroll
+        for (int q = 0; q < USL_HID; ++q) {
+            float s = sm.b2[q];
+#pragma unroll
+            for (int j = 0; j < USL_HID; ++j) s = fmaf(sm.w2[q][j], fmaxf(h1[j], 0.f), s);
+            float d = 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) d = fmaf(sm.wo[o][q], du[o], d);
+            d = (s > 0.f) ? d : 0.f;
+            a2[q] = fmaxf(s, 0.f);
+            dh2[q] = d;
+#pragma unroll
+            for (int j = 0; j < USL_HID; ++j) dh1[j] = fmaf(sm.w2[q][j], d, dh1[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < USL_HID; ++j) dh1[j] = (h1[j] > 0.f) ? dh1[j] : 0.f;
+    } else {
+#pragma unroll
+        for (int j = 0; j < USL_HID; ++j) {
+            float d = 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) d = fmaf(sm.wo[o][j], du[o], d);
+            dh1[j] = (h1[j] > 0.f) ? d : 0.f;
+        }
+    }
+
+    // ---- decoder weight gradients: warp-private tile, each lane owns a patch of every matrix ----
+    float acc1[16], acc2[8], acco[2], accb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc1[q] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc2[q] = 0.f;
+    acco[0] = acco[1] = 0.f;
+    if (A.has_gm) {
+        float4 *row = reinterpret_cast<float4 *>(tile[lane]);
+        // phase 1: [0:16] dh1, [16:48] f
+#pragma unroll
+        for (int q = 0; q < 4; ++q) row[q] = make_float4(dh1[4 * q], dh1[4 * q + 1], dh1[4 * q + 2], dh1[4 * q + 3]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) row[4 + q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        __syncwarp();
+        {
+            const int j = lane >> 1, k0 = (lane & 1) * 16;
+            for (int p = 0; p < 32; ++p) {
+                const float d = tile[p][j];
+                const float4 *fr = reinterpret_cast<const float4 *>(&tile[p][16 + k0]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = fr[q];
+                    acc1[4 * q + 0] = fmaf(d, v.x, acc1[4 * q + 0]);
+                    acc1[4 * q + 1] = fmaf(d, v.y, acc1[4 * q + 1]);
+                    acc1[4 * q + 2] = fmaf(d, v.z, acc1[4 * q + 2]);
+                    acc1[4 * q + 3] = fmaf(d, v.w, acc1[4 * q + 3]);
+                }
+                if (lane < 16) accb[0] += tile[p][lane];
+            }
+        }
+        __syncwarp();
+        // phase 2: [0:16] dh2, [16:32] a1, [32:36] du, [36:52] a_last
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            row[q] = (NH == 2) ? make_float4(dh2[4 * q], dh2[4 * q + 1], dh2[4 * q + 2], dh2[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a1v = make_float4(fmaxf(h1[4 * q], 0.f), fmaxf(h1[4 * q + 1], 0.f), fmaxf(h1[4 * q + 2], 0.f), fmaxf(h1[4 * q + 3], 0.f));
+            row[4 + q] = a1v;
+            row[9 + q] = (NH == 2) ? make_float4(a2[4 * q], a2[4 * q + 1], a2[4 * q + 2], a2[4 * q + 3]) : a1v;
+        }
+        row[8] = make_float4(du[0], du[1], du[2], du[3]);
+        __syncwarp();
+        {
+            const int r2 = lane >> 1, j0 = (lane & 1) * 8;
+            const int o = lane >> 3, i0 = (lane & 7) * 2;
+            for (int p = 0; p < 32; ++p) {
+                if (NH == 2) {
+                    const float d = tile[p][r2];
+                    const float4 *ar = reinterpret_cast<const float4 *>(&tile[p][16 + j0]);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float4 v = ar[q];
+                        acc2[4 * q + 0] = fmaf(d, v.x, acc2[4 * q + 0]);
+                        acc2[4 * q + 1] = fmaf(d, v.y, acc2[4 * q + 1]);
+                        acc2[4 * q + 2] = fmaf(d, v.z, acc2[4 * q + 2]);
+                        acc2[4 * q + 3] = fmaf(d, v.w, acc2[4 * q + 3]);
+                    }
+                    if (lane < 16) accb[1] += tile[p][lane];
+                }
+                const float duo = tile[p][32 + o];
+                const float2 al = *reinterpret_cast<const float2 *>(&tile[p][36 + i0]);
+                acco[0] = fmaf(duo, al.x, acco[0]);
+                acco[1] = fmaf(duo, al.y, acco[1]);
+                if (lane < 4) accb[2] += tile[p][32 + lane];
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- hash-table gradient scatter: d f_l = W1[:, 2l:2l+2]^T dh1, then 8 vector atomics ----
+    if (STANDALONE ? (active && A.dh != nullptr) : (active && A.grad_table[gi] != nullptr)) {
+        float2 *gt = STANDALONE ? nullptr : reinterpret_cast<float2 *>(A.grad_table[gi]);
+        for (int l = 0; l < L; ++l) {
+            float dfx = 0.f, dfy = 0.f;
+            const float4 *wa = reinterpret_cast<const float4 *>(sm.w1t[2 * l]);
+            const float4 *wb = reinterpret_cast<const float4 *>(sm.w1t[2 * l + 1]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 a = wa[q], b = wb[q];
+                dfx = fmaf(a.x, dh1[4 * q], dfx); dfx = fmaf(a.y, dh1[4 * q + 1], dfx);
+                dfx = fmaf(a.z, dh1[4 * q + 2], dfx); dfx = fmaf(a.w, dh1[4 * q + 3], dfx);
+                dfy = fmaf(b.x, dh1[4 * q], dfy); dfy = fmaf(b.y, dh1[4 * q + 1], dfy);
+                dfy = fmaf(b.z, dh1[4 * q + 2], dfy); dfy = fmaf(b.w, dh1[4 * q + 3], dfy);
+            }
+            if (STANDALONE) {
+                reinterpret_cast<float2 *>(A.dh)[i * (USL_IN / 2) + l] = make_float2(dfx, dfy);
+                continue;
+            }
+            const usl_level_t &lv = g.levels[l];
+            const Cell c = make_cell(lv, xc[0], xc[1], xc[2]);
+            uint32_t idx[8];
+            float wt[8];
+            corner_indices(lv, c, idx);
+            corner_weights(c, wt);
+            float2 *tab = gt + lv.offset;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(tab + idx[k], make_float2(wt[k] * dfx, wt[k] * dfy));
+        }
+    }
+
+    // ---- block reduction of the decoder gradients, one atomic per element per CTA ----
+    if (A.has_gm) {
+        __syncthreads();
+        float *red = &tiles[0][0][0];               // reuse: [BWD_WARPS][32][32] floats needed (<= tile storage)
+        float *mine = red + (warp * 32 + lane) * 32;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) mine[q] = acc1[q];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) mine[16 + q] = acc2[q];
+        mine[24] = acco[0]; mine[25] = acco[1];
+        mine[26] = accb[0]; mine[27] = accb[1]; mine[28] = accb[2];
+        __syncthreads();
+        const usl_mlp_t &gm = A.gm[gi];
+        for (int e = threadIdx.x; e < 32 * 29; e += blockDim.x) {
+            const int ln = e / 29, q = e % 29;
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < BWD_WARPS; ++w) s += red[(w * 32 + ln) * 32 + q];
+            if (q < 16) {                                   // dW1[j][k0+q]
+                const int j = ln >> 1, k = (ln & 1) * 16 + q;
+                if (gm.w1) atomicAdd(gm.w1 + j * USL_IN + k, s);
+            } else if (q < 24) {                            // dW2[i][j0+q]
+                if (NH == 2 && gm.w2) atomicAdd(gm.w2 + (ln >> 1) * USL_HID + (ln & 1) * 8 + (q - 16), s);
+            } else if (q < 26) {                            // dWo[o][i0+q]
+                const int o = ln >> 3, ii = (ln & 7) * 2 + (q - 24);
+                if (o < m.n_out && gm.wo) atomicAdd(gm.wo + o * USL_HID + ii, s);
+            } else if (q == 26) {
+                if (ln < 16 && gm.b1) atomicAdd(gm.b1 + ln, s);
+            } else if (q == 27) {
+                if (NH == 2 && ln < 16 && gm.b2) atomicAdd(gm.b2 + ln, s);
+            } else {
+                if (ln < m.n_out && gm.bo) atomicAdd(gm.bo + ln, s);
+            }
+        }
+    }
+}
+
+// ---- stand-alone decoder (tinycudann.Network / nn.Linear stacks on given features) -------------
+__global__ void __launch_bounds__(256) mlp_fwd_kernel(usl_mlp_t m, const float *__restrict__ h, int64_t n,
+                                                      float *__restrict__ out) {
+    __shared__ MlpSmem sm;
+    stage_mlp(m, sm);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a1[USL_HID];
+#pragma unroll
+    for (int j = 0; j < USL_HID; ++j) a1[j] = sm.b1[j];
+    const float4 *hin = reinterpret_cast<const float4 *>(h + i * USL_IN);
+#pragma unroll
+    for (int q = 0; q < USL_IN / 4; ++q) {
+        const float4 v = __ldg(hin + q);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int j = 0; j < USL_HID; ++j) a1[j] = fmaf(sm.w1t[q * 4 + e][j], vv[e], a1[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < USL_HID; ++j) a1[j] = fmaxf(a1[j], 0.f);
+    float u[4] = {sm.bo[0], sm.bo[1], sm.bo[2], sm.bo[3]};
+    if (m.n_hidden == 2) {
+        for (int q = 0; q < USL_HID; ++q) {
+            float s = sm.b2[q];
+#pragma unroll
+            for (int j = 0; j < USL_HID; ++j) s = fmaf(sm.w2[q][j], a1[j], s);
+            s = fmaxf(s, 0.f);
+#pragma unroll
+            for (int o = 0; o < 4; ++o) u[o] = fmaf(sm.wo[o][q], s, u[o]);
+        }
+    } else {
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int j = 0; j < USL_HID; ++j) u[o] = fmaf(sm.wo[o][j], a1[j], u[o]);
+    }
+    for (int o = 0; o < m.n_out; ++o) out[i * m.n_out + o] = act_fwd(m.out_act, u[o]);
+}
+
+static int check_field(const usl_field_t *f, const usl_points_t *p) {
+    if (!f || !p) { set_error("null field/points"); return 1; }
+    for (int gi = 0; gi < 2; ++gi) {
+        if (f->grid[gi].n_levels != USL_IN / USL_FEATS) { set_error("field grids must have 16 levels x 2 features"); return 1; }
+        if (f->mlp[gi].n_hidden < 1 || f->mlp[gi].n_hidden > 2 || f->mlp[gi].n_out < 1 || f->mlp[gi].n_out > 3) {
+            set_error("unsupported decoder shape"); return 1;
+        }
+    }
+    if (!p->x && (!p->rays_o || !p->rays_d || !p->z || p->S <= 0)) { set_error("points: need x or (rays_o, rays_d, z, S)"); return 1; }
+    return 0;
+}
+
+}  // namespace usl
+
+using namespace usl;
+
+extern "C" {
+
+int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac,
+                  usl_stream_t stream) {
+    if (check_field(f, p)) return 1;
+    if (p->n <= 0) return 0;
+    FieldArgs A;
+    A.f = *f; A.p = *p; A.raw = raw; A.feat = feat; A.jac = jac; A.sdf = nullptr;
+    dim3 grid((unsigned)((p->n + 255) / 256), 2);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (jac && feat) field_fwd_kernel<true, true><<<grid, 256, 0, s>>>(A);
+    else if (jac) field_fwd_kernel<true, false><<<grid, 256, 0, s>>>(A);
+    else if (feat) field_fwd_kernel<false, true><<<grid, 256, 0, s>>>(A);
+    else field_fwd_kernel<false, false><<<grid, 256, 0, s>>>(A);
+    return check_launch("usl_field_fwd");
+}
+
+int usl_field_sdf(const usl_field_t *f, const usl_points_t *p, float *sdf, usl_stream_t stream) {
+    if (check_field(f, p)) return 1;
+    if (p->n <= 0) return 0;
+    FieldArgs A;
+    A.f = *f; A.p = *p; A.raw = nullptr; A.feat = nullptr; A.jac = nullptr; A.sdf = sdf;
+    field_sdf_kernel<<<(unsigned)((p->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A);
+    return check_launch("usl_field_sdf");
+}
+
+int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw, const float *feat,
+                  const float *d_raw, float *grad_table_sdf, float *grad_table_rgb, const usl_mlp_t *gm,
+                  usl_stream_t stream) {
+    if (check_field(f, p)) return 1;
+    if (p->n <= 0) return 0;
+    if (!feat || !raw || !d_raw) { set_error("usl_field_bwd: raw, feat and d_raw are required"); return 1; }
+    if (f->mlp[0].n_hidden != f->mlp[1].n_hidden) { set_error("usl_field_bwd: decoders must share n_hidden"); return 1; }
+    FieldBwdArgs A;
+    A.f = *f; A.p = *p; A.raw = raw; A.feat = feat; A.d_raw = d_raw;
+    A.grad_table[0] = grad_table_sdf; A.grad_table[1] = grad_table_rgb;
+    A.has_gm = gm ? 1 : 0;
+    A.dh = nullptr;
+    if (gm) { A.gm[0] = gm[0]; A.gm[1] = gm[1]; }
+    dim3 grid((unsigned)((p->n + BWD_THREADS - 1) / BWD_THREADS), 2);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (f->mlp[0].n_hidden == 2) field_bwd_kernel<2, false><<<grid, BWD_THREADS, 0, s>>>(A);
+    else field_bwd_kernel<1, false><<<grid, BWD_THREADS, 0, s>>>(A);
+    return check_launch("usl_field_bwd");
+}
+
+int usl_mlp_bwd(const usl_mlp_t *m, const usl_mlp_t *gm, const float *h, const float *out, const float *dout,
+                int64_t n, float *dh, usl_stream_t stream) {
+    if (!m || m->n_hidden < 1 || m->n_hidden > 2 || m->n_out < 1 || m->n_out > 3) { set_error("usl_mlp_bwd: unsupported decoder shape"); return 1; }
+    if (n <= 0) return 0;
+    FieldBwdArgs A;
+    memset(&A, 0, sizeof(A));
+    A.f.mlp[0] = *m;
+    A.f.grid[0].n_levels = USL_IN / USL_FEATS;
+    A.p.n = n;
+    A.raw = out; A.feat = h; A.d_raw = dout; A.dh = dh;
+    A.has_gm = gm ? 1 : 0;
+    if (gm) A.gm[0] = *gm;
+    dim3 grid((unsigned)((n + BWD_THREADS - 1) / BWD_THREADS), 1);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (m->n_hidden == 2) field_bwd_kernel<2, true><<<grid, BWD_THREADS, 0, s>>>(A);
+    else field_bwd_kernel<1, true><<<grid, BWD_THREADS, 0, s>>>(A);
+    return check_launch("usl_mlp_bwd");
+}
+
+int usl_mlp_fwd(const usl_mlp_t *m, const float *h, int64_t n, float *out, usl_stream_t stream) {
+    if (!m || m->n_hidden < 1 || m->n_hidden > 2 || m->n_out < 1 || m->n_out > 3) { set_error("usl_mlp_fwd: unsupported decoder shape"); return 1; }
+    if (n <= 0) return 0;
+    mlp_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*m, h, n, out);
+    return check_launch("usl_mlp_fwd");
+}
+
+int usl_sdf_query_grid(const usl_field_t *f, const float *ax, const float *ay, const float *az, int nx, int ny,
+                       int nz, int y_begin, int y_end, float *out, usl_stream_t stream) {
+    if (!f || y_begin < 0 || y_end > ny || y_end < y_begin) { set_error("usl_sdf_query_grid: bad arguments"); return 1; }
+    const int64_t total = (int64_t)(y_end - y_begin) * nx * nz;
+    if (total <= 0) return 0;
+    QueryArgs A;
+    A.f = *f; A.ax = ax; A.ay = ay; A.az = az; A.nx = nx; A.ny = ny; A.nz = nz; A.y_begin = y_begin; A.y_end = y_end; A.out = out;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = 148 * 64;
+    if (blocks > cap) blocks = cap;
+    sdf_query_grid_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A);
+    return check_launch("usl_sdf_query_grid");
+}
+
+}  // extern "C"

@@ -1,0 +1,349 @@
+// Ray generation, ray/bbox prefilter and z sampling.
+// Replaces get_samples / get_samples_all / get_rays (src/common.py:95-180,210-228), the bbox prefilter
+// (src/Mapper.py:396-401, src/Tracker.py:177-183), Renderer.perturbation + the depth-guided sampling
+// (src/utils/Renderer.py:42-57,77-101) and the no-depth importance branch (Renderer.py:103-130 with
+// common.sample_pdf, common.py:49-85).  RNG draws (torch.randint / torch.rand) are made by the host
+// code exactly as in the reference and passed in as tensors.
+#include "usl_field.cuh"
+
+namespace usl {
+
+// rays_d[a] = sum_b dir[b] * R[a][b]   (torch.sum(dirs[...,None,:] * c2w[:3,:3], -1), common.py:103,161)
+// summed left to right like a sequential reduction over the length-3 axis.
+__device__ __forceinline__ float rot_row(const float *__restrict__ c2w, int a, float d0, float d1, float d2) {
+    const float p0 = __fmul_rn(d0, c2w[a * 4 + 0]);
+    const float p1 = __fmul_rn(d1, c2w[a * 4 + 1]);
+    const float p2 = __fmul_rn(d2, c2w[a * 4 + 2]);
+    return __fadd_rn(__fadd_rn(p0, p1), p2);
+}
+
+__global__ void __launch_bounds__(256) sample_keyframe_rays_kernel(
+    const float *__restrict__ c2ws, const float *__restrict__ depths, const float *__restrict__ colors,
+    const float *__restrict__ dirs_cam, const int64_t *__restrict__ indices, int K, int64_t P, int n, int frame_base,
+    float *__restrict__ rays_o, float *__restrict__ rays_d, float *__restrict__ gt_depth, float *__restrict__ gt_color,
+    float *__restrict__ dirs_out, int32_t *__restrict__ frame_id) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= (int64_t)K * n) return;
+    const int k = (int)(m / n);
+    const int64_t src = (int64_t)k * P + indices[m];
+    const float *c2w = c2ws + (int64_t)k * 16;
+    const float d0 = dirs_cam[src * 3 + 0], d1 = dirs_cam[src * 3 + 1], d2 = dirs_cam[src * 3 + 2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        rays_d[m * 3 + a] = rot_row(c2w, a, d0, d1, d2);
+        rays_o[m * 3 + a] = c2w[a * 4 + 3];
+        gt_color[m * 3 + a] = colors[src * 3 + a];
+    }
+    gt_depth[m] = depths[src];
+    if (dirs_out) { dirs_out[m * 3 + 0] = d0; dirs_out[m * 3 + 1] = d1; dirs_out[m * 3 + 2] = d2; }
+    if (frame_id) frame_id[m] = frame_base + k;
+}
+
+// camera-frame direction of pixel (i,j): ((i-cx)/fx, -(j-cy)/fy, -1)  (common.py:100)
+__device__ __forceinline__ void pixel_dir(float i, float j, float fx, float fy, float cx, float cy, float d[3]) {
+    d[0] = __fdiv_rn(__fsub_rn(i, cx), fx);
+    d[1] = -__fdiv_rn(__fsub_rn(j, cy), fy);
+    d[2] = -1.0f;
+}
+
+__global__ void __launch_bounds__(256) sample_window_rays_kernel(
+    const float *__restrict__ c2w, const float *__restrict__ depth, const float *__restrict__ color, int H, int W,
+    int H0, int H1, int W0, int W1, float fx, float fy, float cx, float cy, const int64_t *__restrict__ indices,
+    int64_t n, float *__restrict__ rays_o, float *__restrict__ rays_d, float *__restrict__ gt_depth,
+    float *__restrict__ gt_color, float *__restrict__ dirs_out) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const int64_t idx = indices[m];
+    const int Wc = W1 - W0;
+    const int pi = (int)(idx % Wc) + W0, pj = (int)(idx / Wc) + H0;
+    float d[3];
+    pixel_dir((float)pi, (float)pj, fx, fy, cx, cy, d);
+    const int64_t src = (int64_t)pj * W + pi;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        rays_d[m * 3 + a] = rot_row(c2w, a, d[0], d[1], d[2]);
+        rays_o[m * 3 + a] = c2w[a * 4 + 3];
+        gt_color[m * 3 + a] = color[src * 3 + a];
+        if (dirs_out) dirs_out[m * 3 + a] = d[a];
+    }
+    gt_depth[m] = depth[src];
+}
+
+__global__ void __launch_bounds__(256) image_rays_kernel(const float *__restrict__ c2w, int H, int W, float fx, float fy,
+                                                         float cx, float cy, float *__restrict__ rays_o,
+                                                         float *__restrict__ rays_d) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= (int64_t)H * W) return;
+    float d[3];
+    pixel_dir((float)(m % W), (float)(m / W), fx, fy, cx, cy, d);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        rays_d[m * 3 + a] = rot_row(c2w, a, d[0], d[1], d[2]);
+        rays_o[m * 3 + a] = c2w[a * 4 + 3];
+    }
+}
+
+// t_exit = min_d max((lo_d - o_d)/d_d, (hi_d - o_d)/d_d)
+__device__ __forceinline__ float bbox_exit(const float o[3], const float d[3], const usl_bound_t &b) {
+    float t = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float t0 = __fdiv_rn(__fsub_rn(b.lo[a], o[a]), d[a]);
+        const float t1 = __fdiv_rn(__fsub_rn(b.hi[a], o[a]), d[a]);
+        // torch.max / torch.min propagate NaN (0/0 when a ray is parallel to and on a face)
+        float m = fmaxf(t0, t1);
+        if (t0 != t0 || t1 != t1) m = NAN;
+        t = (m != m || t != t) ? NAN : fminf(t, m);
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(256) bbox_prefilter_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                                                             const float *__restrict__ gt_depth, int64_t n, usl_bound_t b,
+                                                             int require_depth, float *__restrict__ t_exit,
+                                                             uint8_t *__restrict__ valid) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const float o[3] = {rays_o[m * 3], rays_o[m * 3 + 1], rays_o[m * 3 + 2]};
+    const float d[3] = {rays_d[m * 3], rays_d[m * 3 + 1], rays_d[m * 3 + 2]};
+    const float t = bbox_exit(o, d, b);
+    if (t_exit) t_exit[m] = t;
+    if (valid) {
+        const float g = gt_depth[m];
+        bool v = t >= g;
+        if (require_depth) v = v && (g > 0.f);
+        valid[m] = v ? 1 : 0;
+    }
+}
+
+// ---- depth-guided z sampling: thread per ray, two-pointer merge of two ascending sequences ----
+__global__ void __launch_bounds__(128) zsample_depth_kernel(usl_zsample_args_t a, const float *__restrict__ gt_depth,
+                                                            const uint8_t *__restrict__ valid,
+                                                            const float *__restrict__ t_rand,
+                                                            const int32_t *__restrict__ row_map, int64_t n_rays,
+                                                            float *__restrict__ z) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    if (valid && !valid[r]) return;
+    const float gt = gt_depth[r];
+    if (!(gt > 0.f)) return;
+    const int ns = a.n_stratified, ni = a.n_importance, S = ns + ni;
+    float *zr = z + r * S;
+    // z_free_i = 0.0 + (1.2*gt)*t_uni[i] ; z_surf_j = (gt - 1.5tr) + (3tr * t_surf[j])     (Renderer.py:91-95)
+    const float g12 = __fmul_rn(1.2f, gt);
+    const float s0 = __fsub_rn(gt, a.c_surf_lo);
+    int i = 0, j = 0;
+    float fi = __fadd_rn(0.0f, __fmul_rn(g12, a.t_uni[0]));
+    float sj = __fadd_rn(s0, __fmul_rn(a.c_surf_span, a.t_surf[0]));
+    for (int k = 0; k < S; ++k) {
+        const bool take_free = (j >= ni) || (i < ns && fi <= sj);
+        if (take_free) {
+            zr[k] = fi; ++i;
+            if (i < ns) fi = __fadd_rn(0.0f, __fmul_rn(g12, a.t_uni[i]));
+        } else {
+            zr[k] = sj; ++j;
+            if (j < ni) sj = __fadd_rn(s0, __fmul_rn(a.c_surf_span, a.t_surf[j]));
+        }
+    }
+    if (t_rand) {   // Renderer.perturbation (Renderer.py:42-57), in place with the original neighbours in registers
+        const float *tr = t_rand + (int64_t)(row_map ? row_map[r] : r) * S;
+        float prev = 0.f, cur = zr[0];
+        for (int k = 0; k < S; ++k) {
+            const float next = (k + 1 < S) ? zr[k + 1] : cur;
+            const float lower = (k == 0) ? cur : __fmul_rn(0.5f, __fadd_rn(cur, prev));
+            const float upper = (k == S - 1) ? cur : __fmul_rn(0.5f, __fadd_rn(next, cur));
+            zr[k] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr[k]));
+            prev = cur; cur = next;
+        }
+    }
+}
+
+// ---- no-depth rays: uniform samples to the bbox exit + inverse-CDF resampling from an SDF query ----
+#define ND_MAX_STRAT 64
+#define ND_MAX_IMP 32
+struct NoDepthArgs {
+    usl_zsample_args_t a;
+    usl_field_t f;
+    const float *beta, *rays_o, *rays_d, *gt_depth, *t_rand_uni, *u_pdf;
+    const uint8_t *valid;
+    const int32_t *row_map;
+    int64_t n_rays;
+    float *z;
+    int64_t *pdf_inds;
+};
+
+__global__ void __launch_bounds__(128) zsample_nodepth_kernel(const __grid_constant__ NoDepthArgs A) {
+    __shared__ MlpSmem sm;
+    __shared__ float s_z[4][ND_MAX_STRAT], s_w[4][ND_MAX_STRAT], s_cdf[4][ND_MAX_STRAT], s_smp[4][ND_MAX_IMP];
+    stage_mlp(A.f.mlp[0], sm);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * 4 + warp;
+    if (r >= A.n_rays) return;
+    if (A.valid && !A.valid[r]) return;
+    if (A.gt_depth[r] > 0.f) return;                      // handled by zsample_depth (gt_mask, Renderer.py:83)
+    const int ns = A.a.n_stratified, ni = A.a.n_importance, S = ns + ni;
+    const int row = A.row_map ? A.row_map[r] : (int)r;
+    float *zs = s_z[warp], *ws = s_w[warp], *cdf = s_cdf[warp], *smp = s_smp[warp];
+    const float o[3] = {A.rays_o[r * 3], A.rays_o[r * 3 + 1], A.rays_o[r * 3 + 2]};
+    const float d[3] = {A.rays_d[r * 3], A.rays_d[r * 3 + 1], A.rays_d[r * 3 + 2]};
+    usl_bound_t b;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { b.lo[q] = A.f.bound_lo[q]; b.hi[q] = A.f.bound_hi[q]; }
+    const float far_bb = __fadd_rn(bbox_exit(o, d, b), 0.01f);                       // Renderer.py:110-113
+    const float beta = A.beta[0];
+    // z_uni = near*(1-t) + far*t with near = 0.0                                      (Renderer.py:115)
+    for (int k = lane; k < ns; k += 32) {
+        const float t = A.a.t_uni[k];
+        zs[k] = __fadd_rn(__fmul_rn(0.0f, __fsub_rn(1.0f, t)), __fmul_rn(far_bb, t));
+    }
+    __syncwarp();
+    if (A.t_rand_uni) {
+        float pert[(ND_MAX_STRAT + 31) / 32];
+        int q = 0;
+        for (int k = lane; k < ns; k += 32, ++q) {
+            const float cur = zs[k];
+            const float lower = (k == 0) ? cur : __fmul_rn(0.5f, __fadd_rn(cur, zs[k - 1]));
+            const float upper = (k == ns - 1) ? cur : __fmul_rn(0.5f, __fadd_rn(zs[k + 1], cur));
+            pert[q] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), A.t_rand_uni[(int64_t)row * ns + k]));
+        }
+        __syncwarp();
+        q = 0;
+        for (int k = lane; k < ns; k += 32, ++q) zs[k] = pert[q];
+        __syncwarp();
+    }
+    // SDF query at coords normalised to [-1,1] then clamped to [0,1] (Renderer.py:120, common.py:231-245, decoders.py:101)
+    for (int k = lane; k < ns; k += 32) {
+        float xc[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float p = __fadd_rn(o[q], __fmul_rn(d[q], zs[k]));
+            const float xn = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(p, b.lo[q]), __fsub_rn(b.hi[q], b.lo[q])), 2.0f), 1.0f);
+            xc[q] = fminf(fmaxf(xn, 0.f), 1.f);
+        }
+        float out[4], tout[4][3];
+        decode_point<false, false>(A.f.grid[0], reinterpret_cast<const float2 *>(A.f.table[0]), A.f.mlp[0], sm, xc,
+                                   nullptr, 0, out, tout);
+        const float sg = 1.0f / (1.0f + expf(out[0] * beta));                        // sigmoid(-sdf*beta)
+        ws[k] = 1.0f - expf(-beta * sg);                                             // alpha (Renderer.py:154-158)
+    }
+    __syncwarp();
+    // weights = alpha * exclusive cumprod(1 - alpha + 1e-10); cdf = [0, cumsum(weights[1:-1])] -- sequential like torch
+    if (lane == 0) {
+        float T = 1.0f;
+        for (int k = 0; k < ns; ++k) {
+            const float al = ws[k];
+            ws[k] = __fmul_rn(al, T);
+            T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, al), 1e-10f));
+        }
+        float c = 0.f;
+        cdf[0] = 0.f;
+        for (int k = 1; k <= ns - 2; ++k) { c = __fadd_rn(c, ws[k]); cdf[k] = c; }
+    }
+    __syncwarp();
+    const int ncdf = ns - 1;                                  // == number of bins (z_mid)
+    for (int q = lane; q < ni; q += 32) {
+        const float u = A.u_pdf[(int64_t)row * ni + q];
+        int lo = 0, hi = ncdf;                               // searchsorted(cdf, u, right=True): #elements <= u
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+        const int inds = lo;
+        if (A.pdf_inds) A.pdf_inds[(int64_t)row * ni + q] = inds;
+        const int below = max(inds - 1, 0), above = min(ncdf - 1, inds);
+        float denom = __fsub_rn(cdf[above], cdf[below]);
+        if (denom < 1e-5f) denom = 1.0f;
+        const float t = __fdiv_rn(__fsub_rn(u, cdf[below]), denom);
+        const float bb = __fmul_rn(0.5f, __fadd_rn(zs[below + 1], zs[below]));
+        const float ba = __fmul_rn(0.5f, __fadd_rn(zs[above + 1], zs[above]));
+        smp[q] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+    }
+    __syncwarp();
+    // sort(cat(z_uni, samples)): rank every element among both lists (ties: z_uni first, then by index)
+    float *zr = A.z + r * S;
+    for (int k = lane; k < S; k += 32) {
+        const bool from_uni = k < ns;
+        const float v = from_uni ? zs[k] : smp[k - ns];
+        int rank = 0;
+        for (int q = 0; q < ns; ++q) {
+            const float w = zs[q];
+            rank += (w < v) || (w == v && (!from_uni || q < k));
+        }
+        for (int q = 0; q < ni; ++q) {
+            const float w = smp[q];
+            rank += (w < v) || (w == v && !from_uni && q < k - ns);
+        }
+        zr[rank] = v;
+    }
+}
+
+}  // namespace usl
+
+using namespace usl;
+
+extern "C" {
+
+int usl_sample_keyframe_rays(const float *c2ws, const float *depths, const float *colors, const float *dirs_cam,
+                             const int64_t *indices, int K, int64_t P, int n, int frame_base, float *rays_o,
+                             float *rays_d, float *gt_depth, float *gt_color, float *dirs_out, int32_t *frame_id,
+                             usl_stream_t stream) {
+    const int64_t M = (int64_t)K * n;
+    if (M <= 0) return 0;
+    sample_keyframe_rays_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        c2ws, depths, colors, dirs_cam, indices, K, P, n, frame_base, rays_o, rays_d, gt_depth, gt_color, dirs_out, frame_id);
+    return check_launch("usl_sample_keyframe_rays");
+}
+
+int usl_sample_window_rays(const float *c2w, const float *depth, const float *color, int H, int W, int H0, int H1,
+                           int W0, int W1, float fx, float fy, float cx, float cy, const int64_t *indices, int64_t n,
+                           float *rays_o, float *rays_d, float *gt_depth, float *gt_color, float *dirs_out,
+                           usl_stream_t stream) {
+    if (n <= 0) return 0;
+    if (H0 < 0 || H1 > H || W0 < 0 || W1 > W || H1 <= H0 || W1 <= W0) { set_error("usl_sample_window_rays: bad window"); return 1; }
+    sample_window_rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        c2w, depth, color, H, W, H0, H1, W0, W1, fx, fy, cx, cy, indices, n, rays_o, rays_d, gt_depth, gt_color, dirs_out);
+    return check_launch("usl_sample_window_rays");
+}
+
+int usl_image_rays(const float *c2w, int H, int W, float fx, float fy, float cx, float cy, float *rays_o,
+                   float *rays_d, usl_stream_t stream) {
+    const int64_t M = (int64_t)H * W;
+    if (M <= 0) return 0;
+    image_rays_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c2w, H, W, fx, fy, cx, cy, rays_o, rays_d);
+    return check_launch("usl_image_rays");
+}
+
+int usl_bbox_prefilter(const float *rays_o, const float *rays_d, const float *gt_depth, int64_t n,
+                       const usl_bound_t *bound, int require_depth, float *t_exit, uint8_t *valid,
+                       usl_stream_t stream) {
+    if (n <= 0) return 0;
+    if (!bound || (valid && !gt_depth)) { set_error("usl_bbox_prefilter: bad arguments"); return 1; }
+    bbox_prefilter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, gt_depth, n, *bound,
+                                                                                         require_depth, t_exit, valid);
+    return check_launch("usl_bbox_prefilter");
+}
+
+int usl_zsample_depth(const usl_zsample_args_t *a, const float *gt_depth, const uint8_t *valid, const float *t_rand,
+                      const int32_t *row_map, int64_t n_rays, float *z, usl_stream_t stream) {
+    if (n_rays <= 0) return 0;
+    if (!a || a->n_stratified < 1 || a->n_importance < 1) { set_error("usl_zsample_depth: bad arguments"); return 1; }
+    zsample_depth_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*a, gt_depth, valid, t_rand, row_map,
+                                                                                             n_rays, z);
+    return check_launch("usl_zsample_depth");
+}
+
+int usl_zsample_nodepth(const usl_zsample_args_t *a, const usl_field_t *f, const float *beta, const float *rays_o,
+                        const float *rays_d, const float *gt_depth, const uint8_t *valid, const float *t_rand_uni,
+                        const float *u_pdf, const int32_t *row_map, int64_t n_rays, float *z, int64_t *pdf_inds,
+                        usl_stream_t stream) {
+    if (n_rays <= 0) return 0;
+    if (!a || !f || a->n_stratified < 3 || a->n_stratified > ND_MAX_STRAT || a->n_importance < 1 || a->n_importance > ND_MAX_IMP || !u_pdf) {
+        set_error("usl_zsample_nodepth: unsupported sample counts (n_stratified 3..64, n_importance 1..32)");
+        return 1;
+    }
+    NoDepthArgs A;
+    A.a = *a; A.f = *f; A.beta = beta; A.rays_o = rays_o; A.rays_d = rays_d; A.gt_depth = gt_depth;
+    A.t_rand_uni = t_rand_uni; A.u_pdf = u_pdf; A.valid = valid; A.row_map = row_map; A.n_rays = n_rays; A.z = z; A.pdf_inds = pdf_inds;
+    zsample_nodepth_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, (cudaStream_t)stream>>>(A);
+    return check_launch("usl_zsample_nodepth");
+}
+
+}  // extern "C"

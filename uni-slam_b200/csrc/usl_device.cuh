@@ -1,0 +1,178 @@
+// Device-side building blocks shared by all kernels: hash-grid level math, decoder MLP staging.
+// sm_100a only.  Reference semantics: SURVEY.md section 8a-1 (tcnn GridEncoding restated).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/unislam_b200.h"
+
+#define USL_PRIME_Y 2654435761u
+#define USL_PRIME_Z 805459861u
+
+namespace usl {
+
+// ---- error plumbing (host) ------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int check_launch(const char *what);
+
+// ---- hash-grid level ------------------------------------------------------------------------
+struct Cell {
+    uint32_t g[3];
+    float w[3];
+};
+
+// pos = fmaf(scale, x, 0.5f); g = floorf(pos); w = pos - g     (tcnn pos_fract, Linear interpolation)
+__device__ __forceinline__ void pos_fract(float scale, float x, uint32_t &g, float &w) {
+    const float pos = __fmaf_rn(scale, x, 0.5f);
+    const float fl = floorf(pos);
+    g = (uint32_t)(int32_t)fl;
+    w = pos - fl;
+}
+
+__device__ __forceinline__ Cell make_cell(const usl_level_t &lv, float x0, float x1, float x2) {
+    Cell c;
+    pos_fract(lv.scale, x0, c.g[0], c.w[0]);
+    pos_fract(lv.scale, x1, c.g[1], c.w[1]);
+    pos_fract(lv.scale, x2, c.g[2], c.w[2]);
+    return c;
+}
+
+// Entry indices (within the level) of the 8 corners; corner c: bit d set -> g_d + 1.
+// tcnn grid_index<3, CoherentPrime> with `% size`: hashed levels have power-of-two size (mask),
+// dense levels only wrap at the x==1 boundary (or for out-of-range inputs) -> rare slow path.
+__device__ __forceinline__ void corner_indices(const usl_level_t &lv, const Cell &c, uint32_t idx[8]) {
+    if (lv.hashed) {
+        const uint32_t mask = lv.size - 1u;
+        const uint32_t hx0 = c.g[0], hx1 = c.g[0] + 1u;
+        const uint32_t hy0 = c.g[1] * USL_PRIME_Y, hy1 = hy0 + USL_PRIME_Y;
+        const uint32_t hz0 = c.g[2] * USL_PRIME_Z, hz1 = hz0 + USL_PRIME_Z;
+        idx[0] = (hx0 ^ hy0 ^ hz0) & mask;
+        idx[1] = (hx1 ^ hy0 ^ hz0) & mask;
+        idx[2] = (hx0 ^ hy1 ^ hz0) & mask;
+        idx[3] = (hx1 ^ hy1 ^ hz0) & mask;
+        idx[4] = (hx0 ^ hy0 ^ hz1) & mask;
+        idx[5] = (hx1 ^ hy0 ^ hz1) & mask;
+        idx[6] = (hx0 ^ hy1 ^ hz1) & mask;
+        idx[7] = (hx1 ^ hy1 ^ hz1) & mask;
+    } else {
+        const uint32_t res = lv.res, res2 = lv.res * lv.res;
+        const uint32_t base = c.g[0] + c.g[1] * res + c.g[2] * res2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t i = base + (k & 1) + ((k >> 1) & 1) * res + ((k >> 2) & 1) * res2;
+            if (i >= lv.size) i %= lv.size;
+            idx[k] = i;
+        }
+    }
+}
+
+// Trilinear weights in tcnn's multiplication order: ((1 * f0) * f1) * f2.
+__device__ __forceinline__ void corner_weights(const Cell &c, float wt[8]) {
+    const float a0 = 1.0f - c.w[0], a1 = 1.0f - c.w[1], a2 = 1.0f - c.w[2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float w = (k & 1) ? c.w[0] : a0;
+        w *= (k & 2) ? c.w[1] : a1;
+        w *= (k & 4) ? c.w[2] : a2;
+        wt[k] = w;
+    }
+}
+
+__device__ __forceinline__ float2 ldg2(const float2 *p) { return __ldg(p); }
+
+// Gather the 8 corners of one level and interpolate; optionally the d f / d x tangents.
+template <bool WITH_JAC>
+__device__ __forceinline__ void level_interp(const usl_level_t &lv, const float2 *__restrict__ table,
+                                             float x0, float x1, float x2, float2 &f, float2 df[3]) {
+    const Cell c = make_cell(lv, x0, x1, x2);
+    uint32_t idx[8];
+    corner_indices(lv, c, idx);
+    const float2 *tab = table + lv.offset;
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ldg2(tab + idx[k]);
+    float wt[8];
+    corner_weights(c, wt);
+    f.x = 0.f; f.y = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        f.x = __fmaf_rn(wt[k], v[k].x, f.x);
+        f.y = __fmaf_rn(wt[k], v[k].y, f.y);
+    }
+    if (WITH_JAC) {
+        const float a0 = 1.0f - c.w[0], a1 = 1.0f - c.w[1], a2 = 1.0f - c.w[2];
+        const float b0 = c.w[0], b1 = c.w[1], b2 = c.w[2];
+        const float s = lv.scale;
+        // d/dx0: sum over (c1,c2) of w1*w2*(v[1|..]-v[0|..])
+        {
+            const float w00 = a1 * a2, w10 = b1 * a2, w01 = a1 * b2, w11 = b1 * b2;
+            df[0].x = s * (w00 * (v[1].x - v[0].x) + w10 * (v[3].x - v[2].x) + w01 * (v[5].x - v[4].x) + w11 * (v[7].x - v[6].x));
+            df[0].y = s * (w00 * (v[1].y - v[0].y) + w10 * (v[3].y - v[2].y) + w01 * (v[5].y - v[4].y) + w11 * (v[7].y - v[6].y));
+        }
+        {
+            const float w00 = a0 * a2, w10 = b0 * a2, w01 = a0 * b2, w11 = b0 * b2;
+            df[1].x = s * (w00 * (v[2].x - v[0].x) + w10 * (v[3].x - v[1].x) + w01 * (v[6].x - v[4].x) + w11 * (v[7].x - v[5].x));
+            df[1].y = s * (w00 * (v[2].y - v[0].y) + w10 * (v[3].y - v[1].y) + w01 * (v[6].y - v[4].y) + w11 * (v[7].y - v[5].y));
+        }
+        {
+            const float w00 = a0 * a1, w10 = b0 * a1, w01 = a0 * b1, w11 = b0 * b1;
+            df[2].x = s * (w00 * (v[4].x - v[0].x) + w10 * (v[5].x - v[1].x) + w01 * (v[6].x - v[2].x) + w11 * (v[7].x - v[3].x));
+            df[2].y = s * (w00 * (v[4].y - v[0].y) + w10 * (v[5].y - v[1].y) + w01 * (v[6].y - v[2].y) + w11 * (v[7].y - v[3].y));
+        }
+    }
+}
+
+// ---- decoder weights staged in shared memory --------------------------------------------------
+// Layout (floats): w1t[32][16] (transposed: [k][j]), b1[16], w2[16][16], b2[16], wo[4][16], bo[4]
+struct MlpSmem {
+    float w1t[USL_IN][USL_HID];
+    float b1[USL_HID];
+    float w2[USL_HID][USL_HID];
+    float b2[USL_HID];
+    float wo[4][USL_HID];
+    float bo[4];
+};
+
+__device__ __forceinline__ void stage_mlp(const usl_mlp_t &m, MlpSmem &s) {
+    const int t = threadIdx.x, nt = blockDim.x;
+    for (int i = t; i < USL_IN * USL_HID; i += nt) {
+        const int j = i / USL_IN, k = i % USL_IN;          // w1 is [j][k] row-major
+        s.w1t[k][j] = m.w1[i];
+    }
+    for (int i = t; i < USL_HID; i += nt) {
+        s.b1[i] = m.b1 ? m.b1[i] : 0.f;
+        s.b2[i] = (m.n_hidden == 2 && m.b2) ? m.b2[i] : 0.f;
+    }
+    for (int i = t; i < USL_HID * USL_HID; i += nt)
+        (&s.w2[0][0])[i] = (m.n_hidden == 2) ? m.w2[i] : 0.f;
+    for (int i = t; i < 4 * USL_HID; i += nt)
+        (&s.wo[0][0])[i] = (i / USL_HID < m.n_out) ? m.wo[i] : 0.f;
+    for (int i = t; i < 4; i += nt) s.bo[i] = (i < m.n_out && m.bo) ? m.bo[i] : 0.f;
+}
+
+__device__ __forceinline__ float act_fwd(int act, float u) {
+    if (act == USL_ACT_TANH) return tanhf(u);
+    if (act == USL_ACT_SIGMOID) return 1.0f / (1.0f + expf(-u));
+    return u;
+}
+// derivative expressed with the activated output y
+__device__ __forceinline__ float act_bwd(int act, float y) {
+    if (act == USL_ACT_TANH) return 1.0f - y * y;
+    if (act == USL_ACT_SIGMOID) return y * (1.0f - y);
+    return 1.0f;
+}
+
+// Normalised coordinate of sample s on ray r: x = ((o + d*z) - lo) / (hi - lo), op-for-op like
+// src/utils/Renderer.py:132,137 (separate mul/add, IEEE division; no FMA contraction).
+__device__ __forceinline__ float norm_coord(float o, float d, float z, float lo, float hi) {
+    const float p = __fadd_rn(o, __fmul_rn(d, z));
+    return __fdiv_rn(__fsub_rn(p, lo), __fsub_rn(hi, lo));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace usl

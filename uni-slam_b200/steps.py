@@ -1,0 +1,234 @@
+"""Fused per-iteration drivers: one Mapper iteration / one Tracker iteration / the dense SDF query,
+as fixed sequences of C-ABI launches on preallocated buffers (no host sync, no boolean-index
+compaction, CUDA-graph capturable).
+
+They compute what src/Mapper.py:366-445 (optimize_mapping loop body up to loss.backward()),
+src/Tracker.py:149-244 (optimize_tracking up to loss.backward()) and src/utils/Mesher.py:134-227
+(eval_points over get_grid_uniform) compute, and leave the gradients in ``.grad``-compatible buffers
+so the host code's own torch.optim.Adam can step on them.
+
+RNG contract: the torch.randint / torch.rand draws stay on the host side (reference behaviour);
+because rays are masked instead of compacted, the draws are indexed by ray slot: t_rand is (R,S),
+t_rand_uni (R,n_stratified), u_pdf (R,n_importance).  (The drop-in ``modules.Renderer`` keeps the
+reference's compacted draw shapes instead.)
+"""
+from ctypes import byref
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from . import ops
+from ._lib import call, ptr, stream
+
+
+class _FieldState:
+    """Tables + decoder tensors + beta, their packed descriptor and persistent gradient buffers."""
+
+    def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec: Sequence[torch.Tensor], beta: torch.Tensor,
+                 with_grads: bool):
+        self.meta, self.sdf_table, self.rgb_table, self.dec, self.beta = meta, sdf_table, rgb_table, list(dec), beta
+        self.field = meta.pack(sdf_table, rgb_table, self.dec)
+        if with_grads:
+            self.g_sdf_table = torch.zeros_like(sdf_table)
+            self.g_rgb_table = torch.zeros_like(rgb_table)
+            # decoder grads + beta grad live in ONE flat buffer so a single memset clears them
+            sizes = [t.numel() for t in self.dec] + [1]
+            self.g_flat = torch.zeros(sum(sizes), device=sdf_table.device, dtype=torch.float32)
+            views, o = [], 0
+            for t, s in zip(self.dec + [beta], sizes):
+                views.append(self.g_flat[o:o + s].view(t.shape if t is not beta else (1,)))
+                o += s
+            self.g_dec, self.g_beta = views[:-1], views[-1]
+            self.g_mlp = meta.pack_grads(self.g_dec)
+
+    def repack(self):
+        self.field = self.meta.pack(self.sdf_table, self.rgb_table, self.dec)
+
+
+class MappingStep:
+    """One mapping iteration (sample -> prefilter -> z-sample -> render -> loss -> backward)."""
+
+    def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec, beta, *, n_stratified, n_importance, truncation,
+                 weights=(5.0, 200.0, 10.0, 0.1, 5.0), max_rays: int, max_frames: int = 1, perturb: bool = True):
+        dev = sdf_table.device
+        self.fs = _FieldState(meta, sdf_table, rgb_table, dec, beta, with_grads=True)
+        self.zs = ops.ZSampler(n_stratified, n_importance, truncation, dev)
+        self.S = self.zs.S
+        self.perturb = perturb
+        self.loss_args = ops.make_loss_args(truncation, weights[0], weights[1], weights[2], weights[3], weights[4], 0)
+        R, S = max_rays, self.S
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.max_rays = R
+        self.rays_o = torch.empty((R, 3), **f32); self.rays_d = torch.empty((R, 3), **f32)
+        self.gt_depth = torch.empty((R,), **f32); self.gt_color = torch.empty((R, 3), **f32)
+        self.dirs = torch.empty((R, 3), **f32); self.frame_id = torch.empty((R,), device=dev, dtype=torch.int32)
+        self.valid = torch.empty((R,), device=dev, dtype=torch.uint8); self.mask = torch.empty((R,), device=dev, dtype=torch.uint8)
+        self.z = torch.zeros((R, S), **f32)
+        self.raw = torch.empty((R, S, 4), **f32); self.feat = torch.empty((2, ops.N_LEVELS, R * S, 2), **f32)
+        self.jac = torch.empty((R * S, 12), **f32)
+        self.term = torch.empty((R,), **f32); self.punc = torch.empty((R,), **f32); self.depth = torch.empty((R,), **f32)
+        self.rgb = torch.empty((R, 3), **f32); self.dunc = torch.empty((R,), **f32)
+        self.acc = torch.zeros((L.LOSS_SLOTS,), **f32); self.loss = torch.zeros((1,), **f32)
+        self.g_depth = torch.empty((R,), **f32); self.g_rgb = torch.empty((R, 3), **f32); self.g_sdf = torch.empty((R, S), **f32)
+        self.d_raw = torch.empty((R, S, 4), **f32)
+        self.d_rays_o = torch.empty((R, 3), **f32); self.d_rays_d = torch.empty((R, 3), **f32)
+        self.c2ws = torch.empty((max_frames, 4, 4), **f32)
+        self.d_c2w = torch.zeros((max_frames, 12), **f32); self.d_pose = torch.zeros((max_frames, 7), **f32)
+        self.n_rays = 0
+
+    # gradients, in the order Mapper.create_optimizer groups the parameters (Mapper.py:111-139)
+    @property
+    def grads(self):
+        return dict(dec=self.fs.g_dec, beta=self.fs.g_beta, sdf_table=self.fs.g_sdf_table, rgb_table=self.fs.g_rgb_table)
+
+    def run(self, batches, t_rand, t_rand_uni=None, u_pdf=None, cam_poses: Optional[torch.Tensor] = None,
+            c2w_fixed: Optional[torch.Tensor] = None, has_holes: bool = True):
+        """batches: list of (c2ws|None, depths (K,P), colors (K,P,3), dirs_cam (K,P,3), indices (K*n,), n, frame_base).
+        When cam_poses (K-1,7) is given (joint_opt, Mapper.py:372-376) the camera matrices are rebuilt on
+        device as cat(c2w_fixed[None], pose_to_matrix(cam_poses)) and pose gradients land in self.d_pose."""
+        st = stream()
+        fs, S = self.fs, self.S
+        joint = cam_poses is not None
+        if joint:
+            K = cam_poses.shape[0] + 1
+            self.c2ws[0].copy_(c2w_fixed)
+            call("usl_pose_to_matrix", ptr(cam_poses), K - 1, ptr(self.c2ws[1:K]), st)
+        # ---- a-3: gather-then-rotate ray generation ----
+        off = 0
+        for (c2ws, depths, colors, dirs_cam, indices, n, frame_base) in batches:
+            Kb, P = depths.shape
+            M = Kb * n
+            cw = self.c2ws[frame_base:frame_base + Kb] if joint else c2ws
+            sl = slice(off, off + M)
+            call("usl_sample_keyframe_rays", ptr(cw), ptr(depths), ptr(colors), ptr(dirs_cam), ptr(indices), Kb, P, n, frame_base,
+                 ptr(self.rays_o[sl]), ptr(self.rays_d[sl]), ptr(self.gt_depth[sl]), ptr(self.gt_color[sl]), ptr(self.dirs[sl]),
+                 ptr(self.frame_id[sl]), st)
+            off += M
+        R = off
+        assert R <= self.max_rays
+        self.n_rays = R
+        v = lambda t: ptr(t[:R]) if t is not None else None
+        # ---- a-4 prefilter, a-5/a-6 z sampling ----
+        call("usl_bbox_prefilter", v(self.rays_o), v(self.rays_d), v(self.gt_depth), R, byref(fs.meta.bound), 0, None, v(self.valid), st)
+        call("usl_zsample_depth", byref(self.zs.args), v(self.gt_depth), v(self.valid), ptr(t_rand) if self.perturb else None, None, R, v(self.z), st)
+        if has_holes:
+            call("usl_zsample_nodepth", byref(self.zs.args), byref(fs.field), ptr(fs.beta), v(self.rays_o), v(self.rays_d), v(self.gt_depth),
+                 v(self.valid), ptr(t_rand_uni) if self.perturb else None, ptr(u_pdf), None, R, v(self.z), None, st)
+        # ---- a-7, a-1, a-2: field query; a-8: compositing ----
+        pts = L.Points()
+        pts.x = None; pts.rays_o, pts.rays_d, pts.z, pts.valid = v(self.rays_o), v(self.rays_d), v(self.z), v(self.valid)
+        pts.S, pts.n = S, R * S
+        # feat is laid out [2][L][n][2] with n = R*S of THIS call
+        call("usl_field_fwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), ptr(self.jac) if joint else None, st)
+        call("usl_composite_fwd", v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), R, S, v(self.term), v(self.punc), v(self.depth),
+             v(self.rgb), v(self.dunc), None, st)
+        # ---- a-9: losses (two-phase) ----
+        self.acc.zero_()
+        call("usl_loss_fwd", byref(self.loss_args), v(self.raw), v(self.z), v(self.gt_depth), v(self.gt_color), v(self.valid), v(self.punc),
+             v(self.depth), v(self.rgb), None, R, S, ptr(self.acc), v(self.mask), st)
+        call("usl_loss_finalize", byref(self.loss_args), ptr(self.acc), ptr(self.loss), st)
+        call("usl_loss_bwd", byref(self.loss_args), v(self.raw), v(self.z), v(self.gt_depth), v(self.gt_color), v(self.valid), v(self.mask),
+             v(self.depth), v(self.rgb), ptr(self.acc), None, R, S, v(self.g_depth), v(self.g_rgb), v(self.g_sdf), st)
+        # ---- backward ----
+        fs.g_flat.zero_(); fs.g_sdf_table.zero_(); fs.g_rgb_table.zero_()
+        call("usl_composite_bwd", v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), R, S, None, None, v(self.g_depth), v(self.g_rgb), None,
+             v(self.g_sdf), ptr(self.jac) if joint else None, byref(fs.meta.bound), v(self.d_raw), ptr(fs.g_beta),
+             v(self.d_rays_o) if joint else None, v(self.d_rays_d) if joint else None, st)
+        call("usl_field_bwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), v(self.d_raw), ptr(fs.g_sdf_table),
+             ptr(fs.g_rgb_table), fs.g_mlp, st)
+        if joint:
+            self.d_c2w[:K].zero_()
+            call("usl_pose_reduce", v(self.d_rays_o), v(self.d_rays_d), v(self.dirs), v(self.frame_id), v(self.valid), R, K, ptr(self.d_c2w), st)
+            call("usl_pose_matrix_bwd", ptr(cam_poses), ptr(self.d_c2w[1:K]), K - 1, ptr(self.d_pose[:K - 1]), st)
+        return self.loss
+
+
+class TrackingStep:
+    """One tracking iteration: pose -> rays -> render -> median mask -> loss -> d loss / d (quat, trans).
+    The hash tables and decoders are read-only here (the reference's dead table scatter is skipped)."""
+
+    def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec, beta, *, n_stratified, n_importance, truncation,
+                 H, W, fx, fy, cx, cy, ignore_edge_h, ignore_edge_w, n_rays: int,
+                 weights=(10.0, 200.0, 50.0, 1.0, 5.0), perturb: bool = True):
+        dev = sdf_table.device
+        self.fs = _FieldState(meta, sdf_table, rgb_table, dec, beta, with_grads=False)
+        self.zs = ops.ZSampler(n_stratified, n_importance, truncation, dev)
+        self.S = self.zs.S
+        self.perturb = perturb
+        self.cam = (H, W, float(fx), float(fy), float(cx), float(cy))
+        self.win = (ignore_edge_h, H - ignore_edge_h, ignore_edge_w, W - ignore_edge_w)
+        self.loss_args = ops.make_loss_args(truncation, weights[0], weights[1], weights[2], weights[3], weights[4], 1)
+        R, S = n_rays, self.S
+        self.R = R
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.c2w = torch.empty((1, 4, 4), **f32)
+        self.rays_o = torch.empty((R, 3), **f32); self.rays_d = torch.empty((R, 3), **f32)
+        self.gt_depth = torch.empty((R,), **f32); self.gt_color = torch.empty((R, 3), **f32); self.dirs = torch.empty((R, 3), **f32)
+        self.valid = torch.empty((R,), device=dev, dtype=torch.uint8); self.mask = torch.empty((R,), device=dev, dtype=torch.uint8)
+        self.z = torch.zeros((R, S), **f32)
+        self.raw = torch.empty((R, S, 4), **f32); self.jac = torch.empty((R * S, 12), **f32)
+        self.term = torch.empty((R,), **f32); self.punc = torch.empty((R,), **f32); self.depth = torch.empty((R,), **f32)
+        self.rgb = torch.empty((R, 3), **f32); self.dunc = torch.empty((R,), **f32)
+        self.acc = torch.zeros((L.LOSS_SLOTS,), **f32); self.loss = torch.zeros((1,), **f32)
+        self.median = torch.zeros((1,), **f32); self.ws = torch.empty((R,), **f32)
+        self.g_depth = torch.empty((R,), **f32); self.g_rgb = torch.empty((R, 3), **f32); self.g_sdf = torch.empty((R, S), **f32)
+        self.d_raw = torch.empty((R, S, 4), **f32)
+        self.d_rays_o = torch.empty((R, 3), **f32); self.d_rays_d = torch.empty((R, 3), **f32)
+        self.d_c2w = torch.zeros((1, 12), **f32); self.d_pose = torch.zeros((1, 7), **f32)
+
+    def run(self, cam_pose, depth_img, color_img, indices, t_rand):
+        """cam_pose (1,7) = [quat(real first), trans] (common.py:196-208); depth_img (H,W); color_img (H,W,3);
+        indices: torch.randint(window_pixels, (R,)) (common.py:116); t_rand (R,S). Returns loss (1,);
+        d loss/d cam_pose in self.d_pose; mean pixel uncertainty = acc[11]/acc[9]."""
+        st = stream()
+        fs, S, R = self.fs, self.S, self.R
+        H, W, fx, fy, cx, cy = self.cam
+        H0, H1, W0, W1 = self.win
+        call("usl_pose_to_matrix", ptr(cam_pose), 1, ptr(self.c2w), st)
+        call("usl_sample_window_rays", ptr(self.c2w), ptr(depth_img), ptr(color_img), H, W, H0, H1, W0, W1, fx, fy, cx, cy, ptr(indices), R,
+             ptr(self.rays_o), ptr(self.rays_d), ptr(self.gt_depth), ptr(self.gt_color), ptr(self.dirs), st)
+        call("usl_bbox_prefilter", ptr(self.rays_o), ptr(self.rays_d), ptr(self.gt_depth), R, byref(fs.meta.bound), 1, None, ptr(self.valid), st)
+        call("usl_zsample_depth", byref(self.zs.args), ptr(self.gt_depth), ptr(self.valid), ptr(t_rand) if self.perturb else None, None, R,
+             ptr(self.z), st)
+        pts = L.Points()
+        pts.x = None; pts.rays_o, pts.rays_d, pts.z, pts.valid = ptr(self.rays_o), ptr(self.rays_d), ptr(self.z), ptr(self.valid)
+        pts.S, pts.n = S, R * S
+        call("usl_field_fwd", byref(fs.field), byref(pts), ptr(self.raw), None, ptr(self.jac), st)
+        call("usl_composite_fwd", ptr(self.raw), ptr(self.z), ptr(fs.beta), ptr(self.valid), R, S, ptr(self.term), ptr(self.punc),
+             ptr(self.depth), ptr(self.rgb), ptr(self.dunc), None, st)
+        call("usl_depth_error_median", ptr(self.gt_depth), ptr(self.depth), ptr(self.valid), R, ptr(self.ws), ptr(self.median), st)
+        self.acc.zero_()
+        call("usl_loss_fwd", byref(self.loss_args), ptr(self.raw), ptr(self.z), ptr(self.gt_depth), ptr(self.gt_color), ptr(self.valid),
+             ptr(self.punc), ptr(self.depth), ptr(self.rgb), ptr(self.median), R, S, ptr(self.acc), ptr(self.mask), st)
+        call("usl_loss_finalize", byref(self.loss_args), ptr(self.acc), ptr(self.loss), st)
+        call("usl_loss_bwd", byref(self.loss_args), ptr(self.raw), ptr(self.z), ptr(self.gt_depth), ptr(self.gt_color), ptr(self.valid),
+             ptr(self.mask), ptr(self.depth), ptr(self.rgb), ptr(self.acc), None, R, S, ptr(self.g_depth), ptr(self.g_rgb), ptr(self.g_sdf), st)
+        call("usl_composite_bwd", ptr(self.raw), ptr(self.z), ptr(fs.beta), ptr(self.valid), R, S, None, None, ptr(self.g_depth), ptr(self.g_rgb),
+             None, ptr(self.g_sdf), ptr(self.jac), byref(fs.meta.bound), ptr(self.d_raw), None, ptr(self.d_rays_o), ptr(self.d_rays_d), st)
+        self.d_c2w.zero_()
+        call("usl_pose_reduce", ptr(self.d_rays_o), ptr(self.d_rays_d), ptr(self.dirs), None, ptr(self.valid), R, 1, ptr(self.d_c2w), st)
+        call("usl_pose_matrix_bwd", ptr(cam_pose), ptr(self.d_c2w), 1, ptr(self.d_pose), st)
+        return self.loss
+
+
+class DenseSdfQuery:
+    """Mesher.get_grid_uniform + eval_points (SDF channel) over a y-slab of the 1 cm query grid
+    (src/utils/Mesher.py:134-195,219-227); points are generated in-kernel from the per-axis coordinates."""
+
+    def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec, axes: Sequence[torch.Tensor]):
+        self.field = meta.pack(sdf_table, rgb_table, list(dec))
+        self._keep = (sdf_table, rgb_table, list(dec))
+        self.ax, self.ay, self.az = [a.contiguous().float() for a in axes]
+        self.nx, self.ny, self.nz = self.ax.numel(), self.ay.numel(), self.az.numel()
+
+    def slab_points(self, y_begin, y_end):
+        return (y_end - y_begin) * self.nx * self.nz
+
+    def run(self, y_begin: int, y_end: int, out: Optional[torch.Tensor] = None):
+        n = self.slab_points(y_begin, y_end)
+        if out is None:
+            out = torch.empty((n,), device=self.ax.device, dtype=torch.float32)
+        call("usl_sdf_query_grid", byref(self.field), ptr(self.ax), ptr(self.ay), ptr(self.az), self.nx, self.ny, self.nz,
+             y_begin, y_end, ptr(out), stream())
+        return out
