@@ -112,8 +112,14 @@ def load():
     return lib
 
 
+LAUNCHES = 0   # number of kernel-launching C-ABI calls made so far (bench.py reports it as gpu_launches)
+
+
 def call(name, *args):
+    global LAUNCHES
     lib = load()
+    if name != "usl_grid_build":
+        LAUNCHES += 1
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed: {lib.usl_last_error().decode()}")

@@ -22,6 +22,27 @@ from . import ops
 from ._lib import call, ptr, stream
 
 
+class _Profiled:
+    """Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline leg)."""
+    profile = False
+
+    def _init_prof(self):
+        self.events = {}          # kernel name -> list of (start, stop) events
+
+    def _call(self, name, *args):
+        if not self.profile:
+            return call(name, *args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call(name, *args)
+        e1.record()
+        self.events.setdefault(name, []).append((e0, e1))
+
+    def kernel_ms(self):
+        """Mean duration per launch (ms) of every profiled entry point; call after a synchronize."""
+        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in self.events.items()}
+
+
 class _FieldState:
     """Tables + decoder tensors + beta, their packed descriptor and persistent gradient buffers."""
 
@@ -46,7 +67,7 @@ class _FieldState:
         self.field = self.meta.pack(self.sdf_table, self.rgb_table, self.dec)
 
 
-class MappingStep:
+class MappingStep(_Profiled):
     """One mapping iteration (sample -> prefilter -> z-sample -> render -> loss -> backward)."""
 
     def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec, beta, *, n_stratified, n_importance, truncation,
@@ -76,6 +97,8 @@ class MappingStep:
         self.c2ws = torch.empty((max_frames, 4, 4), **f32)
         self.d_c2w = torch.zeros((max_frames, 12), **f32); self.d_pose = torch.zeros((max_frames, 7), **f32)
         self.n_rays = 0
+        self.acc_hook = None      # multi-GPU: called with self.acc between loss_fwd and loss_bwd (all-reduce of sums/counts)
+        self._init_prof()
 
     # gradients, in the order Mapper.create_optimizer groups the parameters (Mapper.py:111-139)
     @property
@@ -101,7 +124,7 @@ class MappingStep:
             M = Kb * n
             cw = self.c2ws[frame_base:frame_base + Kb] if joint else c2ws
             sl = slice(off, off + M)
-            call("usl_sample_keyframe_rays", ptr(cw), ptr(depths), ptr(colors), ptr(dirs_cam), ptr(indices), Kb, P, n, frame_base,
+            self._call("usl_sample_keyframe_rays", ptr(cw), ptr(depths), ptr(colors), ptr(dirs_cam), ptr(indices), Kb, P, n, frame_base,
                  ptr(self.rays_o[sl]), ptr(self.rays_d[sl]), ptr(self.gt_depth[sl]), ptr(self.gt_color[sl]), ptr(self.dirs[sl]),
                  ptr(self.frame_id[sl]), st)
             off += M
@@ -111,40 +134,42 @@ class MappingStep:
         v = lambda t: ptr(t[:R]) if t is not None else None
         # ---- a-4 prefilter, a-5/a-6 z sampling ----
         call("usl_bbox_prefilter", v(self.rays_o), v(self.rays_d), v(self.gt_depth), R, byref(fs.meta.bound), 0, None, v(self.valid), st)
-        call("usl_zsample_depth", byref(self.zs.args), v(self.gt_depth), v(self.valid), ptr(t_rand) if self.perturb else None, None, R, v(self.z), st)
+        self._call("usl_zsample_depth", byref(self.zs.args), v(self.gt_depth), v(self.valid), ptr(t_rand) if self.perturb else None, None, R, v(self.z), st)
         if has_holes:
-            call("usl_zsample_nodepth", byref(self.zs.args), byref(fs.field), ptr(fs.beta), v(self.rays_o), v(self.rays_d), v(self.gt_depth),
+            self._call("usl_zsample_nodepth", byref(self.zs.args), byref(fs.field), ptr(fs.beta), v(self.rays_o), v(self.rays_d), v(self.gt_depth),
                  v(self.valid), ptr(t_rand_uni) if self.perturb else None, ptr(u_pdf), None, R, v(self.z), None, st)
         # ---- a-7, a-1, a-2: field query; a-8: compositing ----
         pts = L.Points()
         pts.x = None; pts.rays_o, pts.rays_d, pts.z, pts.valid = v(self.rays_o), v(self.rays_d), v(self.z), v(self.valid)
         pts.S, pts.n = S, R * S
         # feat is laid out [2][L][n][2] with n = R*S of THIS call
-        call("usl_field_fwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), ptr(self.jac) if joint else None, st)
-        call("usl_composite_fwd", v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), R, S, v(self.term), v(self.punc), v(self.depth),
+        self._call("usl_field_fwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), ptr(self.jac) if joint else None, st)
+        self._call("usl_composite_fwd", v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), R, S, v(self.term), v(self.punc), v(self.depth),
              v(self.rgb), v(self.dunc), None, st)
         # ---- a-9: losses (two-phase) ----
         self.acc.zero_()
-        call("usl_loss_fwd", byref(self.loss_args), v(self.raw), v(self.z), v(self.gt_depth), v(self.gt_color), v(self.valid), v(self.punc),
+        self._call("usl_loss_fwd", byref(self.loss_args), v(self.raw), v(self.z), v(self.gt_depth), v(self.gt_color), v(self.valid), v(self.punc),
              v(self.depth), v(self.rgb), None, R, S, ptr(self.acc), v(self.mask), st)
+        if self.acc_hook is not None:
+            self.acc_hook(self.acc)
         call("usl_loss_finalize", byref(self.loss_args), ptr(self.acc), ptr(self.loss), st)
-        call("usl_loss_bwd", byref(self.loss_args), v(self.raw), v(self.z), v(self.gt_depth), v(self.gt_color), v(self.valid), v(self.mask),
+        self._call("usl_loss_bwd", byref(self.loss_args), v(self.raw), v(self.z), v(self.gt_depth), v(self.gt_color), v(self.valid), v(self.mask),
              v(self.depth), v(self.rgb), ptr(self.acc), None, R, S, v(self.g_depth), v(self.g_rgb), v(self.g_sdf), st)
         # ---- backward ----
         fs.g_flat.zero_(); fs.g_sdf_table.zero_(); fs.g_rgb_table.zero_()
-        call("usl_composite_bwd", v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), R, S, None, None, v(self.g_depth), v(self.g_rgb), None,
+        self._call("usl_composite_bwd", v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), R, S, None, None, v(self.g_depth), v(self.g_rgb), None,
              v(self.g_sdf), ptr(self.jac) if joint else None, byref(fs.meta.bound), v(self.d_raw), ptr(fs.g_beta),
              v(self.d_rays_o) if joint else None, v(self.d_rays_d) if joint else None, st)
-        call("usl_field_bwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), v(self.d_raw), ptr(fs.g_sdf_table),
+        self._call("usl_field_bwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), v(self.d_raw), ptr(fs.g_sdf_table),
              ptr(fs.g_rgb_table), fs.g_mlp, st)
         if joint:
             self.d_c2w[:K].zero_()
-            call("usl_pose_reduce", v(self.d_rays_o), v(self.d_rays_d), v(self.dirs), v(self.frame_id), v(self.valid), R, K, ptr(self.d_c2w), st)
+            self._call("usl_pose_reduce", v(self.d_rays_o), v(self.d_rays_d), v(self.dirs), v(self.frame_id), v(self.valid), R, K, ptr(self.d_c2w), st)
             call("usl_pose_matrix_bwd", ptr(cam_poses), ptr(self.d_c2w[1:K]), K - 1, ptr(self.d_pose[:K - 1]), st)
         return self.loss
 
 
-class TrackingStep:
+class TrackingStep(_Profiled):
     """One tracking iteration: pose -> rays -> render -> median mask -> loss -> d loss / d (quat, trans).
     The hash tables and decoders are read-only here (the reference's dead table scatter is skipped)."""
 
@@ -176,6 +201,7 @@ class TrackingStep:
         self.d_raw = torch.empty((R, S, 4), **f32)
         self.d_rays_o = torch.empty((R, 3), **f32); self.d_rays_d = torch.empty((R, 3), **f32)
         self.d_c2w = torch.zeros((1, 12), **f32); self.d_pose = torch.zeros((1, 7), **f32)
+        self._init_prof()
 
     def run(self, cam_pose, depth_img, color_img, indices, t_rand):
         """cam_pose (1,7) = [quat(real first), trans] (common.py:196-208); depth_img (H,W); color_img (H,W,3);
@@ -186,28 +212,28 @@ class TrackingStep:
         H, W, fx, fy, cx, cy = self.cam
         H0, H1, W0, W1 = self.win
         call("usl_pose_to_matrix", ptr(cam_pose), 1, ptr(self.c2w), st)
-        call("usl_sample_window_rays", ptr(self.c2w), ptr(depth_img), ptr(color_img), H, W, H0, H1, W0, W1, fx, fy, cx, cy, ptr(indices), R,
+        self._call("usl_sample_window_rays", ptr(self.c2w), ptr(depth_img), ptr(color_img), H, W, H0, H1, W0, W1, fx, fy, cx, cy, ptr(indices), R,
              ptr(self.rays_o), ptr(self.rays_d), ptr(self.gt_depth), ptr(self.gt_color), ptr(self.dirs), st)
         call("usl_bbox_prefilter", ptr(self.rays_o), ptr(self.rays_d), ptr(self.gt_depth), R, byref(fs.meta.bound), 1, None, ptr(self.valid), st)
-        call("usl_zsample_depth", byref(self.zs.args), ptr(self.gt_depth), ptr(self.valid), ptr(t_rand) if self.perturb else None, None, R,
+        self._call("usl_zsample_depth", byref(self.zs.args), ptr(self.gt_depth), ptr(self.valid), ptr(t_rand) if self.perturb else None, None, R,
              ptr(self.z), st)
         pts = L.Points()
         pts.x = None; pts.rays_o, pts.rays_d, pts.z, pts.valid = ptr(self.rays_o), ptr(self.rays_d), ptr(self.z), ptr(self.valid)
         pts.S, pts.n = S, R * S
-        call("usl_field_fwd", byref(fs.field), byref(pts), ptr(self.raw), None, ptr(self.jac), st)
-        call("usl_composite_fwd", ptr(self.raw), ptr(self.z), ptr(fs.beta), ptr(self.valid), R, S, ptr(self.term), ptr(self.punc),
+        self._call("usl_field_fwd", byref(fs.field), byref(pts), ptr(self.raw), None, ptr(self.jac), st)
+        self._call("usl_composite_fwd", ptr(self.raw), ptr(self.z), ptr(fs.beta), ptr(self.valid), R, S, ptr(self.term), ptr(self.punc),
              ptr(self.depth), ptr(self.rgb), ptr(self.dunc), None, st)
-        call("usl_depth_error_median", ptr(self.gt_depth), ptr(self.depth), ptr(self.valid), R, ptr(self.ws), ptr(self.median), st)
+        self._call("usl_depth_error_median", ptr(self.gt_depth), ptr(self.depth), ptr(self.valid), R, ptr(self.ws), ptr(self.median), st)
         self.acc.zero_()
-        call("usl_loss_fwd", byref(self.loss_args), ptr(self.raw), ptr(self.z), ptr(self.gt_depth), ptr(self.gt_color), ptr(self.valid),
+        self._call("usl_loss_fwd", byref(self.loss_args), ptr(self.raw), ptr(self.z), ptr(self.gt_depth), ptr(self.gt_color), ptr(self.valid),
              ptr(self.punc), ptr(self.depth), ptr(self.rgb), ptr(self.median), R, S, ptr(self.acc), ptr(self.mask), st)
         call("usl_loss_finalize", byref(self.loss_args), ptr(self.acc), ptr(self.loss), st)
-        call("usl_loss_bwd", byref(self.loss_args), ptr(self.raw), ptr(self.z), ptr(self.gt_depth), ptr(self.gt_color), ptr(self.valid),
+        self._call("usl_loss_bwd", byref(self.loss_args), ptr(self.raw), ptr(self.z), ptr(self.gt_depth), ptr(self.gt_color), ptr(self.valid),
              ptr(self.mask), ptr(self.depth), ptr(self.rgb), ptr(self.acc), None, R, S, ptr(self.g_depth), ptr(self.g_rgb), ptr(self.g_sdf), st)
-        call("usl_composite_bwd", ptr(self.raw), ptr(self.z), ptr(fs.beta), ptr(self.valid), R, S, None, None, ptr(self.g_depth), ptr(self.g_rgb),
+        self._call("usl_composite_bwd", ptr(self.raw), ptr(self.z), ptr(fs.beta), ptr(self.valid), R, S, None, None, ptr(self.g_depth), ptr(self.g_rgb),
              None, ptr(self.g_sdf), ptr(self.jac), byref(fs.meta.bound), ptr(self.d_raw), None, ptr(self.d_rays_o), ptr(self.d_rays_d), st)
         self.d_c2w.zero_()
-        call("usl_pose_reduce", ptr(self.d_rays_o), ptr(self.d_rays_d), ptr(self.dirs), None, ptr(self.valid), R, 1, ptr(self.d_c2w), st)
+        self._call("usl_pose_reduce", ptr(self.d_rays_o), ptr(self.d_rays_d), ptr(self.dirs), None, ptr(self.valid), R, 1, ptr(self.d_c2w), st)
         call("usl_pose_matrix_bwd", ptr(cam_pose), ptr(self.d_c2w), 1, ptr(self.d_pose), st)
         return self.loss
 
