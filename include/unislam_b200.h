@@ -172,8 +172,8 @@ typedef struct usl_points {
     int32_t S;
     int64_t n;            /* number of points (= R*S when built from rays) */
 } usl_points_t;
-/* raw[n,4] = (r,g,b,sdf). feat (nullable): [2][L][n][2] interpolated features kept for the
- * decoder weight gradient. jac (nullable): [n,12] d raw / d x (rows r,g,b,sdf; clamp-gated). */
+/* raw[n,4] = (r,g,b,sdf). feat (nullable): activation stash for the backward pass, 2*n*48 floats:
+ * interpolated features [2][L][n][2] followed by the hidden pre-activations [2][16][n]. jac (nullable): [n,12] d raw / d x (rows r,g,b,sdf; clamp-gated). */
 USL_API int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac,
                   usl_stream_t stream);
 /* d_raw[n,4] -> table gradients (scatter), decoder gradients (gm[2], may be NULL to skip). */
@@ -241,6 +241,13 @@ USL_API int usl_pose_matrix_bwd(const float *pose, const float *d_c2w, int K, fl
  * [y_begin,y_end). SDF = -1 outside the open bound. out[(y_end-y_begin)*nx*nz]. */
 USL_API int usl_sdf_query_grid(const usl_field_t *f, const float *ax, const float *ay, const float *az, int nx,
                        int ny, int nz, int y_begin, int y_end, float *out, usl_stream_t stream);
+
+/* ---- measurement utilities (no reference counterpart): ceilings for the roofline discussion ---- */
+/* n_threads threads each issue per_thread random 8-byte loads from / vector atomics into table[entries*2] */
+USL_API int usl_bench_gather(const float *table, uint32_t entries, int64_t n_threads, int per_thread, float *out,
+                             usl_stream_t stream);
+USL_API int usl_bench_scatter(float *table, uint32_t entries, int64_t n_threads, int per_thread, int mode,
+                              usl_stream_t stream);
 
 #ifdef __cplusplus
 }

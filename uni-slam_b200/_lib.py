@@ -84,6 +84,8 @@ _SIGS = {
     "usl_pose_to_matrix": [_P, c_int, _P, _P],
     "usl_pose_matrix_bwd": [_P, _P, c_int, _P, _P],
     "usl_sdf_query_grid": [POINTER(Field), _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "usl_bench_gather": [_P, c_uint32, c_int64, c_int, _P, _P],
+    "usl_bench_scatter": [_P, c_uint32, c_int64, c_int, c_int, _P],
 }
 EXPORTS = ["usl_last_error", "usl_version"] + list(_SIGS)
 

@@ -54,9 +54,7 @@ __global__ void __launch_bounds__(256) encode_bwd_params_kernel(usl_grid_t g, co
     corner_indices(lv, c, idx);
     corner_weights(c, wt);
     const float2 d = dy[i * g.n_levels + l];
-    float2 *tab = grad + lv.offset;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(tab + idx[k], make_float2(wt[k] * d.x, wt[k] * d.y));
+    scatter_level(grad + lv.offset, idx, wt, d.x, d.y);
 }
 
 __global__ void __launch_bounds__(256) encode_bwd_input_kernel(usl_grid_t g, const float2 *__restrict__ table,
@@ -88,6 +86,49 @@ __global__ void __launch_bounds__(256) corner_indices_kernel(usl_grid_t g, const
     corner_indices(g.levels[l], c, idx);
 #pragma unroll
     for (int k = 0; k < 8; ++k) out[(i * g.n_levels + l) * 8 + k] = idx[k];
+}
+
+// ---- measurement utilities: L2-resident random 8-byte gather / vector-atomic scatter ceilings ----
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) bench_gather_kernel(const float2 *__restrict__ table, uint32_t entries, int64_t n,
+                                                           int per_thread, float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float ax = 0.f, ay = 0.f;
+    uint32_t h = mix32((uint32_t)i * 2654435761u + 12345u);
+    for (int k = 0; k < per_thread; k += 8) {
+        float2 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { h = mix32(h + q); v[q] = __ldg(table + (h % entries)); }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { ax += v[q].x; ay += v[q].y; }
+    }
+    if (ax == 123.456f) out[i] = ax + ay;            // keep the loads alive
+}
+
+// mode 0: every lane its own random entry; 1: lane pairs share a 16 B slot; 3: lane quads share a 32 B sector;
+// 4: a warp covers 32 consecutive entries; 2: one float4 atomic per lane at a random 16 B slot
+__global__ void __launch_bounds__(256) bench_scatter_kernel(float2 *__restrict__ table, uint32_t entries, int64_t n,
+                                                            int per_thread, int mode) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t lane = threadIdx.x & 31;
+    // 5: all 32 lanes the SAME entry; 6: runs of 4 lanes the same entry; 7: runs of 2 lanes the same entry
+    const uint32_t grp = (mode == 1 || mode == 7) ? (uint32_t)(i >> 1) : (mode == 3 || mode == 6) ? (uint32_t)(i >> 2) : (mode == 4 || mode == 5) ? (uint32_t)(i >> 5) : (uint32_t)i;
+    uint32_t h = mix32(grp * 2654435761u + 12345u);
+    for (int k = 0; k < per_thread; ++k) {
+        h = mix32(h + k);
+        uint32_t e = h % entries;
+        if (mode == 1) e = (e & ~1u) | (lane & 1u);
+        else if (mode == 3) e = (e & ~3u) | (lane & 3u);
+        else if (mode == 4) e = (e & ~31u) | lane;
+        if (mode == 2) atomicAdd(reinterpret_cast<float4 *>(table + (e & ~1u)), make_float4(1.0f, 0.5f, 0.25f, 2.0f));
+        else atomicAdd(table + e, make_float2(1.0f, 0.5f));
+    }
 }
 
 static int check_grid(const usl_grid_t *g) {
@@ -163,6 +204,17 @@ int usl_grid_encode_bwd_input(const usl_grid_t *g, const float *params, const fl
     encode_bwd_input_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         *g, (const float2 *)params, x, (const float2 *)dy, n, dx);
     return check_launch("usl_grid_encode_bwd_input");
+}
+
+int usl_bench_gather(const float *table, uint32_t entries, int64_t n_threads, int per_thread, float *out,
+                     usl_stream_t stream) {
+    bench_gather_kernel<<<(unsigned)((n_threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float2 *)table, entries, n_threads, per_thread, out);
+    return check_launch("usl_bench_gather");
+}
+
+int usl_bench_scatter(float *table, uint32_t entries, int64_t n_threads, int per_thread, int mode, usl_stream_t stream) {
+    bench_scatter_kernel<<<(unsigned)((n_threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>((float2 *)table, entries, n_threads, per_thread, mode);
+    return check_launch("usl_bench_scatter");
 }
 
 int usl_grid_corner_indices(const usl_grid_t *g, const float *x, int64_t n, uint32_t *idx, usl_stream_t stream) {

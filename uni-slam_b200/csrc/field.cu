@@ -4,6 +4,7 @@
 // tcnn.Encoding calls + two tcnn.Network / nn.Linear stacks, together with the point construction
 // and normalisation of src/utils/Renderer.py:132-137.  blockIdx.y selects the grid (0 sdf, 1 colour)
 // so each thread carries one decoder's registers and the two grids run as independent CTAs.
+#include <cstdlib>
 #include <cstring>
 
 #include "usl_field.cuh"
@@ -53,9 +54,11 @@ __global__ void __launch_bounds__(256) field_fwd_kernel(const __grid_constant__ 
     if (!load_point(A.p, A.f, i, xc, gate)) return;
     const usl_grid_t &g = A.f.grid[gi];
     float out[4], tout[4][3];
+    // stash layout: features [2][L][n][2] then hidden pre-activations [2][16][n]
     float2 *fo = SAVE_FEAT ? reinterpret_cast<float2 *>(A.feat) + ((int64_t)gi * g.n_levels) * A.p.n + i : nullptr;
+    float *ho = SAVE_FEAT ? A.feat + (int64_t)2 * USL_IN * A.p.n + ((int64_t)gi * USL_HID) * A.p.n + i : nullptr;
     decode_point<WITH_JAC, SAVE_FEAT>(g, reinterpret_cast<const float2 *>(A.f.table[gi]), A.f.mlp[gi], sm, xc, fo,
-                                      A.p.n, out, tout);
+                                      A.p.n, out, tout, ho);
     if (gi == 0) {
         A.raw[i * 4 + 3] = out[0];
         if (WITH_JAC) {
@@ -140,12 +143,13 @@ struct FieldBwdArgs {
     float *grad_table[2];
     usl_mlp_t gm[2];
     int has_gm;
+    int dbg;              // development switches (USL_DEBUG_BWD): 1 = skip scatter, 2 = skip weight-gradient tiles
     float *dh;            // stand-alone decoder mode: [n,32] gradient wrt the input features (nullable)
 };
 
 // STANDALONE: tinycudann.Network seam -- feat is h[n,32] (row-major), raw/d_raw are [n,n_out], no scatter.
 template <int NH, bool STANDALONE>
-__global__ void __launch_bounds__(BWD_THREADS) field_bwd_kernel(const __grid_constant__ FieldBwdArgs A) {
+__global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? 6 : 3) field_bwd_kernel(const __grid_constant__ FieldBwdArgs A) {
     __shared__ MlpSmem sm;
     __shared__ __align__(16) float tiles[BWD_WARPS][32][TILE_STRIDE];
     const int gi = blockIdx.y;
@@ -163,31 +167,33 @@ __global__ void __launch_bounds__(BWD_THREADS) field_bwd_kernel(const __grid_con
     bool active = (i < n);
     if (!STANDALONE) active = active && load_point(A.p, A.f, i, xc, gate);
 
-    // ---- recompute the decoder forward from the saved features ----
-    float f[USL_IN];
+    // ---- hidden pre-activations: stashed by the forward pass (fused) or recomputed from h (stand-alone) ----
     float h1[USL_HID];
-#pragma unroll
-    for (int j = 0; j < USL_HID; ++j) h1[j] = sm.b1[j];
     const float2 *fin = STANDALONE ? reinterpret_cast<const float2 *>(A.feat) + (active ? i : 0) * (USL_IN / 2)
                                    : reinterpret_cast<const float2 *>(A.feat) + ((int64_t)gi * L) * n + (active ? i : 0);
     const int64_t fstride = STANDALONE ? 1 : n;
+    if (STANDALONE) {
 #pragma unroll
-    for (int l = 0; l < USL_IN / 2; ++l) {
-        float2 v = make_float2(0.f, 0.f);
-        if (active && l < L) v = __ldg(fin + (int64_t)l * fstride);
-        f[2 * l] = v.x; f[2 * l + 1] = v.y;
-    }
+        for (int j = 0; j < USL_HID; ++j) h1[j] = sm.b1[j];
 #pragma unroll
-    for (int k = 0; k < USL_IN; ++k) {
-        const float4 *w = reinterpret_cast<const float4 *>(sm.w1t[k]);
+        for (int l = 0; l < USL_IN / 2; ++l) {
+            float2 v = make_float2(0.f, 0.f);
+            if (active) v = __ldg(fin + (int64_t)l * fstride);
+            const float4 *wa = reinterpret_cast<const float4 *>(sm.w1t[2 * l]);
+            const float4 *wb = reinterpret_cast<const float4 *>(sm.w1t[2 * l + 1]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 a = w[q];
-            h1[q * 4 + 0] = fmaf(a.x, f[k], h1[q * 4 + 0]);
-            h1[q * 4 + 1] = fmaf(a.y, f[k], h1[q * 4 + 1]);
-            h1[q * 4 + 2] = fmaf(a.z, f[k], h1[q * 4 + 2]);
-            h1[q * 4 + 3] = fmaf(a.w, f[k], h1[q * 4 + 3]);
+            for (int q = 0; q < 4; ++q) {
+                const float4 a = wa[q], b = wb[q];
+                h1[q * 4 + 0] = fmaf(b.x, v.y, fmaf(a.x, v.x, h1[q * 4 + 0]));
+                h1[q * 4 + 1] = fmaf(b.y, v.y, fmaf(a.y, v.x, h1[q * 4 + 1]));
+                h1[q * 4 + 2] = fmaf(b.z, v.y, fmaf(a.z, v.x, h1[q * 4 + 2]));
+                h1[q * 4 + 3] = fmaf(b.w, v.y, fmaf(a.w, v.x, h1[q * 4 + 3]));
+            }
         }
+    } else {
+        const float *hin = A.feat + (int64_t)2 * USL_IN * n + ((int64_t)gi * USL_HID) * n + (active ? i : 0);
+#pragma unroll
+        for (int j = 0; j < USL_HID; ++j) h1[j] = active ? __ldg(hin + (int64_t)j * n) : 0.f;
     }
     // output-side gradient
     float du[4] = {0.f, 0.f, 0.f, 0.f};
@@ -239,16 +245,21 @@ __global__ void __launch_bounds__(BWD_THREADS) field_bwd_kernel(const __grid_con
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc2[q] = 0.f;
     acco[0] = acco[1] = 0.f;
-    if (A.has_gm) {
+    if (A.has_gm && !(A.dbg & 2)) {
         float4 *row = reinterpret_cast<float4 *>(tile[lane]);
         // phase 1: [0:16] dh1, [16:48] f
 #pragma unroll
         for (int q = 0; q < 4; ++q) row[q] = make_float4(dh1[4 * q], dh1[4 * q + 1], dh1[4 * q + 2], dh1[4 * q + 3]);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) row[4 + q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        for (int q = 0; q < 8; ++q) {     // features go global -> shared without living in registers
+            float2 u0 = make_float2(0.f, 0.f), u1 = u0;
+            if (active) { u0 = __ldg(fin + (int64_t)(2 * q) * fstride); u1 = __ldg(fin + (int64_t)(2 * q + 1) * fstride); }
+            row[4 + q] = make_float4(u0.x, u0.y, u1.x, u1.y);
+        }
         __syncwarp();
         {
             const int j = lane >> 1, k0 = (lane & 1) * 16;
+#pragma unroll 4
             for (int p = 0; p < 32; ++p) {
                 const float d = tile[p][j];
                 const float4 *fr = reinterpret_cast<const float4 *>(&tile[p][16 + k0]);
@@ -277,6 +288,7 @@ __global__ void __launch_bounds__(BWD_THREADS) field_bwd_kernel(const __grid_con
         {
             const int r2 = lane >> 1, j0 = (lane & 1) * 8;
             const int o = lane >> 3, i0 = (lane & 7) * 2;
+#pragma unroll 4
             for (int p = 0; p < 32; ++p) {
                 if (NH == 2) {
                     const float d = tile[p][r2];
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(BWD_THREADS) field_bwd_kernel(const __grid_con
     }
 
     // ---- hash-table gradient scatter: d f_l = W1[:, 2l:2l+2]^T dh1, then 8 vector atomics ----
-    if (STANDALONE ? (active && A.dh != nullptr) : (active && A.grad_table[gi] != nullptr)) {
+    if (!(A.dbg & 1) && (STANDALONE ? (active && A.dh != nullptr) : (active && A.grad_table[gi] != nullptr))) {
         float2 *gt = STANDALONE ? nullptr : reinterpret_cast<float2 *>(A.grad_table[gi]);
         for (int l = 0; l < L; ++l) {
             float dfx = 0.f, dfy = 0.f;
@@ -326,9 +338,7 @@ __global__ void __launch_bounds__(BWD_THREADS) field_bwd_kernel(const __grid_con
             float wt[8];
             corner_indices(lv, c, idx);
             corner_weights(c, wt);
-            float2 *tab = gt + lv.offset;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) atomicAdd(tab + idx[k], make_float2(wt[k] * dfx, wt[k] * dfy));
+            scatter_level(gt + lv.offset, idx, wt, dfx, dfy);
         }
     }
 
@@ -465,6 +475,7 @@ int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw,
     A.grad_table[0] = grad_table_sdf; A.grad_table[1] = grad_table_rgb;
     A.has_gm = gm ? 1 : 0;
     A.dh = nullptr;
+    { const char *e = getenv("USL_DEBUG_BWD"); A.dbg = e ? atoi(e) : 0; }
     if (gm) { A.gm[0] = gm[0]; A.gm[1] = gm[1]; }
     dim3 grid((unsigned)((p->n + BWD_THREADS - 1) / BWD_THREADS), 2);
     cudaStream_t s = (cudaStream_t)stream;

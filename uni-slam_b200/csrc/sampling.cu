@@ -116,46 +116,48 @@ __global__ void __launch_bounds__(256) bbox_prefilter_kernel(const float *__rest
     }
 }
 
-// ---- depth-guided z sampling: thread per ray, two-pointer merge of two ascending sequences ----
-__global__ void __launch_bounds__(128) zsample_depth_kernel(usl_zsample_args_t a, const float *__restrict__ gt_depth,
-                                                            const uint8_t *__restrict__ valid,
-                                                            const float *__restrict__ t_rand,
-                                                            const int32_t *__restrict__ row_map, int64_t n_rays,
-                                                            float *__restrict__ z) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rays) return;
-    if (valid && !valid[r]) return;
-    const float gt = gt_depth[r];
-    if (!(gt > 0.f)) return;
+// ---- depth-guided z sampling: one thread per (ray, sample); merge by rank, perturb through shared memory ----
+#define ZS_RAYS_PER_BLOCK 8
+__global__ void zsample_depth_kernel(usl_zsample_args_t a, const float *__restrict__ gt_depth,
+                                     const uint8_t *__restrict__ valid, const float *__restrict__ t_rand,
+                                     const int32_t *__restrict__ row_map, int64_t n_rays, float *__restrict__ z) {
+    extern __shared__ float sz[];   // [ZS_RAYS_PER_BLOCK][S] merged (sorted) samples
     const int ns = a.n_stratified, ni = a.n_importance, S = ns + ni;
-    float *zr = z + r * S;
+    const int rl = threadIdx.x / S, k = threadIdx.x - rl * S;
+    const int64_t r = (int64_t)blockIdx.x * ZS_RAYS_PER_BLOCK + rl;
+    float gt = 0.f;
+    bool live = r < n_rays && (!valid || valid[r]);
+    if (live) { gt = gt_depth[r]; live = gt > 0.f; }
     // z_free_i = 0.0 + (1.2*gt)*t_uni[i] ; z_surf_j = (gt - 1.5tr) + (3tr * t_surf[j])     (Renderer.py:91-95)
     const float g12 = __fmul_rn(1.2f, gt);
     const float s0 = __fsub_rn(gt, a.c_surf_lo);
-    int i = 0, j = 0;
-    float fi = __fadd_rn(0.0f, __fmul_rn(g12, a.t_uni[0]));
-    float sj = __fadd_rn(s0, __fmul_rn(a.c_surf_span, a.t_surf[0]));
-    for (int k = 0; k < S; ++k) {
-        const bool take_free = (j >= ni) || (i < ns && fi <= sj);
-        if (take_free) {
-            zr[k] = fi; ++i;
-            if (i < ns) fi = __fadd_rn(0.0f, __fmul_rn(g12, a.t_uni[i]));
+    if (live) {
+        float v;
+        int rank;
+        if (k < ns) {           // rank among the merged list: equal values keep the free sample first (== stable two-pointer merge)
+            v = __fadd_rn(0.0f, __fmul_rn(g12, a.t_uni[k]));
+            rank = k;
+            for (int j = 0; j < ni; ++j) rank += (__fadd_rn(s0, __fmul_rn(a.c_surf_span, a.t_surf[j])) < v) ? 1 : 0;
         } else {
-            zr[k] = sj; ++j;
-            if (j < ni) sj = __fadd_rn(s0, __fmul_rn(a.c_surf_span, a.t_surf[j]));
+            const int j0 = k - ns;
+            v = __fadd_rn(s0, __fmul_rn(a.c_surf_span, a.t_surf[j0]));
+            rank = j0;
+            for (int i = 0; i < ns; ++i) rank += (__fadd_rn(0.0f, __fmul_rn(g12, a.t_uni[i])) <= v) ? 1 : 0;
         }
+        sz[rl * S + rank] = v;
     }
-    if (t_rand) {   // Renderer.perturbation (Renderer.py:42-57), in place with the original neighbours in registers
-        const float *tr = t_rand + (int64_t)(row_map ? row_map[r] : r) * S;
-        float prev = 0.f, cur = zr[0];
-        for (int k = 0; k < S; ++k) {
-            const float next = (k + 1 < S) ? zr[k + 1] : cur;
-            const float lower = (k == 0) ? cur : __fmul_rn(0.5f, __fadd_rn(cur, prev));
-            const float upper = (k == S - 1) ? cur : __fmul_rn(0.5f, __fadd_rn(next, cur));
-            zr[k] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr[k]));
-            prev = cur; cur = next;
-        }
+    __syncthreads();
+    if (!live) return;
+    const float *zr = sz + rl * S;
+    float out = zr[k];
+    if (t_rand) {   // Renderer.perturbation (Renderer.py:42-57)
+        const float cur = out;
+        const float lower = (k == 0) ? cur : __fmul_rn(0.5f, __fadd_rn(cur, zr[k - 1]));
+        const float upper = (k == S - 1) ? cur : __fmul_rn(0.5f, __fadd_rn(zr[k + 1], cur));
+        const float t = t_rand[(int64_t)(row_map ? row_map[r] : r) * S + k];
+        out = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t));
     }
+    z[r * S + k] = out;
 }
 
 // ---- no-depth rays: uniform samples to the bbox exit + inverse-CDF resampling from an SDF query ----
@@ -175,13 +177,14 @@ struct NoDepthArgs {
 __global__ void __launch_bounds__(128) zsample_nodepth_kernel(const __grid_constant__ NoDepthArgs A) {
     __shared__ MlpSmem sm;
     __shared__ float s_z[4][ND_MAX_STRAT], s_w[4][ND_MAX_STRAT], s_cdf[4][ND_MAX_STRAT], s_smp[4][ND_MAX_IMP];
-    stage_mlp(A.f.mlp[0], sm);
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r = (int64_t)blockIdx.x * 4 + warp;
-    if (r >= A.n_rays) return;
-    if (A.valid && !A.valid[r]) return;
-    if (A.gt_depth[r] > 0.f) return;                      // handled by zsample_depth (gt_mask, Renderer.py:83)
+    // only rays with gt_depth == 0 take this branch (gt_mask, Renderer.py:83,104): skip the weight staging otherwise
+    const bool mine = r < A.n_rays && (!A.valid || A.valid[r]) && !(A.gt_depth[r] > 0.f);
+    if (!__syncthreads_or(mine ? 1 : 0)) return;
+    stage_mlp(A.f.mlp[0], sm);
+    __syncthreads();
+    if (!mine) return;
     const int ns = A.a.n_stratified, ni = A.a.n_importance, S = ns + ni;
     const int row = A.row_map ? A.row_map[r] : (int)r;
     float *zs = s_z[warp], *ws = s_w[warp], *cdf = s_cdf[warp], *smp = s_smp[warp];
@@ -325,8 +328,10 @@ int usl_zsample_depth(const usl_zsample_args_t *a, const float *gt_depth, const 
                       const int32_t *row_map, int64_t n_rays, float *z, usl_stream_t stream) {
     if (n_rays <= 0) return 0;
     if (!a || a->n_stratified < 1 || a->n_importance < 1) { set_error("usl_zsample_depth: bad arguments"); return 1; }
-    zsample_depth_kernel<<<(unsigned)((n_rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*a, gt_depth, valid, t_rand, row_map,
-                                                                                             n_rays, z);
+    const int S = a->n_stratified + a->n_importance;
+    if (S > 128) { set_error("usl_zsample_depth: n_stratified + n_importance must be <= 128"); return 1; }
+    zsample_depth_kernel<<<(unsigned)((n_rays + ZS_RAYS_PER_BLOCK - 1) / ZS_RAYS_PER_BLOCK), ZS_RAYS_PER_BLOCK * S,
+                           ZS_RAYS_PER_BLOCK * S * sizeof(float), (cudaStream_t)stream>>>(*a, gt_depth, valid, t_rand, row_map, n_rays, z);
     return check_launch("usl_zsample_depth");
 }
 

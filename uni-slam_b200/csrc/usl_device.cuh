@@ -80,6 +80,28 @@ __device__ __forceinline__ void corner_weights(const Cell &c, float wt[8]) {
 
 __device__ __forceinline__ float2 ldg2(const float2 *p) { return __ldg(p); }
 
+// Gradient scatter of one level: 8 corners = 4 x-pairs.  The two corners of an x-pair land in the same
+// 16-byte slot whenever their indices differ only in bit 0 (dense levels: even base index; CoherentPrime hash:
+// even g_x, because the x coefficient is 1) -- then ONE 16-byte vector atomic replaces two 8-byte ones.
+// L2 atomic throughput on B200 is per 32-byte sector operation (tools/microbench.py), so this removes 25 % of them.
+__device__ __forceinline__ void scatter_level(float2 *__restrict__ tab, const uint32_t idx[8], const float wt[8],
+                                              float dfx, float dfy) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const uint32_t i0 = idx[2 * p], i1 = idx[2 * p + 1];
+        const float2 v0 = make_float2(wt[2 * p] * dfx, wt[2 * p] * dfy);
+        const float2 v1 = make_float2(wt[2 * p + 1] * dfx, wt[2 * p + 1] * dfy);
+        if ((i0 ^ i1) == 1u) {
+            const bool lo_first = (i0 & 1u) == 0u;
+            const float4 v = lo_first ? make_float4(v0.x, v0.y, v1.x, v1.y) : make_float4(v1.x, v1.y, v0.x, v0.y);
+            atomicAdd(reinterpret_cast<float4 *>(tab + (i0 & ~1u)), v);
+        } else {
+            atomicAdd(tab + i0, v0);
+            atomicAdd(tab + i1, v1);
+        }
+    }
+}
+
 // Gather the 8 corners of one level and interpolate; optionally the d f / d x tangents.
 template <bool WITH_JAC>
 __device__ __forceinline__ void level_interp(const usl_level_t &lv, const float2 *__restrict__ table,

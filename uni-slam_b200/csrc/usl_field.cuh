@@ -9,7 +9,7 @@ template <bool WITH_JAC, bool SAVE_FEAT>
 __device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *__restrict__ table,
                                              const usl_mlp_t &m, const MlpSmem &sm, const float xc[3],
                                              float2 *__restrict__ feat_out, int64_t feat_stride,
-                                             float out[4], float tout[4][3]) {
+                                             float out[4], float tout[4][3], float *__restrict__ h1_out = nullptr) {
     float h[USL_HID];
     float th[WITH_JAC ? 3 : 1][USL_HID];
 #pragma unroll
@@ -41,6 +41,10 @@ __device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *
                 }
             }
         }
+    }
+    if (SAVE_FEAT && h1_out) {   // hidden pre-activations kept for the backward pass: [16][n]
+#pragma unroll
+        for (int j = 0; j < USL_HID; ++j) h1_out[(int64_t)j * feat_stride] = h[j];
     }
 #pragma unroll
     for (int j = 0; j < USL_HID; ++j) {

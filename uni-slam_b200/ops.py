@@ -160,7 +160,7 @@ class _FieldPointsFn(torch.autograd.Function):
         need_p = any(ctx.needs_input_grad[2:])
         need_x = ctx.needs_input_grad[1]
         raw = torch.empty((n, 4), device=x.device, dtype=torch.float32)
-        feat = torch.empty((2, N_LEVELS, n, 2), device=x.device, dtype=torch.float32) if need_p else None
+        feat = torch.empty((2 * (C_DIM + HIDDEN) * n,), device=x.device, dtype=torch.float32) if need_p else None
         jac = torch.empty((n, 12), device=x.device, dtype=torch.float32) if need_x else None
         f = meta.pack(sdf_table, rgb_table, dec)
         pts = _points_from_x(x)
@@ -215,7 +215,7 @@ class _RenderFn(torch.autograd.Function):
         need_rays = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         need_p = any(ctx.needs_input_grad[5:])
         raw = torch.empty((R, S, 4), device=dev, dtype=torch.float32)
-        feat = torch.empty((2, N_LEVELS, R * S, 2), device=dev, dtype=torch.float32) if need_p else None
+        feat = torch.empty((2 * (C_DIM + HIDDEN) * R * S,), device=dev, dtype=torch.float32) if need_p else None
         jac = torch.empty((R * S, 12), device=dev, dtype=torch.float32) if need_rays else None
         f = meta.pack(sdf_table, rgb_table, dec)
         pts = _points_from_rays(rays_o, rays_d, z_vals)
