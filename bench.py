@@ -285,12 +285,14 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
     evs = []
     barrier()
+    torch.cuda.nvtx.range_push("usl_timed")           # ncu --nvtx --nvtx-include "usl_timed/" isolates the timed region
     for _ in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); run_step(); e1.record()
         evs.append((e0, e1))
     barrier()
+    torch.cuda.nvtx.range_pop()
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = sum(step_ms)
     # back-to-back (L2-warm) variant, one bracket around K steps

@@ -64,7 +64,7 @@ class MappingWorkload:
 
 def _matrix_to_cam_pose(c2w: torch.Tensor) -> torch.Tensor:
     """Host-side pose helper (common.py:182-194) -- only used to seed the synthetic workload."""
-    from .compat.pytorch3d.transforms import matrix_to_quaternion
+    from .compat_pytorch3d.pytorch3d.transforms import matrix_to_quaternion
     return torch.cat([matrix_to_quaternion(c2w[:, :3, :3]), c2w[:, :3, 3]], dim=-1)
 
 
