@@ -242,6 +242,19 @@ USL_API int usl_pose_matrix_bwd(const float *pose, const float *d_c2w, int K, fl
 USL_API int usl_sdf_query_grid(const usl_field_t *f, const float *ax, const float *ay, const float *az, int nx,
                        int ny, int nz, int y_begin, int y_end, float *out, usl_stream_t stream);
 
+/* ---- a-12 / f1: optimiser step (torch.optim.Adam of src/Mapper.py:358-364,445, src/Tracker.py:324-329,242) ----- */
+#define USL_ADAM_MAX_GROUPS 24
+typedef struct usl_adam_group {
+    float *param, *grad, *exp_avg, *exp_avg_sq; /* device, n floats each */
+    int64_t n;
+    float lr, beta1, beta2, eps;
+} usl_adam_group_t;
+/* One fused launch over all groups; same update rule as torch.optim.Adam (no weight decay / amsgrad).
+ * step: 1-based step count of this update (bias correction); step_dev (nullable): device int64 holding it instead
+ * (CUDA-graph replay). zero_grad != 0 also clears the gradients (replaces optimizer.zero_grad + tcnn's memset). */
+USL_API int usl_adam_step(const usl_adam_group_t *groups, int n_groups, int64_t step, const int64_t *step_dev,
+                          int zero_grad, usl_stream_t stream);
+
 /* ---- measurement utilities (no reference counterpart): ceilings for the roofline discussion ---- */
 /* n_threads threads each issue per_thread random 8-byte loads from / vector atomics into table[entries*2] */
 USL_API int usl_bench_gather(const float *table, uint32_t entries, int64_t n_threads, int per_thread, float *out,

@@ -252,3 +252,28 @@ def test_dense_sdf_query_matches_oracle():
     assert out.shape == ref.shape
     assert torch.equal(out == -1, ref == -1)                              # strict in-bound mask identical
     assert (out - ref).abs().max() < 2e-5
+
+
+def test_fused_adam_matches_torch_adam():
+    """a-12 / f1: usl_adam_step vs torch.optim.Adam with the host code's group structure (Mapper.py:111-139; Tracker betas)."""
+    P = pkg()
+    g = torch.Generator().manual_seed(0)
+    shapes = [(768,), (100003,), (16, 32), (1,), (20, 7)]
+    ref = [torch.randn(s, generator=g).to(DEV).requires_grad_(True) for s in shapes]
+    ours = [r.detach().clone().requires_grad_(True) for r in ref]
+    mk = lambda ps: [{"params": [ps[0], ps[2], ps[3]], "lr": 1e-3}, {"params": [ps[1]], "lr": 0.05},
+                     {"params": [ps[4]], "lr": 2e-3, "betas": (0.5, 0.999)}]
+    o_ref = torch.optim.Adam(mk(ref))
+    o_our = P.FusedAdam(mk(ours))
+    for it in range(5):
+        for r, o in zip(ref, ours):
+            gr = torch.randn(r.shape, generator=g).to(DEV) * (10.0 ** (it - 2))
+            gr[gr.abs() < 0.3 * gr.abs().max()] = 0                     # sparse gradients like the hash tables'
+            r.grad = gr.clone(); o.grad = gr.clone()
+        o_ref.step(); o_our.step()
+    for r, o in zip(ref, ours):
+        assert rel_err(o.detach().cpu(), r.detach().cpu()) < 1e-6
+    # fused gradient zeroing
+    o_z = P.FusedAdam(mk(ours), zero_grad_in_step=True)
+    o_z.step()
+    assert all(float(o.grad.abs().max()) == 0 for o in ours)

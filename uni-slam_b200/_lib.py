@@ -55,6 +55,12 @@ class LossArgs(Structure):
                 ("w_sdf_tail", c_float), ("w_depth", c_float), ("w_color", c_float), ("mode", c_int32)]
 
 
+class AdamGroup(Structure):
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("n", c_int64),
+                ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float)]
+
+
+ADAM_MAX_GROUPS = 24
 _P = c_void_p
 _SIGS = {
     "usl_grid_build": [c_int, c_int, c_int, c_double, POINTER(Grid)],
@@ -84,6 +90,7 @@ _SIGS = {
     "usl_pose_to_matrix": [_P, c_int, _P, _P],
     "usl_pose_matrix_bwd": [_P, _P, c_int, _P, _P],
     "usl_sdf_query_grid": [POINTER(Field), _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "usl_adam_step": [POINTER(AdamGroup), c_int, c_int64, _P, c_int, _P],
     "usl_bench_gather": [_P, c_uint32, c_int64, c_int, _P, _P],
     "usl_bench_scatter": [_P, c_uint32, c_int64, c_int, c_int, _P],
 }

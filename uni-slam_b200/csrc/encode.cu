@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) encode_fwd_kernel(usl_grid_t g, const flo
     const int l = blockIdx.y;
     const float x0 = x[i * 3 + 0], x1 = x[i * 3 + 1], x2 = x[i * 3 + 2];
     float2 f, df[3];
-    level_interp<false>(g.levels[l], table, x0, x1, x2, f, df);
+    level_interp<false, true>(g.levels[l], table, x0, x1, x2, f, df);
     y[i * g.n_levels + l] = f;
 }
 
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) encode_bwd_input_kernel(usl_grid_t g, con
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     for (int l = 0; l < g.n_levels; ++l) {
         float2 f, df[3];
-        level_interp<true>(g.levels[l], table, x0, x1, x2, f, df);
+        level_interp<true, true>(g.levels[l], table, x0, x1, x2, f, df);
         const float2 d = dy[i * g.n_levels + l];
         a0 += d.x * df[0].x + d.y * df[0].y;
         a1 += d.x * df[1].x + d.y * df[1].y;

@@ -149,7 +149,10 @@ struct FieldBwdArgs {
 
 // STANDALONE: tinycudann.Network seam -- feat is h[n,32] (row-major), raw/d_raw are [n,n_out], no scatter.
 template <int NH, bool STANDALONE>
-__global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? 6 : 3) field_bwd_kernel(const __grid_constant__ FieldBwdArgs A) {
+#ifndef USL_BWD_MINB
+#define USL_BWD_MINB 5
+#endif
+__global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field_bwd_kernel(const __grid_constant__ FieldBwdArgs A) {
     __shared__ MlpSmem sm;
     __shared__ __align__(16) float tiles[BWD_WARPS][32][TILE_STRIDE];
     const int gi = blockIdx.y;
@@ -316,7 +319,17 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? 6 : 3) field_bwd_kernel
     // ---- hash-table gradient scatter: d f_l = W1[:, 2l:2l+2]^T dh1, then 8 vector atomics ----
     if (!(A.dbg & 1) && (STANDALONE ? (active && A.dh != nullptr) : (active && A.grad_table[gi] != nullptr))) {
         float2 *gt = STANDALONE ? nullptr : reinterpret_cast<float2 *>(A.grad_table[gi]);
-        for (int l = 0; l < L; ++l) {
+        // warps walk the levels in rotated order so the atomics in flight at any instant spread over all levels'
+        // sectors instead of hammering the few sectors of one coarse level (L2 same-sector RMW turnaround)
+        const int rot = (int)(((blockIdx.x * BWD_WARPS + warp) * 5u) % (unsigned)L);
+#ifndef USL_BWD_UNROLL
+#define USL_BWD_UNROLL 2
+#endif
+        constexpr int kScatterUnroll = USL_BWD_UNROLL;   // two levels' address chains in flight per thread
+#pragma unroll kScatterUnroll
+        for (int it = 0; it < L; ++it) {
+            int l = it + rot;
+            if (l >= L) l -= L;
             float dfx = 0.f, dfy = 0.f;
             const float4 *wa = reinterpret_cast<const float4 *>(sm.w1t[2 * l]);
             const float4 *wb = reinterpret_cast<const float4 *>(sm.w1t[2 * l + 1]);

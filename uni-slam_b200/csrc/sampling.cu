@@ -225,8 +225,8 @@ __global__ void __launch_bounds__(128) zsample_nodepth_kernel(const __grid_const
             xc[q] = fminf(fmaxf(xn, 0.f), 1.f);
         }
         float out[4], tout[4][3];
-        decode_point<false, false>(A.f.grid[0], reinterpret_cast<const float2 *>(A.f.table[0]), A.f.mlp[0], sm, xc,
-                                   nullptr, 0, out, tout);
+        decode_point<false, false, 8>(A.f.grid[0], reinterpret_cast<const float2 *>(A.f.table[0]), A.f.mlp[0], sm, xc,
+                                      nullptr, 0, out, tout);    // latency-bound (few rays): 8 levels of gathers in flight
         const float sg = 1.0f / (1.0f + expf(out[0] * beta));                        // sigmoid(-sdf*beta)
         ws[k] = 1.0f - expf(-beta * sg);                                             // alpha (Renderer.py:154-158)
     }

@@ -103,7 +103,11 @@ __device__ __forceinline__ void scatter_level(float2 *__restrict__ tab, const ui
 }
 
 // Gather the 8 corners of one level and interpolate; optionally the d f / d x tangents.
-template <bool WITH_JAC>
+// TCNN_ORDER = true reproduces tcnn's corner loop (8 weights, fma chain) for the stand-alone Encoding seam;
+// false evaluates the same trilinear polynomial as nested lerps (x, then y, then z): 14 ops per feature instead
+// of ~26, and the tangents fall out of the differences already formed (6+2+0 extra ops). Results agree to a few
+// ulp (the <=1e-6 feature tolerance of the parity gate); cell indices are identical by construction.
+template <bool WITH_JAC, bool TCNN_ORDER = false>
 __device__ __forceinline__ void level_interp(const usl_level_t &lv, const float2 *__restrict__ table,
                                              float x0, float x1, float x2, float2 &f, float2 df[3]) {
     const Cell c = make_cell(lv, x0, x1, x2);
@@ -113,33 +117,39 @@ __device__ __forceinline__ void level_interp(const usl_level_t &lv, const float2
     float2 v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = ldg2(tab + idx[k]);
-    float wt[8];
-    corner_weights(c, wt);
-    f.x = 0.f; f.y = 0.f;
+    if (TCNN_ORDER) {
+        float wt[8];
+        corner_weights(c, wt);
+        f.x = 0.f; f.y = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        f.x = __fmaf_rn(wt[k], v[k].x, f.x);
-        f.y = __fmaf_rn(wt[k], v[k].y, f.y);
+        for (int k = 0; k < 8; ++k) {
+            f.x = __fmaf_rn(wt[k], v[k].x, f.x);
+            f.y = __fmaf_rn(wt[k], v[k].y, f.y);
+        }
     }
-    if (WITH_JAC) {
-        const float a0 = 1.0f - c.w[0], a1 = 1.0f - c.w[1], a2 = 1.0f - c.w[2];
-        const float b0 = c.w[0], b1 = c.w[1], b2 = c.w[2];
-        const float s = lv.scale;
-        // d/dx0: sum over (c1,c2) of w1*w2*(v[1|..]-v[0|..])
-        {
-            const float w00 = a1 * a2, w10 = b1 * a2, w01 = a1 * b2, w11 = b1 * b2;
-            df[0].x = s * (w00 * (v[1].x - v[0].x) + w10 * (v[3].x - v[2].x) + w01 * (v[5].x - v[4].x) + w11 * (v[7].x - v[6].x));
-            df[0].y = s * (w00 * (v[1].y - v[0].y) + w10 * (v[3].y - v[2].y) + w01 * (v[5].y - v[4].y) + w11 * (v[7].y - v[6].y));
+    if (!TCNN_ORDER || WITH_JAC) {
+        const float w0 = c.w[0], w1 = c.w[1], w2 = c.w[2];
+        float2 dx[4], a[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {                       // along x; p = y + 2 z
+            dx[p] = make_float2(v[2 * p + 1].x - v[2 * p].x, v[2 * p + 1].y - v[2 * p].y);
+            a[p] = make_float2(fmaf(w0, dx[p].x, v[2 * p].x), fmaf(w0, dx[p].y, v[2 * p].y));
         }
-        {
-            const float w00 = a0 * a2, w10 = b0 * a2, w01 = a0 * b2, w11 = b0 * b2;
-            df[1].x = s * (w00 * (v[2].x - v[0].x) + w10 * (v[3].x - v[1].x) + w01 * (v[6].x - v[4].x) + w11 * (v[7].x - v[5].x));
-            df[1].y = s * (w00 * (v[2].y - v[0].y) + w10 * (v[3].y - v[1].y) + w01 * (v[6].y - v[4].y) + w11 * (v[7].y - v[5].y));
+        float2 dy[2], b[2], bx[2];
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {                       // along y
+            dy[z] = make_float2(a[2 * z + 1].x - a[2 * z].x, a[2 * z + 1].y - a[2 * z].y);
+            b[z] = make_float2(fmaf(w1, dy[z].x, a[2 * z].x), fmaf(w1, dy[z].y, a[2 * z].y));
+            if (WITH_JAC)
+                bx[z] = make_float2(fmaf(w1, dx[2 * z + 1].x - dx[2 * z].x, dx[2 * z].x), fmaf(w1, dx[2 * z + 1].y - dx[2 * z].y, dx[2 * z].y));
         }
-        {
-            const float w00 = a0 * a1, w10 = b0 * a1, w01 = a0 * b1, w11 = b0 * b1;
-            df[2].x = s * (w00 * (v[4].x - v[0].x) + w10 * (v[5].x - v[1].x) + w01 * (v[6].x - v[2].x) + w11 * (v[7].x - v[3].x));
-            df[2].y = s * (w00 * (v[4].y - v[0].y) + w10 * (v[5].y - v[1].y) + w01 * (v[6].y - v[2].y) + w11 * (v[7].y - v[3].y));
+        const float2 dz = make_float2(b[1].x - b[0].x, b[1].y - b[0].y);
+        if (!TCNN_ORDER) f = make_float2(fmaf(w2, dz.x, b[0].x), fmaf(w2, dz.y, b[0].y));
+        if (WITH_JAC) {
+            const float s = lv.scale;
+            df[0] = make_float2(s * fmaf(w2, bx[1].x - bx[0].x, bx[0].x), s * fmaf(w2, bx[1].y - bx[0].y, bx[0].y));
+            df[1] = make_float2(s * fmaf(w2, dy[1].x - dy[0].x, dy[0].x), s * fmaf(w2, dy[1].y - dy[0].y, dy[0].y));
+            df[2] = make_float2(s * dz.x, s * dz.y);
         }
     }
 }

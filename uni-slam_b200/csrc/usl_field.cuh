@@ -5,7 +5,7 @@
 namespace usl {
 
 // One decoder on one point. out[o] activated outputs; tout[o][d] = d out / d xc.
-template <bool WITH_JAC, bool SAVE_FEAT>
+template <bool WITH_JAC, bool SAVE_FEAT, int UNR = 1>
 __device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *__restrict__ table,
                                              const usl_mlp_t &m, const MlpSmem &sm, const float xc[3],
                                              float2 *__restrict__ feat_out, int64_t feat_stride,
@@ -17,6 +17,7 @@ __device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *
         h[j] = sm.b1[j];
         if (WITH_JAC) { th[0][j] = 0.f; th[1][j] = 0.f; th[2][j] = 0.f; }
     }
+#pragma unroll UNR
     for (int l = 0; l < g.n_levels; ++l) {
         float2 f, df[3];
         level_interp<WITH_JAC>(g.levels[l], table, xc[0], xc[1], xc[2], f, df);

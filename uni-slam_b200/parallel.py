@@ -1,0 +1,49 @@
+"""Host-side multi-GPU helpers (S§8e): one process per GPU, torch.distributed for the plumbing.
+
+* mapping: ray batches shard across ranks (every rank draws its own batch); two exchange steps per iteration --
+  the 12 loss sums/counts between ``usl_loss_fwd`` and ``usl_loss_bwd`` (so every mean divides by the GLOBAL
+  element count), and one all-reduce of the flat gradient buffer [tables | decoders | beta] (+ pose gradients)
+  after the backward.  Identical Adam on every rank then keeps the replicas in lock-step.
+* dense SDF query: y-slabs of the (ny, nx, nz) volume, no data-path collective, slabs gathered to rank 0.
+* tracking: replicas only (single GPU, BASELINE.json north_star).
+"""
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def slab_range(ny: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous y-slab [begin, end) of rank `rank`; slabs differ by at most one row and tile [0, ny)."""
+    base, rem = divmod(ny, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def attach_mapping_collectives(step, group=None):
+    """Wire the two exchange steps of a sharded mapping iteration onto a MappingStep."""
+    def acc_hook(acc):
+        dist.all_reduce(acc, group=group)
+    step.acc_hook = acc_hook
+
+    def reduce_grads():
+        dist.all_reduce(step.fs.g_all, group=group)
+        dist.all_reduce(step.d_pose, group=group)
+    return reduce_grads
+
+
+def finalize_loss(acc: torch.Tensor, w_fs, w_center, w_tail, w_depth, w_color) -> torch.Tensor:
+    """Host mirror of usl_loss_finalize for logging: loss from the (all-reduced) sums/counts of usl_loss_fwd.
+    Slots: 0 fs 1 center 2 tail 3 depth 4 colour sums; 5 n_front 6 n_center 7 n_tail 8 n_mask 10 n_colour_terms."""
+    return (w_fs * acc[0] / acc[5] + w_center * acc[1] / acc[6] + w_tail * acc[2] / acc[7]
+            + w_color * acc[4] / acc[10] + w_depth * acc[3] / acc[8])
+
+
+def gather_slabs(local: torch.Tensor, ny: int, nx: int, nz: int, rank: int, world: int, group=None):
+    """Gather the per-rank (rows*nx*nz,) SDF slabs into the full (ny*nx*nz,) volume on rank 0 (None elsewhere)."""
+    sizes = [(slab_range(ny, r, world)[1] - slab_range(ny, r, world)[0]) * nx * nz for r in range(world)]
+    if world == 1:
+        return local
+    bufs = [torch.empty(s, dtype=local.dtype, device=local.device) for s in sizes] if rank == 0 else None
+    dist.gather(local, bufs, dst=0, group=group)
+    return torch.cat(bufs) if rank == 0 else None

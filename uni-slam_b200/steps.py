@@ -51,16 +51,19 @@ class _FieldState:
         self.meta, self.sdf_table, self.rgb_table, self.dec, self.beta = meta, sdf_table, rgb_table, list(dec), beta
         self.field = meta.pack(sdf_table, rgb_table, self.dec)
         if with_grads:
-            self.g_sdf_table = torch.zeros_like(sdf_table)
-            self.g_rgb_table = torch.zeros_like(rgb_table)
-            # decoder grads + beta grad live in ONE flat buffer so a single memset clears them
-            sizes = [t.numel() for t in self.dec] + [1]
-            self.g_flat = torch.zeros(sum(sizes), device=sdf_table.device, dtype=torch.float32)
+            # every gradient lives in ONE flat buffer [sdf table | colour table | decoders | beta]: a single memset
+            # clears it and (multi-GPU) a single all-reduce sums it.  Table sizes are multiples of 16 floats, so the
+            # 16-byte vector atomics stay aligned.
+            sizes = [sdf_table.numel(), rgb_table.numel()] + [t.numel() for t in self.dec] + [1]
+            self.g_all = torch.zeros(sum(sizes), device=sdf_table.device, dtype=torch.float32)
             views, o = [], 0
-            for t, s in zip(self.dec + [beta], sizes):
-                views.append(self.g_flat[o:o + s].view(t.shape if t is not beta else (1,)))
-                o += s
-            self.g_dec, self.g_beta = views[:-1], views[-1]
+            for s_ in sizes:
+                views.append(self.g_all[o:o + s_])
+                o += s_
+            self.g_sdf_table, self.g_rgb_table = views[0], views[1]
+            self.g_dec = [v.view(t.shape) for v, t in zip(views[2:-1], self.dec)]
+            self.g_beta = views[-1]
+            self.g_flat = self.g_all[sizes[0] + sizes[1]:]          # decoder + beta gradients
             self.g_mlp = meta.pack_grads(self.g_dec)
 
     def repack(self):
@@ -156,7 +159,7 @@ class MappingStep(_Profiled):
         self._call("usl_loss_bwd", byref(self.loss_args), v(self.raw), v(self.z), v(self.gt_depth), v(self.gt_color), v(self.valid), v(self.mask),
              v(self.depth), v(self.rgb), ptr(self.acc), None, R, S, v(self.g_depth), v(self.g_rgb), v(self.g_sdf), st)
         # ---- backward ----
-        fs.g_flat.zero_(); fs.g_sdf_table.zero_(); fs.g_rgb_table.zero_()
+        fs.g_all.zero_()
         self._call("usl_composite_bwd", v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), R, S, None, None, v(self.g_depth), v(self.g_rgb), None,
              v(self.g_sdf), ptr(self.jac) if joint else None, byref(fs.meta.bound), v(self.d_raw), ptr(fs.g_beta),
              v(self.d_rays_o) if joint else None, v(self.d_rays_d) if joint else None, st)
