@@ -44,6 +44,9 @@ def gather_slabs(local: torch.Tensor, ny: int, nx: int, nz: int, rank: int, worl
     sizes = [(slab_range(ny, r, world)[1] - slab_range(ny, r, world)[0]) * nx * nz for r in range(world)]
     if world == 1:
         return local
-    bufs = [torch.empty(s, dtype=local.dtype, device=local.device) for s in sizes] if rank == 0 else None
-    dist.gather(local, bufs, dst=0, group=group)
-    return torch.cat(bufs) if rank == 0 else None
+    # dist.gather needs equal sizes: pad every slab to the largest one, trim on rank 0
+    mx = max(sizes)
+    padded = local if local.numel() == mx else torch.cat([local, local.new_zeros(mx - local.numel())])
+    bufs = [torch.empty(mx, dtype=local.dtype, device=local.device) for _ in sizes] if rank == 0 else None
+    dist.gather(padded, bufs, dst=0, group=group)
+    return torch.cat([b[:s_] for b, s_ in zip(bufs, sizes)]) if rank == 0 else None
