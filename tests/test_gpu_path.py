@@ -277,3 +277,26 @@ def test_fused_adam_matches_torch_adam():
     o_z = P.FusedAdam(mk(ours), zero_grad_in_step=True)
     o_z.step()
     assert all(float(o.grad.abs().max()) == 0 for o in ours)
+
+
+def test_tcgen05_forward_matches_cuda_core_forward(monkeypatch):
+    """field_tc.cu (tangent contraction on tcgen05 tensor cores, TF32 operands) vs the all-fp32 CUDA-core kernel:
+    identical raw outputs (value path is fp32 in both), Jacobian within the gradient tolerance."""
+    P = pkg()
+    g = load_golden("track_replica")
+    meta, tabs, dec, beta = gpu_cases.cuda_field(g, 50, DEV)
+    n = 128 * 37 + 5                                            # ragged last CTA
+    x = torch.rand(n, 3, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3)) * 1.1 - 0.05   # some points clamp
+    from ctypes import byref
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("USL_TCGEN05", flag)
+        raw = torch.zeros(n, 4, device=DEV); jac = torch.zeros(n, 12, device=DEV)
+        f = meta.pack(tabs[0], tabs[1], dec)
+        pts = P.ops._points_from_x(x)
+        P._lib.call("usl_field_fwd", byref(f), byref(pts), P._lib.ptr(raw), None, P._lib.ptr(jac), P._lib.stream())
+        torch.cuda.synchronize()
+        outs.append((raw.cpu(), jac.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) or (outs[0][0] - outs[1][0]).abs().max() < 1e-6
+    assert rel_err(outs[1][1], outs[0][1]) < 1e-3
+    assert (outs[1][1] - outs[0][1]).abs().max() < 2e-3 * outs[0][1].abs().max()

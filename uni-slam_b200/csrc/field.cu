@@ -450,6 +450,8 @@ static int check_field(const usl_field_t *f, const usl_points_t *p) {
 
 using namespace usl;
 
+int usl_field_fwd_tc_launch(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac, cudaStream_t s);
+
 extern "C" {
 
 int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac,
@@ -460,6 +462,11 @@ int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float
     A.f = *f; A.p = *p; A.raw = raw; A.feat = feat; A.jac = jac; A.sdf = nullptr;
     dim3 grid((unsigned)((p->n + 255) / 256), 2);
     cudaStream_t s = (cudaStream_t)stream;
+    // USL_TCGEN05=1: tangent contraction of the Jacobian path on the tcgen05 tensor cores (field_tc.cu). Parity-tested
+    // and profiled, but not the default: the kernel is bound by L1 sector lookups of the gather,
+    // so moving 57 % of the FMA-pipe work to the tensor pipe does not shorten it (196 us vs 182 us measured).
+    const char *tc_env = getenv("USL_TCGEN05");
+    if (jac && tc_env && tc_env[0] == '1') return usl_field_fwd_tc_launch(f, p, raw, feat, jac, s);
     if (jac && feat) field_fwd_kernel<true, true><<<grid, 256, 0, s>>>(A);
     else if (jac) field_fwd_kernel<true, false><<<grid, 256, 0, s>>>(A);
     else if (feat) field_fwd_kernel<false, true><<<grid, 256, 0, s>>>(A);

@@ -1,0 +1,241 @@
+// field_fwd with the tangent contraction on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// When ray gradients are needed (tracker pose, mapper joint-opt) the forward pass pushes three tangent vectors
+// (d f / d x_0..2, 32 features each) through the first decoder layer: per point a [3 x 32] . [32 x 16] product,
+// 1536 FMAs = 57 % of the CUDA-core FMA-pipe work of field_fwd_kernel<JAC>.  Here a CTA of 128 threads owns 128
+// points = the 128 rows (TMEM lanes) of three M=128, N=16 accumulators; every 4 levels (8 features = one
+// K-step of kind::tf32) each thread writes its three tangent rows into a K-major, un-swizzled shared-memory
+// operand tile and one thread issues 3 tcgen05.mma; tcgen05.ld (32x32b) returns row t to thread t at the end.
+// The VALUE path (h = W1 f + b1) stays in fp32 on the CUDA cores: outputs keep the 1e-4 parity bar, while the
+// tangents only feed gradients (1e-3 bar) where TF32 operands (round-to-nearest, ~2.4e-4 per operand) are ample.
+#include "usl_field.cuh"
+
+namespace usl {
+
+#define TC_THREADS 128      // compute threads = points = accumulator rows per CTA
+#define TC_CTA_THREADS 160  // + one MMA-issuer warp (warp 4): compute warps never block on a CTA-wide barrier
+#define TC_TMEM_COLS 64      // 3 accumulators x 16 fp32 columns, rounded up to a power of two >= 32
+
+struct TcSmem {
+    MlpSmem mlp;
+    alignas(128) uint32_t b[4][2][2][8][4];        // W1 as tf32: [chunk][n-group][k-chunk][n & 7][k & 3]      2 KB
+    alignas(128) uint32_t a[2][3][16][2][8][4];    // tangents:   [buf][dim][row-group][k-chunk][row & 7][k & 3] 24 KB
+    alignas(8) uint64_t full[2];                   // operand buffer written by all 128 compute threads
+    alignas(8) uint64_t empty[2];                  // operand buffer consumed by the tensor core (tcgen05.commit)
+    alignas(8) uint64_t done;                      // all accumulators complete
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE: core matrices of 8 rows x 16 bytes;
+// LBO = byte distance between the two core matrices along K, SBO = between 8-row groups along M/N.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major, N = 16, M = 128
+#define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24))
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct FieldTcArgs {
+    usl_field_t f;
+    usl_points_t p;
+    float *raw, *feat, *jac;
+};
+
+// same point loader as field.cu (kept local: this translation unit is self-contained)
+__device__ __forceinline__ bool tc_load_point(const usl_points_t &p, const usl_field_t &f, int64_t i, float xc[3], float gate[3]) {
+    float x[3];
+    if (p.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x[d] = p.x[i * 3 + d];
+    } else {
+        const int64_t r = i / p.S;
+        if (p.valid && !p.valid[r]) return false;
+        const float z = p.z[i];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x[d] = norm_coord(p.rays_o[r * 3 + d], p.rays_d[r * 3 + d], z, f.bound_lo[d], f.bound_hi[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        xc[d] = fminf(fmaxf(x[d], 0.f), 1.f);
+        gate[d] = (x[d] >= 0.f && x[d] <= 1.f) ? 1.f : 0.f;
+    }
+    return true;
+}
+
+template <bool SAVE_FEAT>
+__global__ void __launch_bounds__(TC_CTA_THREADS, 4) field_fwd_tc_kernel(const __grid_constant__ FieldTcArgs A) {
+    __shared__ TcSmem S;
+    const int gi = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const usl_mlp_t &m = A.f.mlp[gi];
+    stage_mlp(m, S.mlp);
+    // W1[j][k] (row-major, = N x K K-major) -> tf32, UMMA canonical layout per K-chunk of 8
+    for (int e = tid; e < USL_HID * USL_IN; e += TC_CTA_THREADS) {
+        const int j = e / USL_IN, k = e % USL_IN;
+        S.b[k >> 3][j >> 3][(k & 7) >> 2][j & 7][k & 3] = to_tf32(m.w1[e]);
+    }
+    if (tid == 0) {
+        mbar_init(&S.full[0], TC_THREADS); mbar_init(&S.full[1], TC_THREADS);
+        mbar_init(&S.empty[0], 1); mbar_init(&S.empty[1], 1); mbar_init(&S.done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = S.tmem_base;
+
+    if (warp == 4) {
+        // ---- MMA issuer: waits for an operand buffer, issues 3 tcgen05.mma, commits completion to mbarriers ----
+        if (tid == TC_THREADS) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int buf = c & 1;
+                mbar_wait(&S.full[buf], (uint32_t)(c >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t bd = umma_desc(smem_u32(&S.b[c]), 128, 256);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) umma_tf32(tmem + d * 16, umma_desc(smem_u32(&S.a[buf][d]), 128, 256), bd, c > 0 ? 1u : 0u);
+                umma_commit(&S.empty[buf]);
+                if (c == 3) umma_commit(&S.done);
+            }
+        }
+        __syncwarp();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                   // matches the compute warps' final barrier
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+        return;
+    }
+
+    const int64_t n = A.p.n;
+    const int64_t i = (int64_t)blockIdx.x * TC_THREADS + tid;
+    float xc[3] = {0.f, 0.f, 0.f}, gate[3] = {0.f, 0.f, 0.f};
+    const bool active = (i < n) && tc_load_point(A.p, A.f, i, xc, gate);
+    const usl_grid_t &g = A.f.grid[gi];
+    const float2 *table = reinterpret_cast<const float2 *>(A.f.table[gi]);
+    float2 *fo = SAVE_FEAT ? reinterpret_cast<float2 *>(A.feat) + ((int64_t)gi * g.n_levels) * n + i : nullptr;
+
+    float h[USL_HID];
+#pragma unroll
+    for (int j = 0; j < USL_HID; ++j) h[j] = S.mlp.b1[j];
+    const int rg = tid >> 3, rr = tid & 7;
+
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        const int buf = c & 1;
+        uint32_t tv[3][8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int l = 4 * c + q;
+            float2 f = make_float2(0.f, 0.f), df[3] = {f, f, f};
+            if (active) level_interp<true>(g.levels[l], table, xc[0], xc[1], xc[2], f, df);
+            if (SAVE_FEAT && active) fo[(int64_t)l * n] = f;
+            const float4 *wa = reinterpret_cast<const float4 *>(S.mlp.w1t[2 * l]);
+            const float4 *wb = reinterpret_cast<const float4 *>(S.mlp.w1t[2 * l + 1]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float4 a = wa[e], b = wb[e];
+                h[4 * e + 0] = fmaf(b.x, f.y, fmaf(a.x, f.x, h[4 * e + 0]));
+                h[4 * e + 1] = fmaf(b.y, f.y, fmaf(a.y, f.x, h[4 * e + 1]));
+                h[4 * e + 2] = fmaf(b.z, f.y, fmaf(a.z, f.x, h[4 * e + 2]));
+                h[4 * e + 3] = fmaf(b.w, f.y, fmaf(a.w, f.x, h[4 * e + 3]));
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { tv[d][2 * q] = to_tf32(df[d].x); tv[d][2 * q + 1] = to_tf32(df[d].y); }
+        }
+        if (c >= 2) mbar_wait(&S.empty[buf], 0);           // the MMAs of chunk c-2 have consumed this operand buffer
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            *reinterpret_cast<uint4 *>(&S.a[buf][d][rg][0][rr][0]) = make_uint4(tv[d][0], tv[d][1], tv[d][2], tv[d][3]);
+            *reinterpret_cast<uint4 *>(&S.a[buf][d][rg][1][rr][0]) = make_uint4(tv[d][4], tv[d][5], tv[d][6], tv[d][7]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+        mbar_arrive(&S.full[buf]);
+    }
+    if (SAVE_FEAT && active) {
+        float *ho = A.feat + (int64_t)2 * USL_IN * n + ((int64_t)gi * USL_HID) * n + i;
+#pragma unroll
+        for (int j = 0; j < USL_HID; ++j) ho[(int64_t)j * n] = h[j];
+    }
+    mbar_wait(&S.done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float th[3][USL_HID];
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) tmem_ld16(tmem + lane_base + d * 16, th[d]);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+
+    float out[4], tout[4][3];
+    mlp_tail<true>(m, S.mlp, h, th, out, tout);
+    if (active) {
+        if (gi == 0) {
+            A.raw[i * 4 + 3] = out[0];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) A.jac[i * 12 + 9 + d] = tout[0][d] * gate[d];
+        } else {
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                A.raw[i * 4 + o] = out[o];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) A.jac[i * 12 + o * 3 + d] = tout[o][d] * gate[d];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                                       // the issuer warp deallocates TMEM after this barrier
+}
+
+}  // namespace usl
+
+using namespace usl;
+
+// Called by usl_field_fwd (field.cu) when a Jacobian is requested and 16-level grids are used.
+int usl_field_fwd_tc_launch(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac, cudaStream_t s) {
+    FieldTcArgs A;
+    A.f = *f; A.p = *p; A.raw = raw; A.feat = feat; A.jac = jac;
+    dim3 grid((unsigned)((p->n + TC_THREADS - 1) / TC_THREADS), 2);
+    if (feat) field_fwd_tc_kernel<true><<<grid, TC_CTA_THREADS, 0, s>>>(A);
+    else field_fwd_tc_kernel<false><<<grid, TC_CTA_THREADS, 0, s>>>(A);
+    return check_launch("usl_field_fwd (tcgen05)");
+}

@@ -4,49 +4,11 @@
 
 namespace usl {
 
-// One decoder on one point. out[o] activated outputs; tout[o][d] = d out / d xc.
-template <bool WITH_JAC, bool SAVE_FEAT, int UNR = 1>
-__device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *__restrict__ table,
-                                             const usl_mlp_t &m, const MlpSmem &sm, const float xc[3],
-                                             float2 *__restrict__ feat_out, int64_t feat_stride,
-                                             float out[4], float tout[4][3], float *__restrict__ h1_out = nullptr) {
-    float h[USL_HID];
-    float th[WITH_JAC ? 3 : 1][USL_HID];
-#pragma unroll
-    for (int j = 0; j < USL_HID; ++j) {
-        h[j] = sm.b1[j];
-        if (WITH_JAC) { th[0][j] = 0.f; th[1][j] = 0.f; th[2][j] = 0.f; }
-    }
-#pragma unroll UNR
-    for (int l = 0; l < g.n_levels; ++l) {
-        float2 f, df[3];
-        level_interp<WITH_JAC>(g.levels[l], table, xc[0], xc[1], xc[2], f, df);
-        if (SAVE_FEAT) feat_out[(int64_t)l * feat_stride] = f;
-        const float4 *wa = reinterpret_cast<const float4 *>(sm.w1t[2 * l]);
-        const float4 *wb = reinterpret_cast<const float4 *>(sm.w1t[2 * l + 1]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 a = wa[q], b = wb[q];
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = q * 4 + e;
-                h[j] = fmaf(av[e], f.x, h[j]);
-                h[j] = fmaf(bv[e], f.y, h[j]);
-                if (WITH_JAC) {
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        th[d][j] = fmaf(av[e], df[d].x, th[d][j]);
-                        th[d][j] = fmaf(bv[e], df[d].y, th[d][j]);
-                    }
-                }
-            }
-        }
-    }
-    if (SAVE_FEAT && h1_out) {   // hidden pre-activations kept for the backward pass: [16][n]
-#pragma unroll
-        for (int j = 0; j < USL_HID; ++j) h1_out[(int64_t)j * feat_stride] = h[j];
-    }
+// Everything after the first layer's pre-activations h (and their tangents th): ReLU, optional second hidden
+// layer, output layer, output activation.  out[o] activated outputs; tout[o][d] = d out / d xc.
+template <bool WITH_JAC>
+__device__ __forceinline__ void mlp_tail(const usl_mlp_t &m, const MlpSmem &sm, float h[USL_HID],
+                                         float th[WITH_JAC ? 3 : 1][USL_HID], float out[4], float tout[4][3]) {
 #pragma unroll
     for (int j = 0; j < USL_HID; ++j) {
         const bool on = h[j] > 0.f;
@@ -111,5 +73,50 @@ __device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *
     }
 }
 
+// One decoder on one point. out[o] activated outputs; tout[o][d] = d out / d xc.
+template <bool WITH_JAC, bool SAVE_FEAT, int UNR = 1>
+__device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *__restrict__ table,
+                                             const usl_mlp_t &m, const MlpSmem &sm, const float xc[3],
+                                             float2 *__restrict__ feat_out, int64_t feat_stride,
+                                             float out[4], float tout[4][3], float *__restrict__ h1_out = nullptr) {
+    float h[USL_HID];
+    float th[WITH_JAC ? 3 : 1][USL_HID];
+#pragma unroll
+    for (int j = 0; j < USL_HID; ++j) {
+        h[j] = sm.b1[j];
+        if (WITH_JAC) { th[0][j] = 0.f; th[1][j] = 0.f; th[2][j] = 0.f; }
+    }
+#pragma unroll UNR
+    for (int l = 0; l < g.n_levels; ++l) {
+        float2 f, df[3];
+        level_interp<WITH_JAC>(g.levels[l], table, xc[0], xc[1], xc[2], f, df);
+        if (SAVE_FEAT) feat_out[(int64_t)l * feat_stride] = f;
+        const float4 *wa = reinterpret_cast<const float4 *>(sm.w1t[2 * l]);
+        const float4 *wb = reinterpret_cast<const float4 *>(sm.w1t[2 * l + 1]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 a = wa[q], b = wb[q];
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = q * 4 + e;
+                h[j] = fmaf(av[e], f.x, h[j]);
+                h[j] = fmaf(bv[e], f.y, h[j]);
+                if (WITH_JAC) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        th[d][j] = fmaf(av[e], df[d].x, th[d][j]);
+                        th[d][j] = fmaf(bv[e], df[d].y, th[d][j]);
+                    }
+                }
+            }
+        }
+    }
+    if (SAVE_FEAT && h1_out) {   // hidden pre-activations kept for the backward pass: [16][n]
+#pragma unroll
+        for (int j = 0; j < USL_HID; ++j) h1_out[(int64_t)j * feat_stride] = h[j];
+    }
+    mlp_tail<WITH_JAC>(m, sm, h, th, out, tout);
+}
 
 }  // namespace usl
