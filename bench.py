@@ -228,7 +228,7 @@ def run_ours(args, rank, world, local_rank):
         t_rand.uniform_(generator=gen); t_uni.uniform_(generator=gen); u_pdf.uniform_(generator=gen)
         step.run(wl.batches(idx_main, idx_recent), t_rand, t_uni, u_pdf, cam_poses=cam_poses.detach(), c2w_fixed=wl.c2ws[0])
         if world > 1:                                                   # a-12/8e: gradient all-reduce over NVLink
-            dist.all_reduce(step.fs.g_all); dist.all_reduce(step.d_pose)
+            dist.all_reduce(step.fs.g_grads); dist.all_reduce(step.d_pose)
 
     # ---- pre-fit (untimed): shows the gradients train the field; puts masks in a realistic regime ----
     losses = []
@@ -353,7 +353,7 @@ def run_ours(args, rank, world, local_rank):
                 b.copy_(h, non_blocking=True)
         step.run(wl.batches(bufs[0], bufs[1]), bufs[2], bufs[3], bufs[4], cam_poses=cam_poses.detach(), c2w_fixed=wl.c2ws[0])
         if world > 1:
-            dist.all_reduce(step.fs.g_all); dist.all_reduce(step.d_pose)
+            dist.all_reduce(step.fs.g_grads); dist.all_reduce(step.d_pose)
         loss_host.copy_(step.loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_host)

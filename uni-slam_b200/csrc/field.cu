@@ -143,6 +143,9 @@ struct FieldBwdArgs {
     float *grad_table[2];
     usl_mlp_t gm[2];
     int has_gm;
+    float *scratch;               // replicated copies of the small coarse levels (see plan_replicas), or NULL
+    uint32_t rep_count[2][USL_MAX_LEVELS];   // replicas per level (power of two, 1 = scatter straight into the table)
+    uint32_t rep_offset[2][USL_MAX_LEVELS];  // first entry of the level's replica block inside scratch
     int dbg;              // development switches (USL_DEBUG_BWD): 1 = skip scatter, 2 = skip weight-gradient tiles
     float *dh;            // stand-alone decoder mode: [n,32] gradient wrt the input features (nullable)
 };
@@ -321,7 +324,8 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field
         float2 *gt = STANDALONE ? nullptr : reinterpret_cast<float2 *>(A.grad_table[gi]);
         // warps walk the levels in rotated order so the atomics in flight at any instant spread over all levels'
         // sectors instead of hammering the few sectors of one coarse level (L2 same-sector RMW turnaround)
-        const int rot = (int)(((blockIdx.x * BWD_WARPS + warp) * 5u) % (unsigned)L);
+        const uint32_t wid = blockIdx.x * BWD_WARPS + warp;
+        const int rot = (int)((wid * 5u) % (unsigned)L);
 #ifndef USL_BWD_UNROLL
 #define USL_BWD_UNROLL 2
 #endif
@@ -351,7 +355,10 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field
             float wt[8];
             corner_indices(lv, c, idx);
             corner_weights(c, wt);
-            scatter_level(gt + lv.offset, idx, wt, dfx, dfy);
+            const uint32_t R = A.scratch ? A.rep_count[gi][l] : 1u;
+            float2 *tab = (R > 1u) ? reinterpret_cast<float2 *>(A.scratch) + A.rep_offset[gi][l] + (size_t)(wid & (R - 1u)) * lv.size
+                                   : gt + lv.offset;
+            scatter_level(tab, idx, wt, dfx, dfy);
         }
     }
 
@@ -434,6 +441,52 @@ __global__ void __launch_bounds__(256) mlp_fwd_kernel(usl_mlp_t m, const float *
     for (int o = 0; o < m.n_out; ++o) out[i * m.n_out + o] = act_fwd(m.out_act, u[o]);
 }
 
+// ---- replicated coarse levels ---------------------------------------------------------------------
+// L2 atomic throughput collapses on small tables (tools/microbench_footprint.py: 79 G ops/s on 32 KB, 121 G on
+// 175 KB, 220 G from 4 MB up) because operations on one 32-byte sector serialise.  The coarse dense levels are
+// exactly such tables and every sample hits them, so the scatter writes them into R private copies (picked by warp
+// id, ~1 MB per level in total) and a tiny second kernel folds the copies into the gradient table.
+static void plan_replicas(const usl_field_t *f, uint32_t cnt[2][USL_MAX_LEVELS], uint32_t off[2][USL_MAX_LEVELS], int64_t *total_entries) {
+    int64_t o = 0;
+    static const uint64_t max_bytes = getenv("USL_REP_MAXBYTES") ? strtoull(getenv("USL_REP_MAXBYTES"), nullptr, 10) : 512u * 1024u;
+    static const uint64_t target = getenv("USL_REP_TARGET") ? strtoull(getenv("USL_REP_TARGET"), nullptr, 10) : 1024u * 1024u;
+    for (int gi = 0; gi < 2; ++gi)
+        for (int l = 0; l < USL_MAX_LEVELS; ++l) {
+            cnt[gi][l] = 1; off[gi][l] = 0;
+            if (l >= f->grid[gi].n_levels) continue;
+            const uint64_t bytes = (uint64_t)f->grid[gi].levels[l].size * 8u;
+            if (bytes >= max_bytes) continue;
+            uint32_t r = 1;
+            while (r < 32u && (uint64_t)r * bytes < target) r *= 2;
+            cnt[gi][l] = r; off[gi][l] = (uint32_t)o;
+            o += (int64_t)r * f->grid[gi].levels[l].size;
+        }
+    *total_entries = o;
+}
+
+__global__ void __launch_bounds__(256) fold_replicas_kernel(const __grid_constant__ FieldBwdArgs A) {
+    const int gi = blockIdx.y;
+    float2 *gt = reinterpret_cast<float2 *>(A.grad_table[gi]);
+    if (!gt) return;
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    const usl_grid_t &g = A.f.grid[gi];
+    for (int l = 0; l < g.n_levels; ++l) {
+        const uint32_t R = A.rep_count[gi][l], sz = g.levels[l].size;
+        if (R <= 1u) continue;
+        if (e < sz) {
+            const float2 *src = reinterpret_cast<const float2 *>(A.scratch) + A.rep_offset[gi][l] + e;
+            float sx = 0.f, sy = 0.f;
+            for (uint32_t r = 0; r < R; ++r) { const float2 v = src[(size_t)r * sz]; sx += v.x; sy += v.y; }
+            float2 *dst = gt + g.levels[l].offset + e;
+            float2 cur = *dst;
+            cur.x += sx; cur.y += sy;
+            *dst = cur;
+            return;
+        }
+        e -= sz;
+    }
+}
+
 static int check_field(const usl_field_t *f, const usl_points_t *p) {
     if (!f || !p) { set_error("null field/points"); return 1; }
     for (int gi = 0; gi < 2; ++gi) {
@@ -483,9 +536,18 @@ int usl_field_sdf(const usl_field_t *f, const usl_points_t *p, float *sdf, usl_s
     return check_launch("usl_field_sdf");
 }
 
+int usl_field_bwd_scratch_floats(const usl_field_t *f, int64_t *n_floats) {
+    if (!f || !n_floats) { set_error("usl_field_bwd_scratch_floats: null argument"); return 1; }
+    uint32_t cnt[2][USL_MAX_LEVELS], off[2][USL_MAX_LEVELS];
+    int64_t entries = 0;
+    plan_replicas(f, cnt, off, &entries);
+    *n_floats = entries * 2;
+    return 0;
+}
+
 int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw, const float *feat,
                   const float *d_raw, float *grad_table_sdf, float *grad_table_rgb, const usl_mlp_t *gm,
-                  usl_stream_t stream) {
+                  float *scratch, usl_stream_t stream) {
     if (check_field(f, p)) return 1;
     if (p->n <= 0) return 0;
     if (!feat || !raw || !d_raw) { set_error("usl_field_bwd: raw, feat and d_raw are required"); return 1; }
@@ -499,9 +561,23 @@ int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw,
     if (gm) { A.gm[0] = gm[0]; A.gm[1] = gm[1]; }
     dim3 grid((unsigned)((p->n + BWD_THREADS - 1) / BWD_THREADS), 2);
     cudaStream_t s = (cudaStream_t)stream;
+    int64_t rep_entries = 0;
+    plan_replicas(f, A.rep_count, A.rep_offset, &rep_entries);
+    A.scratch = (rep_entries > 0) ? scratch : nullptr;
     if (f->mlp[0].n_hidden == 2) field_bwd_kernel<2, false><<<grid, BWD_THREADS, 0, s>>>(A);
     else field_bwd_kernel<1, false><<<grid, BWD_THREADS, 0, s>>>(A);
-    return check_launch("usl_field_bwd");
+    if (check_launch("usl_field_bwd")) return 1;
+    if (A.scratch) {
+        uint32_t per_grid = 0;
+        for (int gi = 0; gi < 2; ++gi) {
+            uint32_t t = 0;
+            for (int l = 0; l < f->grid[gi].n_levels; ++l) if (A.rep_count[gi][l] > 1) t += f->grid[gi].levels[l].size;
+            if (t > per_grid) per_grid = t;
+        }
+        if (per_grid) fold_replicas_kernel<<<dim3((per_grid + 255) / 256, 2), 256, 0, s>>>(A);
+        return check_launch("usl_field_bwd (fold)");
+    }
+    return 0;
 }
 
 int usl_mlp_bwd(const usl_mlp_t *m, const usl_mlp_t *gm, const float *h, const float *out, const float *dout,
@@ -513,7 +589,7 @@ int usl_mlp_bwd(const usl_mlp_t *m, const usl_mlp_t *gm, const float *h, const f
     A.f.mlp[0] = *m;
     A.f.grid[0].n_levels = USL_IN / USL_FEATS;
     A.p.n = n;
-    A.raw = out; A.feat = h; A.d_raw = dout; A.dh = dh;
+    A.raw = out; A.feat = h; A.d_raw = dout; A.dh = dh; A.scratch = nullptr;
     A.has_gm = gm ? 1 : 0;
     if (gm) A.gm[0] = *gm;
     dim3 grid((unsigned)((n + BWD_THREADS - 1) / BWD_THREADS), 1);

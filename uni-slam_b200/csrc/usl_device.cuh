@@ -115,9 +115,9 @@ __device__ __forceinline__ void level_interp(const usl_level_t &lv, const float2
     corner_indices(lv, c, idx);
     const float2 *tab = table + lv.offset;
     float2 v[8];
-    // (A 128-bit load for x-pairs that share a 16-byte slot was measured SLOWER here -- 200 vs 182 us: the divergent
-    // 128/64-bit split issues three load instructions per pair and loses cross-lane sector merging -- so the gather
-    // stays 8 x 64-bit; the same pairing does pay off for the atomics, see scatter_level.)
+    // (128-bit loads for x-pairs that share a 16-byte slot were measured: divergent 200 us, predicated 183 us vs
+    // 182 us for plain loads -- the gather is bound by the L1 data pipe + latency, not by sector lookups -- so the
+    // gather stays 8 x 64-bit; the same pairing does pay off for the atomics, see scatter_level.)
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = ldg2(tab + idx[k]);
     if (TCNN_ORDER) {

@@ -128,6 +128,18 @@ class FieldMeta:
         return arr
 
 
+def bwd_scratch_floats(field: L.Field) -> int:
+    from ctypes import c_int64
+    n = c_int64(0)
+    call("usl_field_bwd_scratch_floats", byref(field), byref(n))
+    return int(n.value)
+
+
+def bwd_scratch(field: L.Field, device) -> torch.Tensor:
+    """Zero-filled workspace for usl_field_bwd's replicated coarse levels."""
+    return torch.zeros(max(bwd_scratch_floats(field), 4), device=device, dtype=torch.float32)
+
+
 def _points_from_rays(rays_o, rays_d, z, valid=None) -> L.Points:
     p = L.Points()
     p.x = None
@@ -185,7 +197,7 @@ class _FieldPointsFn(torch.autograd.Function):
             f = meta.pack(sdf_table, rgb_table, dec)
             pts = _points_from_x(x)
             call("usl_field_bwd", byref(f), byref(pts), ptr(raw), ptr(feat), ptr(d_raw), ptr(gs), ptr(gr),
-                 meta.pack_grads(gdec), stream())
+                 meta.pack_grads(gdec), ptr(bwd_scratch(f, x.device)), stream())
         return (None, dx, gs, gr, *gdec)
 
 
@@ -258,7 +270,7 @@ class _RenderFn(torch.autograd.Function):
             f = meta.pack(sdf_table, rgb_table, dec)
             pts = _points_from_rays(rays_o, rays_d, z_vals)
             call("usl_field_bwd", byref(f), byref(pts), ptr(raw), ptr(feat), ptr(d_raw), ptr(gs), ptr(gr),
-                 meta.pack_grads(gdec) if want_dec else None, st)
+                 meta.pack_grads(gdec) if want_dec else None, ptr(bwd_scratch(f, dev)), st)
         return (None, d_o if ctx.needs_input_grad[1] else None, d_d if ctx.needs_input_grad[2] else None, None,
                 d_beta if ctx.needs_input_grad[4] else None, gs, gr, *gdec)
 

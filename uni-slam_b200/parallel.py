@@ -27,7 +27,7 @@ def attach_mapping_collectives(step, group=None):
     step.acc_hook = acc_hook
 
     def reduce_grads():
-        dist.all_reduce(step.fs.g_all, group=group)
+        dist.all_reduce(step.fs.g_grads, group=group)
         dist.all_reduce(step.d_pose, group=group)
     return reduce_grads
 

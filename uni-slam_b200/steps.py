@@ -54,16 +54,22 @@ class _FieldState:
             # every gradient lives in ONE flat buffer [sdf table | colour table | decoders | beta]: a single memset
             # clears it and (multi-GPU) a single all-reduce sums it.  Table sizes are multiples of 16 floats, so the
             # 16-byte vector atomics stay aligned.
+            n_scratch = ops.bwd_scratch_floats(self.field)
             sizes = [sdf_table.numel(), rgb_table.numel()] + [t.numel() for t in self.dec] + [1]
+            pad = (-sum(sizes)) % 32                                  # keep the scratch block 128-byte aligned (16-byte vector atomics)
+            sizes += [pad, max(n_scratch, 4)]
             self.g_all = torch.zeros(sum(sizes), device=sdf_table.device, dtype=torch.float32)
             views, o = [], 0
             for s_ in sizes:
                 views.append(self.g_all[o:o + s_])
                 o += s_
             self.g_sdf_table, self.g_rgb_table = views[0], views[1]
-            self.g_dec = [v.view(t.shape) for v, t in zip(views[2:-1], self.dec)]
-            self.g_beta = views[-1]
-            self.g_flat = self.g_all[sizes[0] + sizes[1]:]          # decoder + beta gradients
+            self.g_dec = [v.view(t.shape) for v, t in zip(views[2:-3], self.dec)]
+            self.g_beta = views[-3]
+            self.scratch = views[-1]                                 # replicated coarse levels (usl_field_bwd workspace)
+            self.n_grad = sum(sizes[:-2])
+            self.g_grads = self.g_all[:self.n_grad]                  # what a multi-GPU all-reduce must sum
+            self.g_flat = self.g_all[sizes[0] + sizes[1]:self.n_grad]   # decoder + beta gradients
             self.g_mlp = meta.pack_grads(self.g_dec)
 
     def repack(self):
@@ -164,7 +170,7 @@ class MappingStep(_Profiled):
              v(self.g_sdf), ptr(self.jac) if joint else None, byref(fs.meta.bound), v(self.d_raw), ptr(fs.g_beta),
              v(self.d_rays_o) if joint else None, v(self.d_rays_d) if joint else None, st)
         self._call("usl_field_bwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), v(self.d_raw), ptr(fs.g_sdf_table),
-             ptr(fs.g_rgb_table), fs.g_mlp, st)
+             ptr(fs.g_rgb_table), fs.g_mlp, ptr(fs.scratch), st)
         if joint:
             self.d_c2w[:K].zero_()
             self._call("usl_pose_reduce", v(self.d_rays_o), v(self.d_rays_d), v(self.dirs), v(self.frame_id), v(self.valid), R, K, ptr(self.d_c2w), st)
