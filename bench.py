@@ -50,7 +50,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -275,12 +275,12 @@ def run_ours(args, rank, world, local_rank):
     l0 = L.LAUNCHES
     one_step() if graph is None else None
     launches_per_step = (L.LAUNCHES - l0) if graph is None else None
+    sampler = ClockSampler(local_rank)                # samples clocks / throttle reasons from warm-up to the end of the timed loops
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         run_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     evs = []
     barrier()
     torch.cuda.nvtx.range_push("usl_timed")           # ncu --nvtx --nvtx-include "usl_timed/" isolates the timed region
@@ -395,7 +395,9 @@ def run_ours(args, rank, world, local_rank):
         e1.record(); torch.cuda.synchronize()
         extra["fused_adam_ms_per_step"] = e0.elapsed_time(e1) / 10     # usl_adam_step (f1)
         extra.update(bench_tracking(P, wl, meta, tabs, dec, beta, cfg, dev, args))
-        extra.update(bench_dense_query(P, wl, meta, tabs, dec, dev, rank, world))
+    dq = bench_dense_query(P, wl, meta, tabs, dec, dev, rank, world, dist)      # every rank: its y-slab
+    if rank == 0:
+        extra.update(dq)
 
     if rank == 0:
         cpu_base = None
@@ -431,42 +433,65 @@ def bench_tracking(P, wl, meta, tabs, dec, beta, cfg, dev, args):
     wlmod = importlib.import_module("uni-slam_b200.workload")
     pose = wlmod._matrix_to_cam_pose(c2w[None]).contiguous()
     pose[:, 4:] += 0.01
-    T_ = torch.nn.Parameter(pose[:, 4:].clone()); R_ = torch.nn.Parameter(pose[:, :4].clone())
-    opt = torch.optim.Adam([{"params": [T_], "lr": cfg.lr_T, "betas": (0.5, 0.999)}, {"params": [R_], "lr": cfg.lr_R, "betas": (0.5, 0.999)}])
+    T_ = pose[:, 4:].clone().requires_grad_(True); R_ = pose[:, :4].clone().requires_grad_(True)
+    T_.grad = trk.d_pose[:, 4:]; R_.grad = trk.d_pose[:, :4]           # persistent .grad views of the step's output
+    # Tracker.py:324-329: Adam(T lr_T, R lr_R, betas (0.5, 0.999)) -- here the one-launch fused equivalent
+    opt = P.FusedAdam([{"params": [T_], "lr": cfg.lr_T, "betas": (0.5, 0.999)}, {"params": [R_], "lr": cfg.lr_R, "betas": (0.5, 0.999)}])
+    opt.enable_graph_step_counter(dev)
     npx = (cam.H - 2 * e) * (cam.W - 2 * e)
     idx = torch.empty((cfg.track_pixels,), device=dev, dtype=torch.int64)
     t_rand = torch.empty((cfg.track_pixels, trk.S), device=dev)
     cam_pose = torch.empty((1, 7), device=dev)
+    best_loss = torch.full((1,), float("inf"), device=dev); best_pose = torch.zeros((1, 7), device=dev)
 
     def it():
-        idx.random_(0, npx); t_rand.uniform_()
-        cam_pose.copy_(torch.cat([R_.detach(), T_.detach()], -1))
+        idx.random_(0, npx); t_rand.uniform_()                          # common.py:116, Renderer.py:55 (host-side RNG)
+        cam_pose.copy_(torch.cat([R_.detach(), T_.detach()], -1))       # Tracker.py:333
         trk.run(cam_pose, dep, col, idx, t_rand)
-        T_.grad = trk.d_pose[:, 4:]; R_.grad = trk.d_pose[:, :4]
+        better = trk.loss < best_loss                                    # Tracker.py:346-348, kept on the device (no .item() sync)
+        best_pose.copy_(torch.where(better, cam_pose, best_pose)); best_loss.copy_(torch.where(better, trk.loss, best_loss))
         opt.step()
 
+    s_ = torch.cuda.Stream(); s_.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s_):
+        for _ in range(3):
+            it()
+    torch.cuda.current_stream().wait_stream(s_); torch.cuda.synchronize()
+    graph = None
+    if not args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                it()
+        except Exception as ex:                                          # noqa: BLE001
+            print(f"[bench] tracking graph capture failed ({ex}); eager", file=sys.stderr)
+            graph = None; torch.cuda.synchronize()
+    run = graph.replay if graph is not None else it
     for _ in range(5):
-        it()
+        run()
     torch.cuda.synchronize()
-    n = max(args.steps, 20)
+    n = max(args.steps, 50)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
     for _ in range(n):
-        it()
+        run()
     e1.record(); torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     trk.profile = True; trk.events = {}
     for _ in range(5):
         it()
     torch.cuda.synchronize()
-    return {"tracking_iters_per_s": n / wall, "tracking_ms_per_iter_device": e0.elapsed_time(e1) / n,
-            "tracking_kernel_ms": trk.kernel_ms(), "tracking_loss": float(trk.loss)}
+    return {"tracking_iters_per_s": n / wall, "tracking_ms_per_iter_device": e0.elapsed_time(e1) / n, "tracking_cuda_graph": graph is not None,
+            "tracking_kernel_ms": trk.kernel_ms(), "tracking_loss": float(trk.loss), "tracking_best_loss": float(best_loss)}
 
 
-def bench_dense_query(P, wl, meta, tabs, dec, dev, rank, world):
-    """BASELINE config 5: 810x510x320 = 132.2 M point SDF query at 1 cm (Mesher.get_grid_uniform bounds +-0.05)."""
+def bench_dense_query(P, wl, meta, tabs, dec, dev, rank, world, dist=None):
+    """BASELINE config 5: 810x510x320 = 132.2 M point SDF query at 1 cm (Mesher.get_grid_uniform bounds +-0.05),
+    y-slab sharded across the ranks (no data-path collective); time = max over ranks; the slabs are then gathered
+    to rank 0 (reported separately -- the reference copies the volume to the host at this point, Mesher.py:225-226)."""
     import numpy as np
+    par = importlib.import_module("uni-slam_b200.parallel")
     axes = []
     for a in range(3):
         lo, hi = wl.cfg.bound_yaml[a]
@@ -474,16 +499,29 @@ def bench_dense_query(P, wl, meta, tabs, dec, dev, rank, world):
         axes.append(torch.from_numpy(np.linspace(lo - 0.05, hi + 0.05, n)).float().to(dev))
     q = P.DenseSdfQuery(meta, tabs[0].detach(), tabs[1].detach(), [d.detach() for d in dec], axes)
     ny = q.ny
-    out = torch.empty((q.slab_points(0, ny),), device=dev)
-    q.run(0, ny, out)
+    yb, ye = par.slab_range(ny, rank, world)
+    out = torch.empty((q.slab_points(yb, ye),), device=dev)
+    q.run(yb, ye, out)
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); q.run(0, ny, out); e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    e0.record(); q.run(yb, ye, out); e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    gather_ms = None
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        g0 = time.perf_counter()
+        vol = par.gather_slabs(out, ny, q.nx, q.nz, rank, world)
+        torch.cuda.synchronize(); dist.barrier()
+        gather_ms = (time.perf_counter() - g0) * 1e3
+        del vol
+    ms = float(t[0])
     npts = q.slab_points(0, ny)
     peak, _ = _peaks()
     return {"dense_query_points": npts, "dense_query_ms": ms, "dense_query_points_per_s": npts / (ms * 1e-3),
-            "dense_query_alg_gbs": npts * 1028 / (ms * 1e-3) / 1e9, "dense_query_frac_of_hbm_peak": npts * 1028 / (ms * 1e-3) / 1e9 / peak}
+            "dense_query_alg_gbs": npts * 1028 / (ms * 1e-3) / 1e9, "dense_query_frac_of_hbm_peak_per_gpu": npts * 1028 / (ms * 1e-3) / 1e9 / peak / world,
+            "dense_query_gather_ms": gather_ms}
 
 
 def cpu_baseline_leg(wl, tabs, dec, beta):

@@ -1,0 +1,161 @@
+"""Minimal Tracker + Mapper loop on a synthetic RGB-D sequence, built from the fused step drivers.
+
+This is BASELINE.json config 2 ("full Tracker+Mapper loop over a synthetic sequence on 1 B200") as a *driver*:
+it reproduces the data flow of src/Tracker.py:271-372 and src/Mapper.py:461-575 -- constant-speed pose
+initialisation, N tracking iterations with Adam(T, R; betas 0.5/0.999) keeping the best pose, mapping every
+`map_every` frames over all keyframes + the current frame (10 % pixel subsets, new Adam per mapped frame,
+joint pose optimisation once > 4 keyframes, 200 px x last-10-frames extra batch once > 20 keyframes) -- in one
+process.  The reference's control policy around it (two OS processes, loop-closure keyframe selection,
+uncertainty-triggered extra iterations, logging, meshing) is out of scope.
+It exists to show the hot path does SLAM end to end (trajectory error vs the analytic ground truth) and to
+measure frames/s; it is not part of the drop-in boundary.
+"""
+import math
+import time
+from dataclasses import dataclass, field
+from typing import List
+
+import torch
+
+from . import synthetic as syn
+from . import workload as wlmod
+from .optim import FusedAdam
+from .steps import MappingStep, TrackingStep
+
+
+@dataclass
+class SlamResult:
+    est_c2w: torch.Tensor
+    gt_c2w: torch.Tensor
+    ate_rmse: float
+    ate_rmse_no_tracking: float       # error of the constant-velocity prior alone (what tracking must beat)
+    frames_per_s: float
+    tracking_iters: int
+    mapping_iters: int
+    mapping_samples: int
+    seconds: float
+    loss_first_map: float
+    loss_last_map: float
+
+
+def run_slam(cfg: syn.SceneCfg = syn.REPLICA_ROOM0, n_frames: int = 40, device="cuda:0", scale_hw: float = 0.5,
+             frame_stride: int = 1, track_iters: int = None, map_iters: int = None, map_iters_first: int = 10,
+             seed: int = 0, prior_noise_m: float = 0.0, verbose: bool = False) -> SlamResult:
+    torch.manual_seed(seed)
+    seq = syn.SyntheticSequence(cfg, n_frames=max(200, n_frames * frame_stride), device=device, seed=1, scale_hw=scale_hw)
+    cam = seq.cam
+    H, W = cam.H, cam.W
+    P = int(H * W * 0.1)
+    bound = syn.load_bound(cfg.bound_yaml)
+    res = syn.grid_resolution(bound, cfg.voxel)
+    pls = float(2.0 ** (math.log2(res / 16) / 15))
+    meta, tabs, dec, beta = wlmod.init_field_tensors(cfg, bound, pls, device, seed=seed)
+    S = cfg.n_stratified + cfg.n_importance
+    track_iters = track_iters or cfg.track_iters
+    map_iters = map_iters or cfg.map_iters
+    edge = max(int(cfg.ignore_edge * scale_hw), 2)
+    max_kf = n_frames // cfg.map_every + 3
+    max_rays = cfg.map_pixels + 2000 + 64
+    mstep = MappingStep(meta, tabs[0], tabs[1], dec, beta, n_stratified=cfg.n_stratified, n_importance=cfg.n_importance,
+                        truncation=cfg.truncation, max_rays=max_rays, max_frames=max_kf)
+    tstep = TrackingStep(meta, tabs[0], tabs[1], dec, beta, n_stratified=cfg.n_stratified, n_importance=cfg.n_importance,
+                         truncation=cfg.truncation, H=H, W=W, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy,
+                         ignore_edge_h=edge, ignore_edge_w=edge, n_rays=cfg.track_pixels)
+    params = [tabs[0], tabs[1], beta] + dec
+    grads = [mstep.fs.g_sdf_table, mstep.fs.g_rgb_table, mstep.fs.g_beta] + mstep.fs.g_dec
+    for p_, g_ in zip(params, grads):
+        p_.requires_grad_(True); p_.grad = g_
+    dirs_full = seq.dirs.reshape(-1, 3)
+    # keyframe store (Mapper.py:528-541): 10 % pixel subsets, device resident
+    kf_depth = torch.zeros((max_kf, P), device=device); kf_color = torch.zeros((max_kf, P, 3), device=device)
+    kf_dirs = torch.zeros((max_kf, P, 3), device=device); kf_c2w = torch.zeros((max_kf, 4, 4), device=device)
+    n_kf = 0
+    est = torch.zeros((n_frames, 4, 4), device=device); gt = torch.zeros((n_frames, 4, 4), device=device)
+    prior = torch.zeros((n_frames, 4, 4), device=device)
+    n_track = n_map = map_samples = 0
+    loss_first = loss_last = float("nan")
+    to_pose = wlmod._matrix_to_cam_pose
+    npx_win = (H - 2 * edge) * (W - 2 * edge)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(n_frames):
+        col, dep, c2w_gt = seq.frame(k * frame_stride)
+        gt[k] = c2w_gt
+        # ---------------- tracking (Tracker.py:306-368) ----------------
+        if k == 0:
+            est[0] = c2w_gt; prior[0] = c2w_gt
+        else:
+            if k >= 2:
+                pp = to_pose(torch.stack([est[k - 2], est[k - 1]]))
+                pose0 = 2 * pp[1:] - pp[0:1]                                   # constant-speed assumption (Tracker.py:315-319)
+            else:
+                pose0 = to_pose(est[k - 1][None])
+            if prior_noise_m > 0:                                              # perturbed initial guess: the tracker has to pull it back
+                pose0 = pose0.clone(); pose0[:, 4:] += prior_noise_m * torch.randn(3, device=device)
+            prior[k] = _pose_to_c2w(pose0)
+            T_ = pose0[:, 4:].clone().contiguous().requires_grad_(True); R_ = pose0[:, :4].clone().contiguous().requires_grad_(True)
+            T_.grad = tstep.d_pose[:, 4:]; R_.grad = tstep.d_pose[:, :4]
+            opt = FusedAdam([{"params": [T_], "lr": cfg.lr_T, "betas": (0.5, 0.999)}, {"params": [R_], "lr": cfg.lr_R, "betas": (0.5, 0.999)}])
+            best_loss = torch.full((1,), float("inf"), device=device); best_pose = pose0.clone()
+            for _ in range(track_iters):
+                cam_pose = torch.cat([R_.detach(), T_.detach()], -1).contiguous()
+                idx = torch.randint(npx_win, (cfg.track_pixels,), device=device)
+                t_rand = torch.rand((cfg.track_pixels, S), device=device)
+                loss = tstep.run(cam_pose, dep, col, idx, t_rand)
+                better = loss < best_loss
+                best_pose = torch.where(better, cam_pose, best_pose); best_loss = torch.where(better, loss, best_loss)
+                opt.step()
+                n_track += 1
+            est[k] = _pose_to_c2w(best_pose)
+        # ---------------- mapping (Mapper.py:485-541) ----------------
+        if k % cfg.map_every == 0:
+            ind = torch.randperm(H * W, device=device)[:P]
+            K = n_kf + 1
+            kf_depth[n_kf] = dep.reshape(-1)[ind]; kf_color[n_kf] = col.reshape(-1, 3)[ind]; kf_dirs[n_kf] = dirs_full[ind]
+            kf_c2w[n_kf] = est[k]
+            joint = n_kf > 4                                                  # Mapper.py:519
+            first = k == 0
+            lr_f = 5.0 if first else 1.0                                       # lr_first_factor / lr_factor
+            groups = [{"params": dec + [beta], "lr": 1e-3 * lr_f}, {"params": [tabs[0]], "lr": cfg.hash_lr * lr_f},
+                      {"params": [tabs[1]], "lr": cfg.hash_lr * lr_f}]
+            cam_poses = None
+            if joint:
+                cam_poses = to_pose(kf_c2w[1:K]).contiguous().requires_grad_(True)
+                cam_poses.grad = mstep.d_pose[:K - 1]
+                groups.append({"params": [cam_poses], "lr": 1e-3})
+            opt = FusedAdam(groups)                                            # new Adam per mapped frame (Mapper.py:364)
+            n_main = cfg.map_pixels // K
+            n_rec = 200 if n_kf > 20 else 0
+            R = K * n_main + 10 * n_rec
+            iters = map_iters_first if first else map_iters
+            for it in range(iters):
+                idx_main = torch.randint(P, (K * n_main,), device=device)
+                batches = [(kf_c2w[:K], kf_depth[:K], kf_color[:K], kf_dirs[:K], idx_main, n_main, 0)]
+                if n_rec:
+                    idx_rec = torch.randint(P, (10 * n_rec,), device=device)
+                    batches.append((kf_c2w[K - 10:K], kf_depth[K - 10:K], kf_color[K - 10:K], kf_dirs[K - 10:K], idx_rec, n_rec, K - 10))
+                loss = mstep.run(batches, torch.rand((R, S), device=device), torch.rand((R, cfg.n_stratified), device=device),
+                                 torch.rand((R, cfg.n_importance), device=device),
+                                 cam_poses=cam_poses.detach() if joint else None, c2w_fixed=kf_c2w[0] if joint else None)
+                opt.step()
+                n_map += 1; map_samples += R * S
+                if first and it == 0:
+                    loss_first = float(loss)
+            loss_last = float(loss)
+            if joint:                                                          # Mapper.py:447-457
+                kf_c2w[1:K] = _pose_to_c2w(cam_poses.detach())
+                est[k] = kf_c2w[K - 1]
+            n_kf += 1                                                          # keyframe_every == map_every in every config
+            if verbose:
+                print(f"frame {k}: mapped K={K} loss={loss_last:.4f}")
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    ate = float((est[:, :3, 3] - gt[:, :3, 3]).pow(2).sum(-1).mean().sqrt())
+    ate_prior = float((prior[:, :3, 3] - gt[:, :3, 3]).pow(2).sum(-1).mean().sqrt())
+    return SlamResult(est, gt, ate, ate_prior, n_frames / dt, n_track, n_map, map_samples, dt, loss_first, loss_last)
+
+
+def _pose_to_c2w(pose: torch.Tensor) -> torch.Tensor:
+    from . import ops
+    out = ops.pose_to_matrix(pose.contiguous())
+    return out[0] if pose.shape[0] == 1 else out

@@ -145,11 +145,12 @@ def look_at_c2w(eye: torch.Tensor, target: torch.Tensor, up=(0.0, 0.0, 1.0)) -> 
     return c2w
 
 
-def trajectory(room: AnalyticRoom, n_frames: int) -> torch.Tensor:
-    """Smooth Lissajous path in the middle of the room, gaze sweeping the walls. (n,4,4)."""
+def trajectory(room: AnalyticRoom, n_frames: int, period: int = 800) -> torch.Tensor:
+    """Smooth Lissajous path in the middle of the room, gaze sweeping the walls. (n,4,4).
+    One lap takes `period` frames: ~0.8 cm and ~0.4 deg per frame, hand-held-camera speed like Replica / ScanNet."""
     out = []
     for k in range(n_frames):
-        s = 2 * math.pi * k / max(n_frames, 200)
+        s = 2 * math.pi * k / period
         off = torch.tensor([0.22 * math.sin(s), 0.20 * math.sin(2 * s + 0.5), 0.10 * math.sin(3 * s)], device=room.device)
         eye = room.c_room + room.h_room * off
         ang = 0.9 * s + 0.4
