@@ -226,7 +226,10 @@ def run_ours(args, rank, world, local_rank):
         if idx_recent is not None:
             idx_recent.random_(0, wl.P, generator=gen)
         t_rand.uniform_(generator=gen); t_uni.uniform_(generator=gen); u_pdf.uniform_(generator=gen)
-        step.run(wl.batches(idx_main, idx_recent), t_rand, t_uni, u_pdf, cam_poses=cam_poses.detach(), c2w_fixed=wl.c2ws[0])
+        if args.no_joint:
+            step.run(wl.batches(idx_main, idx_recent), t_rand, t_uni, u_pdf)
+        else:
+            step.run(wl.batches(idx_main, idx_recent), t_rand, t_uni, u_pdf, cam_poses=cam_poses.detach(), c2w_fixed=wl.c2ws[0])
         if world > 1:                                                   # a-12/8e: gradient all-reduce over NVLink
             dist.all_reduce(step.fs.g_grads); dist.all_reduce(step.d_pose)
 
@@ -552,6 +555,7 @@ def main():
     ap.add_argument("--prefit", type=int, default=60)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-joint", action="store_true", help="ablation: no joint pose optimisation (no Jacobian in the forward pass)")
     ap.add_argument("--quick", action="store_true", help="mapping step only (used under ncu): skip e2e / tracking / dense query / Adam / cpu baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -162,6 +162,38 @@ USL_API int usl_zsample_nodepth(const usl_zsample_args_t *a, const usl_field_t *
                         const int32_t *row_map, int64_t n_rays, float *z, int64_t *pdf_inds,
                         usl_stream_t stream);
 
+/* ---- fused ray set-up: a-3 + a-4 + a-5 in ONE launch (and a-10's pose -> matrix when poses are given) ---------- */
+typedef struct usl_ray_batch {          /* one get_samples_all call (src/Mapper.py:379-393) */
+    const float *c2ws;                  /* [K,4,4] camera matrices, ignored when cam_poses != NULL */
+    const float *depths, *colors, *dirs_cam; /* [K,P], [K,P,3], [K,P,3] stored keyframe pixel subsets */
+    const int64_t *indices;             /* [K*n] torch.randint(P, (n*K,)) */
+    int64_t P;
+    int32_t K, n, frame_base, _pad;
+} usl_ray_batch_t;
+typedef struct usl_ray_setup {
+    int32_t mode;                       /* 0: keyframe batches (mapper), 1: image window (tracker) */
+    int32_t n_batches;
+    usl_ray_batch_t batch[2];
+    const float *depth_img, *color_img; /* mode 1: [H,W], [H,W,3] */
+    const int64_t *win_indices;         /* mode 1: [n_rays] torch.randint((H1-H0)*(W1-W0), (n,)) */
+    int32_t H, W, H0, H1, W0, W1;
+    float fx, fy, cx, cy;
+    const float *c2w;                   /* mode 1: [4,4] when cam_poses == NULL */
+    const float *cam_poses;             /* [K-1,7] (mode 0: frame f>0 uses pose f-1, frame 0 uses c2w_fixed) or [1,7] (mode 1) */
+    const float *c2w_fixed;             /* [4,4] */
+    usl_bound_t bound;
+    int32_t require_depth;              /* tracker: also drop rays with gt_depth <= 0 */
+    int32_t _pad2;
+    usl_zsample_args_t zs;
+    const float *t_rand;                /* [n_rays,S] or NULL (perturb off) */
+    int64_t n_rays;
+    float *rays_o, *rays_d, *gt_depth, *gt_color, *dirs_out; /* outputs */
+    int32_t *frame_id;                  /* nullable */
+    uint8_t *valid;
+    float *z;                           /* [n_rays,S]; rows of depth-less rays are left for usl_zsample_nodepth */
+} usl_ray_setup_t;
+USL_API int usl_ray_setup(const usl_ray_setup_t *a, usl_stream_t stream);
+
 /* ---- B3/B4: field query (Decoders.forward, decoders.py:182-205, with Renderer.py:132-139) -- */
 typedef struct usl_points {
     const float *x;       /* [n,3] normalised coordinates (un-clamped), or NULL to build from rays */
@@ -202,6 +234,9 @@ USL_API int usl_composite_bwd(const float *raw, const float *z, const float *bet
                       const usl_bound_t *bound, float *d_raw, float *d_beta, float *d_rays_o,
                       float *d_rays_d, usl_stream_t stream);
 
+/* usl_composite_bwd with the loss gradient computed in place (== usl_loss_bwd + usl_composite_bwd, no g_sdf round trip)
+ * and loss[0] written by the first CTA (== usl_loss_finalize). Declared after usl_loss_args_t below. */
+
 /* ---- a-9: masks + losses (Mapper.py:141-175,412-430; Tracker.py:113-147,208-228) ----------- */
 typedef struct usl_loss_args {
     float truncation;
@@ -225,6 +260,11 @@ USL_API int usl_loss_bwd(const usl_loss_args_t *a, const float *raw, const float
                  const float *gt_color, const uint8_t *valid, const uint8_t *mask, const float *depth,
                  const float *rgb, const float *acc, const float *g_loss, int64_t R, int S,
                  float *g_depth, float *g_rgb, float *g_sdf, usl_stream_t stream);
+USL_API int usl_composite_loss_bwd(const usl_loss_args_t *a, const float *raw, const float *z, const float *beta,
+                                   const uint8_t *valid, const uint8_t *mask, int64_t R, int S, const float *gt_depth,
+                                   const float *gt_color, const float *depth, const float *rgb, const float *acc,
+                                   const float *g_loss, const float *jac, const usl_bound_t *bound, float *d_raw,
+                                   float *d_beta, float *d_rays_o, float *d_rays_d, float *loss, usl_stream_t stream);
 /* torch.median (lower middle) of |gt - depth| over valid rays: median[0]. workspace: >= R floats. */
 USL_API int usl_depth_error_median(const float *gt_depth, const float *depth, const uint8_t *valid, int64_t R,
                            float *workspace, float *median, usl_stream_t stream);

@@ -50,6 +50,23 @@ class ZSampleArgs(Structure):
                 ("t_uni", c_void_p), ("t_surf", c_void_p)]
 
 
+class RayBatch(Structure):
+    _fields_ = [("c2ws", c_void_p), ("depths", c_void_p), ("colors", c_void_p), ("dirs_cam", c_void_p), ("indices", c_void_p),
+                ("P", c_int64), ("K", c_int32), ("n", c_int32), ("frame_base", c_int32), ("_pad", c_int32)]
+
+
+class RaySetup(Structure):
+    _fields_ = [("mode", c_int32), ("n_batches", c_int32), ("batch", RayBatch * 2),
+                ("depth_img", c_void_p), ("color_img", c_void_p), ("win_indices", c_void_p),
+                ("H", c_int32), ("W", c_int32), ("H0", c_int32), ("H1", c_int32), ("W0", c_int32), ("W1", c_int32),
+                ("fx", c_float), ("fy", c_float), ("cx", c_float), ("cy", c_float),
+                ("c2w", c_void_p), ("cam_poses", c_void_p), ("c2w_fixed", c_void_p),
+                ("bound", Bound), ("require_depth", c_int32), ("_pad2", c_int32),
+                ("zs", ZSampleArgs), ("t_rand", c_void_p), ("n_rays", c_int64),
+                ("rays_o", c_void_p), ("rays_d", c_void_p), ("gt_depth", c_void_p), ("gt_color", c_void_p), ("dirs_out", c_void_p),
+                ("frame_id", c_void_p), ("valid", c_void_p), ("z", c_void_p)]
+
+
 class LossArgs(Structure):
     _fields_ = [("truncation", c_float), ("truncation_center", c_float), ("w_sdf_fs", c_float), ("w_sdf_center", c_float),
                 ("w_sdf_tail", c_float), ("w_depth", c_float), ("w_color", c_float), ("mode", c_int32)]
@@ -91,6 +108,9 @@ _SIGS = {
     "usl_pose_to_matrix": [_P, c_int, _P, _P],
     "usl_pose_matrix_bwd": [_P, _P, c_int, _P, _P],
     "usl_sdf_query_grid": [POINTER(Field), _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "usl_ray_setup": [POINTER(RaySetup), _P],
+    "usl_composite_loss_bwd": [POINTER(LossArgs), _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, POINTER(Bound),
+                               _P, _P, _P, _P, _P, _P],
     "usl_adam_step": [POINTER(AdamGroup), c_int, c_int64, _P, c_int, _P],
     "usl_bench_gather": [_P, c_uint32, c_int64, c_int, _P, _P],
     "usl_bench_scatter": [_P, c_uint32, c_int64, c_int, c_int, _P],

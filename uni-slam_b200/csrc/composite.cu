@@ -1,7 +1,7 @@
 // SDF -> alpha -> transmittance -> weights compositing of depth / colour / uncertainty, one warp per
 // ray with shuffle scans, forward and backward.  Replaces src/utils/Renderer.py:140-158 (sdf2alpha,
 // cumprod transmittance, weighted sums) and the ~25 autograd nodes behind it.
-#include "usl_device.cuh"
+#include "usl_loss.cuh"
 
 namespace usl {
 
@@ -112,6 +112,12 @@ struct CompBwdArgs {
     const float *g_term, *g_punc, *g_depth, *g_rgb, *g_dunc, *g_sdf, *jac;
     usl_bound_t bound;
     float *d_raw, *d_beta, *d_rays_o, *d_rays_d;
+    // fused loss gradient (usl_composite_loss_bwd): upstream gradients derived in place from the loss definition
+    int fused_loss;
+    usl_loss_args_t la;
+    const float *gt_depth, *gt_color, *depth, *rgb, *acc, *g_loss;
+    const uint8_t *mask;
+    float *loss;
 };
 
 __global__ void __launch_bounds__(CMP_WARPS * 32) composite_bwd_kernel(const __grid_constant__ CompBwdArgs A) {
@@ -135,6 +141,23 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_bwd_kernel(const __g
         if (A.g_punc) g_term += A.g_punc[ray] * (-2.0f * (1.0f - term));
         float g_c[3] = {0.f, 0.f, 0.f};
         if (A.g_rgb) { g_c[0] = A.g_rgb[ray * 3]; g_c[1] = A.g_rgb[ray * 3 + 1]; g_c[2] = A.g_rgb[ray * 3 + 2]; }
+        // fused loss: same formulas as loss_bwd_kernel (Mapper.py:141-175,422-430 / Tracker.py:220-228)
+        bool lmask = false;
+        float gt = 0.f, k_fs = 0.f, k_ce = 0.f, k_ta = 0.f;
+        if (A.fused_loss) {
+            const float gl = A.g_loss ? A.g_loss[0] : 1.0f;
+            lmask = A.mask[ray] != 0;
+            gt = A.gt_depth[ray];
+            const float tr = A.la.truncation;
+            k_fs = gl * A.la.w_sdf_fs * 2.0f / A.acc[N_FRONT];
+            k_ce = gl * A.la.w_sdf_center * 2.0f * tr / A.acc[N_CENTER];
+            k_ta = gl * A.la.w_sdf_tail * 2.0f * tr / A.acc[N_TAIL];
+            g_depth = lmask ? gl * A.la.w_depth * 2.0f * (A.depth[ray] - gt) / A.acc[N_MASK] : 0.f;
+            const bool con = (A.la.mode == 0) || lmask;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                g_c[k] = con ? gl * A.la.w_color * 2.0f * (A.rgb[ray * 3 + k] - A.gt_color[ray * 3 + k]) / A.acc[N_COLOR] : 0.f;
+        }
         float dV = 0.f;
         const float g_dunc = A.g_dunc ? A.g_dunc[ray] : 0.f;
         if (g_dunc != 0.f) {
@@ -173,6 +196,12 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_bwd_kernel(const __g
             float g_s = g_alpha * (beta * e) * (-beta * dsg);
             if (in) dbeta += g_alpha * (q.sg * e + beta * e * (-q.sdf * dsg));
             if (A.g_sdf && in) g_s += A.g_sdf[ray * S + s];
+            if (A.fused_loss && lmask && in) {
+                const int c = sample_class(q.z, gt, A.la.truncation, A.la.truncation_center);
+                if (c == 0) g_s += k_fs * (q.sdf - 1.0f);
+                else if (c == 1) g_s += k_ce * ((q.z + q.sdf * A.la.truncation) - gt);
+                else if (c == 2) g_s += k_ta * ((q.z + q.sdf * A.la.truncation) - gt);
+            }
             if (in) {
                 const float4 dr = make_float4(q.w * g_c[0], q.w * g_c[1], q.w * g_c[2], g_s);
                 reinterpret_cast<float4 *>(A.d_raw)[ray * S + s] = dr;
@@ -201,6 +230,7 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_bwd_kernel(const __g
         }
         dbeta = warp_sum(dbeta);
     }
+    if (A.fused_loss && A.loss && blockIdx.x == 0 && threadIdx.x == 0) A.loss[0] = loss_value(A.la, A.acc);   // == usl_loss_finalize
     if (A.d_beta) {
         if (lane == 0) s_dbeta[warp] = dbeta;
         __syncthreads();
@@ -241,8 +271,29 @@ int usl_composite_bwd(const float *raw, const float *z, const float *beta, const
     A.g_term = g_term; A.g_punc = g_punc; A.g_depth = g_depth; A.g_rgb = g_rgb; A.g_dunc = g_dunc; A.g_sdf = g_sdf; A.jac = jac;
     if (bound) A.bound = *bound; else { for (int d = 0; d < 3; ++d) { A.bound.lo[d] = 0.f; A.bound.hi[d] = 1.f; } }
     A.d_raw = d_raw; A.d_beta = d_beta; A.d_rays_o = d_rays_o; A.d_rays_d = d_rays_d;
+    A.fused_loss = 0; A.loss = nullptr; A.mask = nullptr;
     composite_bwd_kernel<<<(unsigned)((R + CMP_WARPS - 1) / CMP_WARPS), CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(A);
     return check_launch("usl_composite_bwd");
+}
+
+int usl_composite_loss_bwd(const usl_loss_args_t *a, const float *raw, const float *z, const float *beta,
+                           const uint8_t *valid, const uint8_t *mask, int64_t R, int S, const float *gt_depth,
+                           const float *gt_color, const float *depth, const float *rgb, const float *acc,
+                           const float *g_loss, const float *jac, const usl_bound_t *bound, float *d_raw, float *d_beta,
+                           float *d_rays_o, float *d_rays_d, float *loss, usl_stream_t stream) {
+    if (R <= 0) return 0;
+    if (S < 1 || S > CMP_MAX_CHUNKS * 32) { set_error("usl_composite_loss_bwd: S must be in 1..128"); return 1; }
+    if (!a || !mask || !acc || !gt_depth || !gt_color || !depth || !rgb) { set_error("usl_composite_loss_bwd: null argument"); return 1; }
+    if (jac && (!bound || !d_rays_o || !d_rays_d)) { set_error("usl_composite_loss_bwd: jac needs bound, d_rays_o, d_rays_d"); return 1; }
+    CompBwdArgs A;
+    A.raw = raw; A.z = z; A.beta = beta; A.valid = valid; A.R = R; A.S = S;
+    A.g_term = nullptr; A.g_punc = nullptr; A.g_depth = nullptr; A.g_rgb = nullptr; A.g_dunc = nullptr; A.g_sdf = nullptr; A.jac = jac;
+    if (bound) A.bound = *bound; else { for (int d = 0; d < 3; ++d) { A.bound.lo[d] = 0.f; A.bound.hi[d] = 1.f; } }
+    A.d_raw = d_raw; A.d_beta = d_beta; A.d_rays_o = d_rays_o; A.d_rays_d = d_rays_d;
+    A.fused_loss = 1; A.la = *a; A.gt_depth = gt_depth; A.gt_color = gt_color; A.depth = depth; A.rgb = rgb; A.acc = acc;
+    A.g_loss = g_loss; A.mask = mask; A.loss = loss;
+    composite_bwd_kernel<<<(unsigned)((R + CMP_WARPS - 1) / CMP_WARPS), CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(A);
+    return check_launch("usl_composite_loss_bwd");
 }
 
 }  // extern "C"

@@ -5,30 +5,9 @@
 // (src/common.py:102-105,196-208 + pytorch3d quaternion_to_matrix).
 // Two-phase design: phase 1 accumulates sums and element counts (no boolean-index compaction, no
 // host sync); phase 2 turns them into per-ray / per-sample upstream gradients.
-#include "usl_device.cuh"
+#include "usl_loss.cuh"
 
 namespace usl {
-
-#define LOSS_WARPS 8
-enum { A_FS = 0, A_CENTER, A_TAIL, A_DEPTH, A_COLOR, N_FRONT, N_CENTER, N_TAIL, N_MASK, N_RAYS, N_COLOR, A_PUNC };
-
-__device__ __forceinline__ bool ray_mask(const usl_loss_args_t &a, float gt, float punc, float depth, const float *median) {
-    const bool alpha_mask = (1.0f - punc) > 0.99f;                          // Mapper.py:414-415 / Tracker.py:210-211
-    if (a.mode == 0) return (gt > 0.f) && alpha_mask;                       // Mapper.py:417-420
-    const float err = fabsf(gt - depth);
-    return (err < 10.0f * median[0]) && alpha_mask;                         // Tracker.py:213-218
-}
-
-// sample class: 0 front, 1 center, 2 tail, 3 none (behind the surface band)
-__device__ __forceinline__ int sample_class(float z, float gt, float tr, float tr04) {
-    const bool front = z < (gt - tr);
-    const bool back = z > (gt + tr);
-    const bool center = (z > (gt - tr04)) && (z < (gt + tr04));
-    if (front) return 0;
-    if (center) return 1;
-    if (!back) return 2;
-    return 3;
-}
 
 __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_fwd_kernel(
     usl_loss_args_t a, const float *__restrict__ raw, const float *__restrict__ z, const float *__restrict__ gt_depth,
@@ -85,13 +64,6 @@ __global__ void __launch_bounds__(LOSS_WARPS * 32) loss_fwd_kernel(
         for (int w = 0; w < LOSS_WARPS; ++w) s += s_acc[w][threadIdx.x];
         if (s != 0.f) atomicAdd(acc + threadIdx.x, s);
     }
-}
-
-__device__ __forceinline__ float loss_value(const usl_loss_args_t &a, const float *acc) {
-    // torch.mean over an empty selection is NaN (0/0): kept
-    const float fs = acc[A_FS] / acc[N_FRONT], ce = acc[A_CENTER] / acc[N_CENTER], ta = acc[A_TAIL] / acc[N_TAIL];
-    const float col = acc[A_COLOR] / acc[N_COLOR], dep = acc[A_DEPTH] / acc[N_MASK];
-    return a.w_sdf_fs * fs + a.w_sdf_center * ce + a.w_sdf_tail * ta + a.w_color * col + a.w_depth * dep;
 }
 
 __global__ void loss_finalize_kernel(usl_loss_args_t a, const float *__restrict__ acc, float *__restrict__ loss) {
@@ -222,28 +194,11 @@ __global__ void __launch_bounds__(256) pose_reduce_kernel(const float *__restric
 __global__ void pose_to_matrix_kernel(const float *__restrict__ pose, int K, float *__restrict__ c2w) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
-    const float r = pose[k * 7], i = pose[k * 7 + 1], j = pose[k * 7 + 2], kk = pose[k * 7 + 3];
-    // op-for-op like torch eager (separate mul / add kernels, no FMA contraction)
-#define MUL(a, b) __fmul_rn(a, b)
-#define ADD(a, b) __fadd_rn(a, b)
-#define SUB(a, b) __fsub_rn(a, b)
-    const float two_s = __fdiv_rn(2.0f, ADD(ADD(ADD(MUL(r, r), MUL(i, i)), MUL(j, j)), MUL(kk, kk)));
+    float m[12];
+    pose_to_c2w(pose + k * 7, m);
     float *o = c2w + k * 16;
-    o[0] = SUB(1.0f, MUL(two_s, ADD(MUL(j, j), MUL(kk, kk))));
-    o[1] = MUL(two_s, SUB(MUL(i, j), MUL(kk, r)));
-    o[2] = MUL(two_s, ADD(MUL(i, kk), MUL(j, r)));
-    o[3] = pose[k * 7 + 4];
-    o[4] = MUL(two_s, ADD(MUL(i, j), MUL(kk, r)));
-    o[5] = SUB(1.0f, MUL(two_s, ADD(MUL(i, i), MUL(kk, kk))));
-    o[6] = MUL(two_s, SUB(MUL(j, kk), MUL(i, r)));
-    o[7] = pose[k * 7 + 5];
-    o[8] = MUL(two_s, SUB(MUL(i, kk), MUL(j, r)));
-    o[9] = MUL(two_s, ADD(MUL(j, kk), MUL(i, r)));
-    o[10] = SUB(1.0f, MUL(two_s, ADD(MUL(i, i), MUL(j, j))));
-    o[11] = pose[k * 7 + 6];
-#undef MUL
-#undef ADD
-#undef SUB
+#pragma unroll
+    for (int q = 0; q < 12; ++q) o[q] = m[q];
     o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
 }
 

@@ -160,6 +160,108 @@ __global__ void zsample_depth_kernel(usl_zsample_args_t a, const float *__restri
     z[r * S + k] = out;
 }
 
+// ---- fused ray set-up: ray generation + bbox prefilter + depth-guided z sampling in one launch ----
+// Block = ZS_RAYS_PER_BLOCK rays x S threads; thread k == 0 of each ray gathers / rotates the ray and tests the bbox,
+// then all S threads of the ray produce its z samples.  With cam_poses the camera matrix is rebuilt from the pose in
+// place (same arithmetic as usl_pose_to_matrix).
+__global__ void ray_setup_kernel(const __grid_constant__ usl_ray_setup_t A) {
+    extern __shared__ float sz[];                      // [ZS_RAYS_PER_BLOCK][S] merged samples
+    __shared__ float s_gt[ZS_RAYS_PER_BLOCK];
+    __shared__ int s_live[ZS_RAYS_PER_BLOCK];
+    const int ns = A.zs.n_stratified, ni = A.zs.n_importance, S = ns + ni;
+    const int rl = threadIdx.x / S, k = threadIdx.x - rl * S;
+    const int64_t r = (int64_t)blockIdx.x * ZS_RAYS_PER_BLOCK + rl;
+    if (k == 0) {
+        int live = 0;
+        float gt = 0.f;
+        if (r < A.n_rays) {
+            float c2w[12], d[3], col[3];
+            int frame = 0;
+            if (A.mode == 0) {
+                int b = 0;
+                int64_t m = r;
+                const int64_t n0 = (int64_t)A.batch[0].K * A.batch[0].n;
+                if (A.n_batches > 1 && m >= n0) { b = 1; m -= n0; }
+                const usl_ray_batch_t &B = A.batch[b];
+                const int kf = (int)(m / B.n);
+                frame = B.frame_base + kf;
+                const int64_t src = (int64_t)kf * B.P + B.indices[m];
+                d[0] = B.dirs_cam[src * 3]; d[1] = B.dirs_cam[src * 3 + 1]; d[2] = B.dirs_cam[src * 3 + 2];
+                col[0] = B.colors[src * 3]; col[1] = B.colors[src * 3 + 1]; col[2] = B.colors[src * 3 + 2];
+                gt = B.depths[src];
+                if (A.cam_poses) {
+                    if (frame == 0) {
+#pragma unroll
+                        for (int q = 0; q < 12; ++q) c2w[q] = A.c2w_fixed[q];
+                    } else pose_to_c2w(A.cam_poses + (int64_t)(frame - 1) * 7, c2w);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) c2w[q] = B.c2ws[(int64_t)kf * 16 + q];
+                }
+            } else {
+                const int64_t idx = A.win_indices[r];
+                const int Wc = A.W1 - A.W0;
+                const int pi = (int)(idx % Wc) + A.W0, pj = (int)(idx / Wc) + A.H0;
+                pixel_dir((float)pi, (float)pj, A.fx, A.fy, A.cx, A.cy, d);
+                const int64_t src = (int64_t)pj * A.W + pi;
+                col[0] = A.color_img[src * 3]; col[1] = A.color_img[src * 3 + 1]; col[2] = A.color_img[src * 3 + 2];
+                gt = A.depth_img[src];
+                if (A.cam_poses) pose_to_c2w(A.cam_poses, c2w);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) c2w[q] = A.c2w[q];
+                }
+            }
+            float o[3], rd[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                rd[a] = __fadd_rn(__fadd_rn(__fmul_rn(d[0], c2w[a * 4]), __fmul_rn(d[1], c2w[a * 4 + 1])), __fmul_rn(d[2], c2w[a * 4 + 2]));
+                o[a] = c2w[a * 4 + 3];
+                A.rays_d[r * 3 + a] = rd[a]; A.rays_o[r * 3 + a] = o[a];
+                A.gt_color[r * 3 + a] = col[a]; A.dirs_out[r * 3 + a] = d[a];
+            }
+            A.gt_depth[r] = gt;
+            if (A.frame_id) A.frame_id[r] = frame;
+            bool v = bbox_exit(o, rd, A.bound) >= gt;
+            if (A.require_depth) v = v && (gt > 0.f);
+            A.valid[r] = v ? 1 : 0;
+            live = (v && gt > 0.f) ? 1 : 0;
+        }
+        s_gt[rl] = gt; s_live[rl] = live;
+    }
+    __syncthreads();
+    const bool live = s_live[rl] != 0;
+    const float gt = s_gt[rl];
+    const float g12 = __fmul_rn(1.2f, gt);
+    const float s0 = __fsub_rn(gt, A.zs.c_surf_lo);
+    if (live) {
+        float v;
+        int rank;
+        if (k < ns) {
+            v = __fadd_rn(0.0f, __fmul_rn(g12, A.zs.t_uni[k]));
+            rank = k;
+            for (int j = 0; j < ni; ++j) rank += (__fadd_rn(s0, __fmul_rn(A.zs.c_surf_span, A.zs.t_surf[j])) < v) ? 1 : 0;
+        } else {
+            const int j0 = k - ns;
+            v = __fadd_rn(s0, __fmul_rn(A.zs.c_surf_span, A.zs.t_surf[j0]));
+            rank = j0;
+            for (int i = 0; i < ns; ++i) rank += (__fadd_rn(0.0f, __fmul_rn(g12, A.zs.t_uni[i])) <= v) ? 1 : 0;
+        }
+        sz[rl * S + rank] = v;
+    }
+    __syncthreads();
+    if (!live) return;
+    const float *zr = sz + rl * S;
+    float out = zr[k];
+    if (A.t_rand) {
+        const float cur = out;
+        const float lower = (k == 0) ? cur : __fmul_rn(0.5f, __fadd_rn(cur, zr[k - 1]));
+        const float upper = (k == S - 1) ? cur : __fmul_rn(0.5f, __fadd_rn(zr[k + 1], cur));
+        out = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), A.t_rand[r * S + k]));
+    }
+    A.z[r * S + k] = out;
+}
+
 // ---- no-depth rays: uniform samples to the bbox exit + inverse-CDF resampling from an SDF query ----
 #define ND_MAX_STRAT 64
 #define ND_MAX_IMP 32
@@ -322,6 +424,17 @@ int usl_bbox_prefilter(const float *rays_o, const float *rays_d, const float *gt
     bbox_prefilter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, gt_depth, n, *bound,
                                                                                          require_depth, t_exit, valid);
     return check_launch("usl_bbox_prefilter");
+}
+
+int usl_ray_setup(const usl_ray_setup_t *a, usl_stream_t stream) {
+    if (!a || a->n_rays <= 0) return a ? 0 : 1;
+    const int S = a->zs.n_stratified + a->zs.n_importance;
+    if (S < 2 || S > 128) { set_error("usl_ray_setup: n_stratified + n_importance must be in 2..128"); return 1; }
+    if (a->mode == 0 && (a->n_batches < 1 || a->n_batches > 2)) { set_error("usl_ray_setup: 1 or 2 keyframe batches"); return 1; }
+    if (a->mode == 1 && (a->H0 < 0 || a->H1 > a->H || a->W0 < 0 || a->W1 > a->W || a->H1 <= a->H0 || a->W1 <= a->W0)) { set_error("usl_ray_setup: bad window"); return 1; }
+    ray_setup_kernel<<<(unsigned)((a->n_rays + ZS_RAYS_PER_BLOCK - 1) / ZS_RAYS_PER_BLOCK), ZS_RAYS_PER_BLOCK * S,
+                       ZS_RAYS_PER_BLOCK * S * sizeof(float), (cudaStream_t)stream>>>(*a);
+    return check_launch("usl_ray_setup");
 }
 
 int usl_zsample_depth(const usl_zsample_args_t *a, const float *gt_depth, const uint8_t *valid, const float *t_rand,

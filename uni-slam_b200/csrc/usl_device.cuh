@@ -204,6 +204,31 @@ __device__ __forceinline__ float norm_coord(float o, float d, float z, float lo,
     return __fdiv_rn(__fsub_rn(p, lo), __fsub_rn(hi, lo));
 }
 
+// pose [qw,qx,qy,qz,tx,ty,tz] -> rows 0..2 of c2w (3x4 row-major): pytorch3d quaternion_to_matrix for an
+// un-normalised real-first quaternion (src/common.py:196-208), op-for-op like torch eager (no FMA contraction).
+__device__ __forceinline__ void pose_to_c2w(const float *__restrict__ pose, float o[12]) {
+    const float r = pose[0], i = pose[1], j = pose[2], kk = pose[3];
+#define USL_MUL(a, b) __fmul_rn(a, b)
+#define USL_ADD(a, b) __fadd_rn(a, b)
+#define USL_SUB(a, b) __fsub_rn(a, b)
+    const float two_s = __fdiv_rn(2.0f, USL_ADD(USL_ADD(USL_ADD(USL_MUL(r, r), USL_MUL(i, i)), USL_MUL(j, j)), USL_MUL(kk, kk)));
+    o[0] = USL_SUB(1.0f, USL_MUL(two_s, USL_ADD(USL_MUL(j, j), USL_MUL(kk, kk))));
+    o[1] = USL_MUL(two_s, USL_SUB(USL_MUL(i, j), USL_MUL(kk, r)));
+    o[2] = USL_MUL(two_s, USL_ADD(USL_MUL(i, kk), USL_MUL(j, r)));
+    o[3] = pose[4];
+    o[4] = USL_MUL(two_s, USL_ADD(USL_MUL(i, j), USL_MUL(kk, r)));
+    o[5] = USL_SUB(1.0f, USL_MUL(two_s, USL_ADD(USL_MUL(i, i), USL_MUL(kk, kk))));
+    o[6] = USL_MUL(two_s, USL_SUB(USL_MUL(j, kk), USL_MUL(i, r)));
+    o[7] = pose[5];
+    o[8] = USL_MUL(two_s, USL_SUB(USL_MUL(i, kk), USL_MUL(j, r)));
+    o[9] = USL_MUL(two_s, USL_ADD(USL_MUL(j, kk), USL_MUL(i, r)));
+    o[10] = USL_SUB(1.0f, USL_MUL(two_s, USL_ADD(USL_MUL(i, i), USL_MUL(j, j))));
+    o[11] = pose[6];
+#undef USL_MUL
+#undef USL_ADD
+#undef USL_SUB
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

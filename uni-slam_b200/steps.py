@@ -47,7 +47,7 @@ class _FieldState:
     """Tables + decoder tensors + beta, their packed descriptor and persistent gradient buffers."""
 
     def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec: Sequence[torch.Tensor], beta: torch.Tensor,
-                 with_grads: bool):
+                 with_grads: bool, max_frames: int = 1):
         self.meta, self.sdf_table, self.rgb_table, self.dec, self.beta = meta, sdf_table, rgb_table, list(dec), beta
         self.field = meta.pack(sdf_table, rgb_table, self.dec)
         if with_grads:
@@ -57,17 +57,19 @@ class _FieldState:
             n_scratch = ops.bwd_scratch_floats(self.field)
             sizes = [sdf_table.numel(), rgb_table.numel()] + [t.numel() for t in self.dec] + [1]
             pad = (-sum(sizes)) % 32                                  # keep the scratch block 128-byte aligned (16-byte vector atomics)
-            sizes += [pad, max(n_scratch, 4)]
+            sizes += [pad, max(n_scratch, 4), L.LOSS_SLOTS, max_frames * 12]   # + loss accumulators + d c2w: one memset clears all
             self.g_all = torch.zeros(sum(sizes), device=sdf_table.device, dtype=torch.float32)
             views, o = [], 0
             for s_ in sizes:
                 views.append(self.g_all[o:o + s_])
                 o += s_
             self.g_sdf_table, self.g_rgb_table = views[0], views[1]
-            self.g_dec = [v.view(t.shape) for v, t in zip(views[2:-3], self.dec)]
-            self.g_beta = views[-3]
-            self.scratch = views[-1]                                 # replicated coarse levels (usl_field_bwd workspace)
-            self.n_grad = sum(sizes[:-2])
+            self.g_dec = [v.view(t.shape) for v, t in zip(views[2:-5], self.dec)]
+            self.g_beta = views[-5]
+            self.scratch = views[-3]                                 # replicated coarse levels (usl_field_bwd workspace)
+            self.acc = views[-2]
+            self.d_c2w = views[-1].view(max_frames, 12)
+            self.n_grad = sum(sizes[:-4])
             self.g_grads = self.g_all[:self.n_grad]                  # what a multi-GPU all-reduce must sum
             self.g_flat = self.g_all[sizes[0] + sizes[1]:self.n_grad]   # decoder + beta gradients
             self.g_mlp = meta.pack_grads(self.g_dec)
@@ -82,7 +84,7 @@ class MappingStep(_Profiled):
     def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec, beta, *, n_stratified, n_importance, truncation,
                  weights=(5.0, 200.0, 10.0, 0.1, 5.0), max_rays: int, max_frames: int = 1, perturb: bool = True):
         dev = sdf_table.device
-        self.fs = _FieldState(meta, sdf_table, rgb_table, dec, beta, with_grads=True)
+        self.fs = _FieldState(meta, sdf_table, rgb_table, dec, beta, with_grads=True, max_frames=max_frames)
         self.zs = ops.ZSampler(n_stratified, n_importance, truncation, dev)
         self.S = self.zs.S
         self.perturb = perturb
@@ -99,12 +101,10 @@ class MappingStep(_Profiled):
         self.jac = torch.empty((R * S, 12), **f32)
         self.term = torch.empty((R,), **f32); self.punc = torch.empty((R,), **f32); self.depth = torch.empty((R,), **f32)
         self.rgb = torch.empty((R, 3), **f32); self.dunc = torch.empty((R,), **f32)
-        self.acc = torch.zeros((L.LOSS_SLOTS,), **f32); self.loss = torch.zeros((1,), **f32)
-        self.g_depth = torch.empty((R,), **f32); self.g_rgb = torch.empty((R, 3), **f32); self.g_sdf = torch.empty((R, S), **f32)
+        self.acc = self.fs.acc; self.loss = torch.zeros((1,), **f32)
         self.d_raw = torch.empty((R, S, 4), **f32)
         self.d_rays_o = torch.empty((R, 3), **f32); self.d_rays_d = torch.empty((R, 3), **f32)
-        self.c2ws = torch.empty((max_frames, 4, 4), **f32)
-        self.d_c2w = torch.zeros((max_frames, 12), **f32); self.d_pose = torch.zeros((max_frames, 7), **f32)
+        self.d_c2w = self.fs.d_c2w; self.d_pose = torch.zeros((max_frames, 7), **f32)
         self.n_rays = 0
         self.acc_hook = None      # multi-GPU: called with self.acc between loss_fwd and loss_bwd (all-reduce of sums/counts)
         self._init_prof()
@@ -122,57 +122,52 @@ class MappingStep(_Profiled):
         st = stream()
         fs, S = self.fs, self.S
         joint = cam_poses is not None
-        if joint:
-            K = cam_poses.shape[0] + 1
-            self.c2ws[0].copy_(c2w_fixed)
-            call("usl_pose_to_matrix", ptr(cam_poses), K - 1, ptr(self.c2ws[1:K]), st)
-        # ---- a-3: gather-then-rotate ray generation ----
-        off = 0
-        for (c2ws, depths, colors, dirs_cam, indices, n, frame_base) in batches:
+        K = (cam_poses.shape[0] + 1) if joint else 0
+        fs.g_all.zero_()                                   # gradients, replica scratch, loss accumulators, d c2w: one memset
+        # ---- a-3 + a-4 + a-5 (+ pose -> matrix): one launch ----
+        rs = L.RaySetup()
+        rs.mode, rs.n_batches = 0, len(batches)
+        R = 0
+        for b_, (c2ws, depths, colors, dirs_cam, indices, n, frame_base) in zip(rs.batch, batches):
             Kb, P = depths.shape
-            M = Kb * n
-            cw = self.c2ws[frame_base:frame_base + Kb] if joint else c2ws
-            sl = slice(off, off + M)
-            self._call("usl_sample_keyframe_rays", ptr(cw), ptr(depths), ptr(colors), ptr(dirs_cam), ptr(indices), Kb, P, n, frame_base,
-                 ptr(self.rays_o[sl]), ptr(self.rays_d[sl]), ptr(self.gt_depth[sl]), ptr(self.gt_color[sl]), ptr(self.dirs[sl]),
-                 ptr(self.frame_id[sl]), st)
-            off += M
-        R = off
+            b_.c2ws = None if joint else ptr(c2ws)
+            b_.depths, b_.colors, b_.dirs_cam, b_.indices = ptr(depths), ptr(colors), ptr(dirs_cam), ptr(indices)
+            b_.P, b_.K, b_.n, b_.frame_base = P, Kb, n, frame_base
+            R += Kb * n
         assert R <= self.max_rays
         self.n_rays = R
         v = lambda t: ptr(t[:R]) if t is not None else None
-        # ---- a-4 prefilter, a-5/a-6 z sampling ----
-        call("usl_bbox_prefilter", v(self.rays_o), v(self.rays_d), v(self.gt_depth), R, byref(fs.meta.bound), 0, None, v(self.valid), st)
-        self._call("usl_zsample_depth", byref(self.zs.args), v(self.gt_depth), v(self.valid), ptr(t_rand) if self.perturb else None, None, R, v(self.z), st)
-        if has_holes:
+        rs.cam_poses = ptr(cam_poses) if joint else None
+        rs.c2w_fixed = ptr(c2w_fixed) if joint else None
+        rs.bound, rs.require_depth, rs.zs = fs.meta.bound, 0, self.zs.args
+        rs.t_rand = ptr(t_rand) if self.perturb else None
+        rs.n_rays = R
+        rs.rays_o, rs.rays_d, rs.gt_depth, rs.gt_color, rs.dirs_out = v(self.rays_o), v(self.rays_d), v(self.gt_depth), v(self.gt_color), v(self.dirs)
+        rs.frame_id, rs.valid, rs.z = v(self.frame_id), v(self.valid), v(self.z)
+        self._call("usl_ray_setup", byref(rs), st)
+        if has_holes:                                      # a-6
             self._call("usl_zsample_nodepth", byref(self.zs.args), byref(fs.field), ptr(fs.beta), v(self.rays_o), v(self.rays_d), v(self.gt_depth),
-                 v(self.valid), ptr(t_rand_uni) if self.perturb else None, ptr(u_pdf), None, R, v(self.z), None, st)
+                       v(self.valid), ptr(t_rand_uni) if self.perturb else None, ptr(u_pdf), None, R, v(self.z), None, st)
         # ---- a-7, a-1, a-2: field query; a-8: compositing ----
         pts = L.Points()
         pts.x = None; pts.rays_o, pts.rays_d, pts.z, pts.valid = v(self.rays_o), v(self.rays_d), v(self.z), v(self.valid)
         pts.S, pts.n = S, R * S
-        # feat is laid out [2][L][n][2] with n = R*S of THIS call
         self._call("usl_field_fwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), ptr(self.jac) if joint else None, st)
         self._call("usl_composite_fwd", v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), R, S, v(self.term), v(self.punc), v(self.depth),
-             v(self.rgb), v(self.dunc), None, st)
-        # ---- a-9: losses (two-phase) ----
-        self.acc.zero_()
+                   v(self.rgb), v(self.dunc), None, st)
+        # ---- a-9: losses, phase 1 (sums + counts) ----
         self._call("usl_loss_fwd", byref(self.loss_args), v(self.raw), v(self.z), v(self.gt_depth), v(self.gt_color), v(self.valid), v(self.punc),
-             v(self.depth), v(self.rgb), None, R, S, ptr(self.acc), v(self.mask), st)
+                   v(self.depth), v(self.rgb), None, R, S, ptr(self.acc), v(self.mask), st)
         if self.acc_hook is not None:
             self.acc_hook(self.acc)
-        call("usl_loss_finalize", byref(self.loss_args), ptr(self.acc), ptr(self.loss), st)
-        self._call("usl_loss_bwd", byref(self.loss_args), v(self.raw), v(self.z), v(self.gt_depth), v(self.gt_color), v(self.valid), v(self.mask),
-             v(self.depth), v(self.rgb), ptr(self.acc), None, R, S, v(self.g_depth), v(self.g_rgb), v(self.g_sdf), st)
-        # ---- backward ----
-        fs.g_all.zero_()
-        self._call("usl_composite_bwd", v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), R, S, None, None, v(self.g_depth), v(self.g_rgb), None,
-             v(self.g_sdf), ptr(self.jac) if joint else None, byref(fs.meta.bound), v(self.d_raw), ptr(fs.g_beta),
-             v(self.d_rays_o) if joint else None, v(self.d_rays_d) if joint else None, st)
+        # ---- backward: loss gradient + compositing adjoint (+ loss value) in one launch, then the field ----
+        self._call("usl_composite_loss_bwd", byref(self.loss_args), v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), v(self.mask), R, S,
+                   v(self.gt_depth), v(self.gt_color), v(self.depth), v(self.rgb), ptr(self.acc), None, ptr(self.jac) if joint else None,
+                   byref(fs.meta.bound), v(self.d_raw), ptr(fs.g_beta), v(self.d_rays_o) if joint else None,
+                   v(self.d_rays_d) if joint else None, ptr(self.loss), st)
         self._call("usl_field_bwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), v(self.d_raw), ptr(fs.g_sdf_table),
-             ptr(fs.g_rgb_table), fs.g_mlp, ptr(fs.scratch), st)
+                   ptr(fs.g_rgb_table), fs.g_mlp, ptr(fs.scratch), st)
         if joint:
-            self.d_c2w[:K].zero_()
             self._call("usl_pose_reduce", v(self.d_rays_o), v(self.d_rays_d), v(self.dirs), v(self.frame_id), v(self.valid), R, K, ptr(self.d_c2w), st)
             call("usl_pose_matrix_bwd", ptr(cam_poses), ptr(self.d_c2w[1:K]), K - 1, ptr(self.d_pose[:K - 1]), st)
         return self.loss
@@ -196,7 +191,6 @@ class TrackingStep(_Profiled):
         R, S = n_rays, self.S
         self.R = R
         f32 = dict(device=dev, dtype=torch.float32)
-        self.c2w = torch.empty((1, 4, 4), **f32)
         self.rays_o = torch.empty((R, 3), **f32); self.rays_d = torch.empty((R, 3), **f32)
         self.gt_depth = torch.empty((R,), **f32); self.gt_color = torch.empty((R, 3), **f32); self.dirs = torch.empty((R, 3), **f32)
         self.valid = torch.empty((R,), device=dev, dtype=torch.uint8); self.mask = torch.empty((R,), device=dev, dtype=torch.uint8)
@@ -204,12 +198,13 @@ class TrackingStep(_Profiled):
         self.raw = torch.empty((R, S, 4), **f32); self.jac = torch.empty((R * S, 12), **f32)
         self.term = torch.empty((R,), **f32); self.punc = torch.empty((R,), **f32); self.depth = torch.empty((R,), **f32)
         self.rgb = torch.empty((R, 3), **f32); self.dunc = torch.empty((R,), **f32)
-        self.acc = torch.zeros((L.LOSS_SLOTS,), **f32); self.loss = torch.zeros((1,), **f32)
+        self._small = torch.zeros((L.LOSS_SLOTS + 12,), **f32)          # loss accumulators + d c2w: one memset per iteration
+        self.acc = self._small[:L.LOSS_SLOTS]; self.d_c2w = self._small[L.LOSS_SLOTS:].view(1, 12)
+        self.loss = torch.zeros((1,), **f32)
         self.median = torch.zeros((1,), **f32); self.ws = torch.empty((R,), **f32)
-        self.g_depth = torch.empty((R,), **f32); self.g_rgb = torch.empty((R, 3), **f32); self.g_sdf = torch.empty((R, S), **f32)
         self.d_raw = torch.empty((R, S, 4), **f32)
         self.d_rays_o = torch.empty((R, 3), **f32); self.d_rays_d = torch.empty((R, 3), **f32)
-        self.d_c2w = torch.zeros((1, 12), **f32); self.d_pose = torch.zeros((1, 7), **f32)
+        self.d_pose = torch.zeros((1, 7), **f32)
         self._init_prof()
 
     def run(self, cam_pose, depth_img, color_img, indices, t_rand):
@@ -220,28 +215,31 @@ class TrackingStep(_Profiled):
         fs, S, R = self.fs, self.S, self.R
         H, W, fx, fy, cx, cy = self.cam
         H0, H1, W0, W1 = self.win
-        call("usl_pose_to_matrix", ptr(cam_pose), 1, ptr(self.c2w), st)
-        self._call("usl_sample_window_rays", ptr(self.c2w), ptr(depth_img), ptr(color_img), H, W, H0, H1, W0, W1, fx, fy, cx, cy, ptr(indices), R,
-             ptr(self.rays_o), ptr(self.rays_d), ptr(self.gt_depth), ptr(self.gt_color), ptr(self.dirs), st)
-        call("usl_bbox_prefilter", ptr(self.rays_o), ptr(self.rays_d), ptr(self.gt_depth), R, byref(fs.meta.bound), 1, None, ptr(self.valid), st)
-        self._call("usl_zsample_depth", byref(self.zs.args), ptr(self.gt_depth), ptr(self.valid), ptr(t_rand) if self.perturb else None, None, R,
-             ptr(self.z), st)
+        self._small.zero_()
+        rs = L.RaySetup()                                   # pose -> matrix, a-3, a-4, a-5 in one launch
+        rs.mode, rs.n_batches = 1, 0
+        rs.depth_img, rs.color_img, rs.win_indices = ptr(depth_img), ptr(color_img), ptr(indices)
+        rs.H, rs.W, rs.H0, rs.H1, rs.W0, rs.W1 = H, W, H0, H1, W0, W1
+        rs.fx, rs.fy, rs.cx, rs.cy = fx, fy, cx, cy
+        rs.cam_poses = ptr(cam_pose)
+        rs.bound, rs.require_depth, rs.zs = fs.meta.bound, 1, self.zs.args
+        rs.t_rand = ptr(t_rand) if self.perturb else None
+        rs.n_rays = R
+        rs.rays_o, rs.rays_d, rs.gt_depth, rs.gt_color, rs.dirs_out = ptr(self.rays_o), ptr(self.rays_d), ptr(self.gt_depth), ptr(self.gt_color), ptr(self.dirs)
+        rs.frame_id, rs.valid, rs.z = None, ptr(self.valid), ptr(self.z)
+        self._call("usl_ray_setup", byref(rs), st)
         pts = L.Points()
         pts.x = None; pts.rays_o, pts.rays_d, pts.z, pts.valid = ptr(self.rays_o), ptr(self.rays_d), ptr(self.z), ptr(self.valid)
         pts.S, pts.n = S, R * S
         self._call("usl_field_fwd", byref(fs.field), byref(pts), ptr(self.raw), None, ptr(self.jac), st)
         self._call("usl_composite_fwd", ptr(self.raw), ptr(self.z), ptr(fs.beta), ptr(self.valid), R, S, ptr(self.term), ptr(self.punc),
-             ptr(self.depth), ptr(self.rgb), ptr(self.dunc), None, st)
+                   ptr(self.depth), ptr(self.rgb), ptr(self.dunc), None, st)
         self._call("usl_depth_error_median", ptr(self.gt_depth), ptr(self.depth), ptr(self.valid), R, ptr(self.ws), ptr(self.median), st)
-        self.acc.zero_()
         self._call("usl_loss_fwd", byref(self.loss_args), ptr(self.raw), ptr(self.z), ptr(self.gt_depth), ptr(self.gt_color), ptr(self.valid),
-             ptr(self.punc), ptr(self.depth), ptr(self.rgb), ptr(self.median), R, S, ptr(self.acc), ptr(self.mask), st)
-        call("usl_loss_finalize", byref(self.loss_args), ptr(self.acc), ptr(self.loss), st)
-        self._call("usl_loss_bwd", byref(self.loss_args), ptr(self.raw), ptr(self.z), ptr(self.gt_depth), ptr(self.gt_color), ptr(self.valid),
-             ptr(self.mask), ptr(self.depth), ptr(self.rgb), ptr(self.acc), None, R, S, ptr(self.g_depth), ptr(self.g_rgb), ptr(self.g_sdf), st)
-        self._call("usl_composite_bwd", ptr(self.raw), ptr(self.z), ptr(fs.beta), ptr(self.valid), R, S, None, None, ptr(self.g_depth), ptr(self.g_rgb),
-             None, ptr(self.g_sdf), ptr(self.jac), byref(fs.meta.bound), ptr(self.d_raw), None, ptr(self.d_rays_o), ptr(self.d_rays_d), st)
-        self.d_c2w.zero_()
+                   ptr(self.punc), ptr(self.depth), ptr(self.rgb), ptr(self.median), R, S, ptr(self.acc), ptr(self.mask), st)
+        self._call("usl_composite_loss_bwd", byref(self.loss_args), ptr(self.raw), ptr(self.z), ptr(fs.beta), ptr(self.valid), ptr(self.mask), R, S,
+                   ptr(self.gt_depth), ptr(self.gt_color), ptr(self.depth), ptr(self.rgb), ptr(self.acc), None, ptr(self.jac),
+                   byref(fs.meta.bound), ptr(self.d_raw), None, ptr(self.d_rays_o), ptr(self.d_rays_d), ptr(self.loss), st)
         self._call("usl_pose_reduce", ptr(self.d_rays_o), ptr(self.d_rays_d), ptr(self.dirs), None, ptr(self.valid), R, 1, ptr(self.d_c2w), st)
         call("usl_pose_matrix_bwd", ptr(cam_pose), ptr(self.d_c2w), 1, ptr(self.d_pose), st)
         return self.loss
