@@ -274,10 +274,9 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- warm-up, then the timed region: K steps, per-step CUDA events, L2 flushed between steps ----
-    launches_per_step = 0
     l0 = L.LAUNCHES
-    one_step() if graph is None else None
-    launches_per_step = (L.LAUNCHES - l0) if graph is None else None
+    one_step()                                            # one eager step: counts this arm's own kernel launches per step
+    launches_per_step = (L.LAUNCHES - l0) + 1             # + the replica-fold kernel usl_field_bwd launches internally
     sampler = ClockSampler(local_rank)                # samples clocks / throttle reasons from warm-up to the end of the timed loops
     if rank == 0:
         sampler.start()
@@ -329,12 +328,25 @@ def run_ours(args, rank, world, local_rank):
         "usl_field_bwd": {"ms": kms.get("usl_field_bwd"), "alg_bytes": gather_bytes + n_pts * 16},
     }
     peak, peak_src = _peaks()
-    for k in kern.values():
+    # ceilings measured on this pool's B200 by tools/microbench.py (profiles/r01_microbench.json): L2-resident random
+    # 8-byte gathers ~280 G loads/s, 8-byte vector atomics ~223 G ops/s
+    l2_ceiling = {"usl_field_fwd": 280.0e9, "usl_field_bwd": 223.0e9}
+    lane_ops = n_pts * 2 * 16 * 8
+    for name, k in kern.items():
         k["gbs"] = k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] else None
         k["frac"] = k["gbs"] / peak if k["gbs"] else None
+        k["lane_ops_per_s"] = lane_ops / (k["ms"] * 1e-3) if k["ms"] else None
+        k["frac_of_measured_l2_random_access_ceiling"] = k["lane_ops_per_s"] / l2_ceiling[name] if k["ms"] else None
+    traffic = {}
+    tp = os.path.join(REPO, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+    for name, k in kern.items():
+        k["dram_traffic_bytes_ncu"] = traffic.get(name)
     dom = max(kern, key=lambda k: kern[k]["ms"] or 0)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
-                "traffic": None, "peak_source": peak_src,
+                "traffic": kern[dom]["dram_traffic_bytes_ncu"], "peak_source": peak_src,
+                "frac_of_measured_l2_random_access_ceiling": kern[dom]["frac_of_measured_l2_random_access_ceiling"],
                 "note": "tables (49 MB) are L2-resident: the binding resource is L2 sector throughput, not HBM; see DESIGN.md section 5"}
 
     if args.quick:
@@ -347,6 +359,27 @@ def run_ours(args, rank, world, local_rank):
     h2d = sum(h.numel() * h.element_size() for h in host if h is not None)
     loss_host = torch.empty(1).pin_memory()
 
+    def run_only():
+        if args.no_joint:
+            step.run(wl.batches(bufs[0], bufs[1]), bufs[2], bufs[3], bufs[4])
+        else:
+            step.run(wl.batches(bufs[0], bufs[1]), bufs[2], bufs[3], bufs[4], cam_poses=cam_poses.detach(), c2w_fixed=wl.c2ws[0])
+        if world > 1:
+            dist.all_reduce(step.fs.g_grads); dist.all_reduce(step.d_pose)
+
+    # the public-API call replayed from a CUDA graph that does NOT contain the RNG draws (those arrive from the host here)
+    e2e_graph = None
+    if graph is not None:
+        try:
+            torch.cuda.synchronize()
+            e2e_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(e2e_graph):
+                run_only()
+        except Exception as e:                                           # noqa: BLE001
+            print(f"[bench] e2e graph capture failed ({type(e).__name__}: {e}); eager", file=sys.stderr)
+            e2e_graph = None
+            torch.cuda.synchronize()
+
     def e2e_step():
         host[0].random_(0, wl.P, generator=gcpu)
         if host[1] is not None:
@@ -354,9 +387,10 @@ def run_ours(args, rank, world, local_rank):
         for h, b in zip(host, bufs):
             if h is not None:
                 b.copy_(h, non_blocking=True)
-        step.run(wl.batches(bufs[0], bufs[1]), bufs[2], bufs[3], bufs[4], cam_poses=cam_poses.detach(), c2w_fixed=wl.c2ws[0])
-        if world > 1:
-            dist.all_reduce(step.fs.g_grads); dist.all_reduce(step.d_pose)
+        if e2e_graph is not None:
+            e2e_graph.replay()
+        else:
+            run_only()
         loss_host.copy_(step.loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_host)
@@ -413,7 +447,7 @@ def run_ours(args, rank, world, local_rank):
                 "clocks": clocks, "roofline": roofline, "kernels": kern, "kernel_ms_all": kms,
                 "cpu_baseline": cpu_base,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-                "gpu_launches": (launches_per_step or len(kms)) * args.steps,
+                "gpu_launches": launches_per_step * args.steps,
                 "value_l2_warm": samples / (warm_ms * 1e-3), "prefit_loss": losses[:1] + losses[-1:], **extra}
         print(json.dumps(line), flush=True)
     if world > 1:

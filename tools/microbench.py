@@ -18,7 +18,7 @@ def timeit(fn, n=10):
 
 res = {}
 out = torch.zeros(1 << 22, device=dev)
-for mb in (42,):
+for mb in (6, 42):
     entries = mb * 1024 * 1024 // 8
     table = torch.zeros(entries * 2, device=dev)
     nthr, per = 1 << 21, 32
@@ -28,7 +28,6 @@ for mb in (42,):
         ms = timeit(lambda: L.call("usl_bench_scatter", L.ptr(table), entries, nthr, per, mode, L.stream()))
         res[f"scatter_{mb}MB_{nm}"] = {"ms": ms, "G_lane_atomics_per_s": nthr * per / ms / 1e6}
 
-print(json.dumps(res, indent=1)); sys.exit(0)
 # stand-alone encode kernels, Replica grids, 240k points
 wl = importlib.import_module("uni-slam_b200.workload")
 syn = P.synthetic
