@@ -205,7 +205,8 @@ typedef struct usl_points {
     int64_t n;            /* number of points (= R*S when built from rays) */
 } usl_points_t;
 /* raw[n,4] = (r,g,b,sdf). feat (nullable): activation stash for the backward pass, 2*n*48 floats:
- * interpolated features [2][L][n][2] followed by the hidden pre-activations [2][16][n]. jac (nullable): [n,12] d raw / d x (rows r,g,b,sdf; clamp-gated). */
+ * interpolated features [2][L][n][2] followed by the hidden pre-activations [2][16][n]. jac (nullable): [12,n] component-major
+ * d raw / d x (component o*3+d, rows o = r,g,b,sdf; clamp-gated). */
 USL_API int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac,
                   usl_stream_t stream);
 /* d_raw[n,4] -> table gradients (scatter), decoder gradients (gm[2], may be NULL to skip).
@@ -226,7 +227,7 @@ USL_API int usl_composite_fwd(const float *raw, const float *z, const float *bet
                       int64_t R, int S, float *term, float *pixel_unc, float *depth, float *rgb,
                       float *depth_unc, float *weights, usl_stream_t stream);
 /* upstream grads (each nullable = zero): g_term[R], g_punc[R], g_depth[R], g_rgb[R,3], g_dunc[R],
- * g_sdf[R,S].  Outputs: d_raw[R,S,4]; d_beta[1] (ADDED); and, when jac!=NULL, d_rays_o/d_rays_d[R,3]
+ * g_sdf[R,S].  Outputs: d_raw[R,S,4]; d_beta[1] (ADDED); and, when jac!=NULL ([12,R*S]), d_rays_o/d_rays_d[R,3]
  * = sum_s (d_raw . jac) chained through the normalisation (extent = hi-lo). */
 USL_API int usl_composite_bwd(const float *raw, const float *z, const float *beta, const uint8_t *valid,
                       int64_t R, int S, const float *g_term, const float *g_punc, const float *g_depth,

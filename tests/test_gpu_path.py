@@ -291,7 +291,7 @@ def test_tcgen05_forward_matches_cuda_core_forward(monkeypatch):
     outs = []
     for flag in ("0", "1"):
         monkeypatch.setenv("USL_TCGEN05", flag)
-        raw = torch.zeros(n, 4, device=DEV); jac = torch.zeros(n, 12, device=DEV)
+        raw = torch.zeros(n, 4, device=DEV); jac = torch.zeros(12, n, device=DEV)
         f = meta.pack(tabs[0], tabs[1], dec)
         pts = P.ops._points_from_x(x)
         P._lib.call("usl_field_fwd", byref(f), byref(pts), P._lib.ptr(raw), None, P._lib.ptr(jac), P._lib.stream())

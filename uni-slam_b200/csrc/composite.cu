@@ -206,12 +206,16 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_bwd_kernel(const __g
                 const float4 dr = make_float4(q.w * g_c[0], q.w * g_c[1], q.w * g_c[2], g_s);
                 reinterpret_cast<float4 *>(A.d_raw)[ray * S + s] = dr;
                 if (A.jac) {
-                    const float4 *J = reinterpret_cast<const float4 *>(A.jac) + (ray * S + s) * 3;
-                    const float4 j0 = __ldg(J), j1 = __ldg(J + 1), j2 = __ldg(J + 2);
-                    // rows: r(j0.xyz) g(j0.w j1.xy) b(j1.zw j2.x) sdf(j2.yzw)
-                    const float gx0 = dr.x * j0.x + dr.y * j0.w + dr.z * j1.z + dr.w * j2.y;
-                    const float gx1 = dr.x * j0.y + dr.y * j1.x + dr.z * j1.w + dr.w * j2.z;
-                    const float gx2 = dr.x * j0.z + dr.y * j1.y + dr.z * j2.x + dr.w * j2.w;
+                    // jac is component-major [12][R*S] (rows r,g,b,sdf x 3 dims): every load is coalesced across the samples
+                    const int64_t npts = A.R * (int64_t)S, pi = ray * S + s;
+                    float gx0 = 0.f, gx1 = 0.f, gx2 = 0.f;
+                    const float drv[4] = {dr.x, dr.y, dr.z, dr.w};
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        gx0 = fmaf(drv[o], __ldg(A.jac + (int64_t)(o * 3 + 0) * npts + pi), gx0);
+                        gx1 = fmaf(drv[o], __ldg(A.jac + (int64_t)(o * 3 + 1) * npts + pi), gx1);
+                        gx2 = fmaf(drv[o], __ldg(A.jac + (int64_t)(o * 3 + 2) * npts + pi), gx2);
+                    }
                     const float gp0 = gx0 / (A.bound.hi[0] - A.bound.lo[0]);
                     const float gp1 = gx1 / (A.bound.hi[1] - A.bound.lo[1]);
                     const float gp2 = gx2 / (A.bound.hi[2] - A.bound.lo[2]);

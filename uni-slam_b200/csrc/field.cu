@@ -43,7 +43,10 @@ __device__ __forceinline__ bool load_point(const usl_points_t &p, const usl_fiel
 }
 
 template <bool WITH_JAC, bool SAVE_FEAT>
-__global__ void __launch_bounds__(256) field_fwd_kernel(const __grid_constant__ FieldArgs A) {
+#ifndef USL_FWD_MINB
+#define USL_FWD_MINB 2
+#endif
+__global__ void __launch_bounds__(256, (WITH_JAC ? USL_FWD_MINB : 4)) field_fwd_kernel(const __grid_constant__ FieldArgs A) {
     __shared__ MlpSmem sm;
     const int gi = blockIdx.y;
     stage_mlp(A.f.mlp[gi], sm);
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(256) field_fwd_kernel(const __grid_constant__ 
         A.raw[i * 4 + 3] = out[0];
         if (WITH_JAC) {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) A.jac[i * 12 + 9 + d] = tout[0][d] * gate[d];
+            for (int d = 0; d < 3; ++d) A.jac[(int64_t)(9 + d) * A.p.n + i] = tout[0][d] * gate[d];   // component-major: coalesced
         }
     } else {
 #pragma unroll
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(256) field_fwd_kernel(const __grid_constant__ 
             A.raw[i * 4 + o] = out[o];
             if (WITH_JAC) {
 #pragma unroll
-                for (int d = 0; d < 3; ++d) A.jac[i * 12 + o * 3 + d] = tout[o][d] * gate[d];
+                for (int d = 0; d < 3; ++d) A.jac[(int64_t)(o * 3 + d) * A.p.n + i] = tout[o][d] * gate[d];
             }
         }
     }

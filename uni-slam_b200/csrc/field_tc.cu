@@ -212,13 +212,13 @@ __global__ void __launch_bounds__(TC_CTA_THREADS, 4) field_fwd_tc_kernel(const _
         if (gi == 0) {
             A.raw[i * 4 + 3] = out[0];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) A.jac[i * 12 + 9 + d] = tout[0][d] * gate[d];
+            for (int d = 0; d < 3; ++d) A.jac[(int64_t)(9 + d) * n + i] = tout[0][d] * gate[d];   // component-major: coalesced
         } else {
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
                 A.raw[i * 4 + o] = out[o];
 #pragma unroll
-                for (int d = 0; d < 3; ++d) A.jac[i * 12 + o * 3 + d] = tout[o][d] * gate[d];
+                for (int d = 0; d < 3; ++d) A.jac[(int64_t)(o * 3 + d) * n + i] = tout[o][d] * gate[d];
             }
         }
     }

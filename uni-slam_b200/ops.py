@@ -173,7 +173,7 @@ class _FieldPointsFn(torch.autograd.Function):
         need_x = ctx.needs_input_grad[1]
         raw = torch.empty((n, 4), device=x.device, dtype=torch.float32)
         feat = torch.empty((2 * (C_DIM + HIDDEN) * n,), device=x.device, dtype=torch.float32) if need_p else None
-        jac = torch.empty((n, 12), device=x.device, dtype=torch.float32) if need_x else None
+        jac = torch.empty((12, n), device=x.device, dtype=torch.float32) if need_x else None
         f = meta.pack(sdf_table, rgb_table, dec)
         pts = _points_from_x(x)
         call("usl_field_fwd", byref(f), byref(pts), ptr(raw), ptr(feat), ptr(jac), stream())
@@ -188,7 +188,7 @@ class _FieldPointsFn(torch.autograd.Function):
         d_raw = f32c(d_raw)
         dx = None
         if jac is not None:
-            dx = torch.einsum("no,nod->nd", d_raw, jac.view(-1, 4, 3))
+            dx = torch.einsum("no,odn->nd", d_raw, jac.view(4, 3, -1))
         gs = gr = None
         gdec = [None] * len(dec)
         if feat is not None:
@@ -228,7 +228,7 @@ class _RenderFn(torch.autograd.Function):
         need_p = any(ctx.needs_input_grad[5:])
         raw = torch.empty((R, S, 4), device=dev, dtype=torch.float32)
         feat = torch.empty((2 * (C_DIM + HIDDEN) * R * S,), device=dev, dtype=torch.float32) if need_p else None
-        jac = torch.empty((R * S, 12), device=dev, dtype=torch.float32) if need_rays else None
+        jac = torch.empty((12, R * S), device=dev, dtype=torch.float32) if need_rays else None
         f = meta.pack(sdf_table, rgb_table, dec)
         pts = _points_from_rays(rays_o, rays_d, z_vals)
         st = stream()

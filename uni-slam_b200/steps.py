@@ -98,7 +98,7 @@ class MappingStep(_Profiled):
         self.valid = torch.empty((R,), device=dev, dtype=torch.uint8); self.mask = torch.empty((R,), device=dev, dtype=torch.uint8)
         self.z = torch.zeros((R, S), **f32)
         self.raw = torch.empty((R, S, 4), **f32); self.feat = torch.empty((2 * (ops.C_DIM + ops.HIDDEN) * R * S,), **f32)   # stash: features + hidden pre-activations
-        self.jac = torch.empty((R * S, 12), **f32)
+        self.jac = torch.empty((12 * R * S,), **f32)        # component-major [12][n] of THIS call's n = R*S
         self.term = torch.empty((R,), **f32); self.punc = torch.empty((R,), **f32); self.depth = torch.empty((R,), **f32)
         self.rgb = torch.empty((R, 3), **f32); self.dunc = torch.empty((R,), **f32)
         self.acc = self.fs.acc; self.loss = torch.zeros((1,), **f32)
@@ -195,7 +195,7 @@ class TrackingStep(_Profiled):
         self.gt_depth = torch.empty((R,), **f32); self.gt_color = torch.empty((R, 3), **f32); self.dirs = torch.empty((R, 3), **f32)
         self.valid = torch.empty((R,), device=dev, dtype=torch.uint8); self.mask = torch.empty((R,), device=dev, dtype=torch.uint8)
         self.z = torch.zeros((R, S), **f32)
-        self.raw = torch.empty((R, S, 4), **f32); self.jac = torch.empty((R * S, 12), **f32)
+        self.raw = torch.empty((R, S, 4), **f32); self.jac = torch.empty((12 * R * S,), **f32)        # component-major [12][n] of THIS call's n = R*S
         self.term = torch.empty((R,), **f32); self.punc = torch.empty((R,), **f32); self.depth = torch.empty((R,), **f32)
         self.rgb = torch.empty((R, 3), **f32); self.dunc = torch.empty((R,), **f32)
         self._small = torch.zeros((L.LOSS_SLOTS + 12,), **f32)          # loss accumulators + d c2w: one memset per iteration
