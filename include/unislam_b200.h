@@ -212,11 +212,12 @@ USL_API int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *ra
 /* d_raw[n,4] -> table gradients (scatter), decoder gradients (gm[2], may be NULL to skip).
  * scratch (nullable): zero-filled workspace of usl_field_bwd_scratch_floats() floats holding private copies of the
  * small coarse levels (L2 atomics serialise on small tables); it is folded into the gradient tables before return
- * and must be zero-filled again by the caller before the next call. */
+ * and must be zero-filled again by the caller before the next call. grid_mask: 1 = sdf grid only, 2 = colour grid
+ * only, 3 = both (one launch); the halves are independent, so a caller can all-reduce one while the other runs. */
 USL_API int usl_field_bwd_scratch_floats(const usl_field_t *f, int64_t *n_floats);
 USL_API int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw, const float *feat,
                   const float *d_raw, float *grad_table_sdf, float *grad_table_rgb,
-                  const usl_mlp_t *gm, float *scratch, usl_stream_t stream);
+                  const usl_mlp_t *gm, float *scratch, int grid_mask, usl_stream_t stream);
 /* SDF channel only, forward only (Renderer.py:121, Mesher.py:134-166). out_of_bound_value used
  * when mask_bound!=0 and the un-normalised point lies outside the open bound. */
 USL_API int usl_field_sdf(const usl_field_t *f, const usl_points_t *p, float *sdf, usl_stream_t stream);

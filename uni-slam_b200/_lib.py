@@ -95,7 +95,7 @@ _SIGS = {
     "usl_zsample_depth": [POINTER(ZSampleArgs), _P, _P, _P, _P, c_int64, _P, _P],
     "usl_zsample_nodepth": [POINTER(ZSampleArgs), POINTER(Field), _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P],
     "usl_field_fwd": [POINTER(Field), POINTER(Points), _P, _P, _P, _P],
-    "usl_field_bwd": [POINTER(Field), POINTER(Points), _P, _P, _P, _P, _P, POINTER(Mlp), _P, _P],
+    "usl_field_bwd": [POINTER(Field), POINTER(Points), _P, _P, _P, _P, _P, POINTER(Mlp), _P, c_int, _P],
     "usl_field_bwd_scratch_floats": [POINTER(Field), POINTER(c_int64)],
     "usl_field_sdf": [POINTER(Field), POINTER(Points), _P, _P],
     "usl_composite_fwd": [_P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P],

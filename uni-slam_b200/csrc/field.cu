@@ -146,6 +146,8 @@ struct FieldBwdArgs {
     float *grad_table[2];
     usl_mlp_t gm[2];
     int has_gm;
+    int gi_base;                  // first grid handled by this launch (gridDim.y grids from here): lets the caller run
+                                  // the colour and sdf halves as separate launches and overlap a collective with the second
     float *scratch;               // replicated copies of the small coarse levels (see plan_replicas), or NULL
     uint32_t rep_count[2][USL_MAX_LEVELS];   // replicas per level (power of two, 1 = scatter straight into the table)
     uint32_t rep_offset[2][USL_MAX_LEVELS];  // first entry of the level's replica block inside scratch
@@ -161,7 +163,7 @@ template <int NH, bool STANDALONE>
 __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field_bwd_kernel(const __grid_constant__ FieldBwdArgs A) {
     __shared__ MlpSmem sm;
     __shared__ __align__(16) float tiles[BWD_WARPS][32][TILE_STRIDE];
-    const int gi = blockIdx.y;
+    const int gi = A.gi_base + blockIdx.y;
     const usl_mlp_t &m = A.f.mlp[gi];
     stage_mlp(m, sm);
     __syncthreads();
@@ -468,7 +470,7 @@ static void plan_replicas(const usl_field_t *f, uint32_t cnt[2][USL_MAX_LEVELS],
 }
 
 __global__ void __launch_bounds__(256) fold_replicas_kernel(const __grid_constant__ FieldBwdArgs A) {
-    const int gi = blockIdx.y;
+    const int gi = A.gi_base + blockIdx.y;
     float2 *gt = reinterpret_cast<float2 *>(A.grad_table[gi]);
     if (!gt) return;
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -550,7 +552,7 @@ int usl_field_bwd_scratch_floats(const usl_field_t *f, int64_t *n_floats) {
 
 int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw, const float *feat,
                   const float *d_raw, float *grad_table_sdf, float *grad_table_rgb, const usl_mlp_t *gm,
-                  float *scratch, usl_stream_t stream) {
+                  float *scratch, int grid_mask, usl_stream_t stream) {
     if (check_field(f, p)) return 1;
     if (p->n <= 0) return 0;
     if (!feat || !raw || !d_raw) { set_error("usl_field_bwd: raw, feat and d_raw are required"); return 1; }
@@ -562,7 +564,10 @@ int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw,
     A.dh = nullptr;
     { const char *e = getenv("USL_DEBUG_BWD"); A.dbg = e ? atoi(e) : 0; }
     if (gm) { A.gm[0] = gm[0]; A.gm[1] = gm[1]; }
-    dim3 grid((unsigned)((p->n + BWD_THREADS - 1) / BWD_THREADS), 2);
+    if (grid_mask < 1 || grid_mask > 3) { set_error("usl_field_bwd: grid_mask must be 1 (sdf), 2 (colour) or 3 (both)"); return 1; }
+    A.gi_base = (grid_mask == 2) ? 1 : 0;
+    const unsigned ny = (grid_mask == 3) ? 2u : 1u;
+    dim3 grid((unsigned)((p->n + BWD_THREADS - 1) / BWD_THREADS), ny);
     cudaStream_t s = (cudaStream_t)stream;
     int64_t rep_entries = 0;
     plan_replicas(f, A.rep_count, A.rep_offset, &rep_entries);
@@ -572,12 +577,12 @@ int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw,
     if (check_launch("usl_field_bwd")) return 1;
     if (A.scratch) {
         uint32_t per_grid = 0;
-        for (int gi = 0; gi < 2; ++gi) {
+        for (int gi = A.gi_base; gi < A.gi_base + (int)ny; ++gi) {
             uint32_t t = 0;
             for (int l = 0; l < f->grid[gi].n_levels; ++l) if (A.rep_count[gi][l] > 1) t += f->grid[gi].levels[l].size;
             if (t > per_grid) per_grid = t;
         }
-        if (per_grid) fold_replicas_kernel<<<dim3((per_grid + 255) / 256, 2), 256, 0, s>>>(A);
+        if (per_grid) fold_replicas_kernel<<<dim3((per_grid + 255) / 256, ny), 256, 0, s>>>(A);
         return check_launch("usl_field_bwd (fold)");
     }
     return 0;
@@ -592,7 +597,7 @@ int usl_mlp_bwd(const usl_mlp_t *m, const usl_mlp_t *gm, const float *h, const f
     A.f.mlp[0] = *m;
     A.f.grid[0].n_levels = USL_IN / USL_FEATS;
     A.p.n = n;
-    A.raw = out; A.feat = h; A.d_raw = dout; A.dh = dh; A.scratch = nullptr;
+    A.raw = out; A.feat = h; A.d_raw = dout; A.dh = dh; A.scratch = nullptr; A.gi_base = 0;
     A.has_gm = gm ? 1 : 0;
     if (gm) A.gm[0] = *gm;
     dim3 grid((unsigned)((n + BWD_THREADS - 1) / BWD_THREADS), 1);

@@ -197,7 +197,7 @@ class _FieldPointsFn(torch.autograd.Function):
             f = meta.pack(sdf_table, rgb_table, dec)
             pts = _points_from_x(x)
             call("usl_field_bwd", byref(f), byref(pts), ptr(raw), ptr(feat), ptr(d_raw), ptr(gs), ptr(gr),
-                 meta.pack_grads(gdec), ptr(bwd_scratch(f, x.device)), stream())
+                 meta.pack_grads(gdec), ptr(bwd_scratch(f, x.device)), 3, stream())
         return (None, dx, gs, gr, *gdec)
 
 
@@ -270,7 +270,7 @@ class _RenderFn(torch.autograd.Function):
             f = meta.pack(sdf_table, rgb_table, dec)
             pts = _points_from_rays(rays_o, rays_d, z_vals)
             call("usl_field_bwd", byref(f), byref(pts), ptr(raw), ptr(feat), ptr(d_raw), ptr(gs), ptr(gr),
-                 meta.pack_grads(gdec) if want_dec else None, ptr(bwd_scratch(f, dev)), st)
+                 meta.pack_grads(gdec) if want_dec else None, ptr(bwd_scratch(f, dev)), 3, st)
         return (None, d_o if ctx.needs_input_grad[1] else None, d_d if ctx.needs_input_grad[2] else None, None,
                 d_beta if ctx.needs_input_grad[4] else None, gs, gr, *gdec)
 

@@ -20,16 +20,35 @@ def slab_range(ny: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def attach_mapping_collectives(step, group=None):
-    """Wire the two exchange steps of a sharded mapping iteration onto a MappingStep."""
+def attach_mapping_collectives(step, group=None, overlap: bool = False):
+    """Wire the exchange steps of a sharded mapping iteration onto a MappingStep.  Returns reduce_rest(), to be called
+    after step.run().  With overlap=True the colour-table gradient (87 % of the bytes) is all-reduced on a side stream
+    while the sdf half of usl_field_bwd still runs (CUDA-graph capturable).  Measured on 2 B200: SLOWER (0.80 vs 0.75 ms per
+    step) -- the two half launches lose the sdf/colour CTA interleaving and NCCL's reduction competes with the atomics for
+    L2 -- so the default is one all-reduce of the flat gradient buffer after the backward."""
     def acc_hook(acc):
         dist.all_reduce(acc, group=group)
     step.acc_hook = acc_hook
+    fs = step.fs
+    if not overlap:
+        def reduce_all():
+            dist.all_reduce(fs.g_grads, group=group)
+            dist.all_reduce(step.d_pose, group=group)
+        return reduce_all
+    side = torch.cuda.Stream()
 
-    def reduce_grads():
-        dist.all_reduce(step.fs.g_grads, group=group)
+    def rgb_hook(g_rgb):
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            dist.all_reduce(g_rgb, group=group)
+    step.rgb_grads_hook = rgb_hook
+
+    def reduce_rest():
+        dist.all_reduce(fs.g_sdf_table, group=group)
+        dist.all_reduce(fs.g_flat, group=group)
         dist.all_reduce(step.d_pose, group=group)
-    return reduce_grads
+        torch.cuda.current_stream().wait_stream(side)
+    return reduce_rest
 
 
 def finalize_loss(acc: torch.Tensor, w_fs, w_center, w_tail, w_depth, w_color) -> torch.Tensor:

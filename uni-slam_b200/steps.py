@@ -107,6 +107,7 @@ class MappingStep(_Profiled):
         self.d_c2w = self.fs.d_c2w; self.d_pose = torch.zeros((max_frames, 7), **f32)
         self.n_rays = 0
         self.acc_hook = None      # multi-GPU: called with self.acc between loss_fwd and loss_bwd (all-reduce of sums/counts)
+        self.rgb_grads_hook = None  # multi-GPU: called with the colour-table gradient as soon as its half of field_bwd is queued
         self._init_prof()
 
     # gradients, in the order Mapper.create_optimizer groups the parameters (Mapper.py:111-139)
@@ -165,8 +166,16 @@ class MappingStep(_Profiled):
                    v(self.gt_depth), v(self.gt_color), v(self.depth), v(self.rgb), ptr(self.acc), None, ptr(self.jac) if joint else None,
                    byref(fs.meta.bound), v(self.d_raw), ptr(fs.g_beta), v(self.d_rays_o) if joint else None,
                    v(self.d_rays_d) if joint else None, ptr(self.loss), st)
-        self._call("usl_field_bwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), v(self.d_raw), ptr(fs.g_sdf_table),
-                   ptr(fs.g_rgb_table), fs.g_mlp, ptr(fs.scratch), st)
+        if self.rgb_grads_hook is None:
+            self._call("usl_field_bwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), v(self.d_raw), ptr(fs.g_sdf_table),
+                       ptr(fs.g_rgb_table), fs.g_mlp, ptr(fs.scratch), 3, st)
+        else:
+            # multi-GPU: the colour half (87 % of the gradient bytes) first, hand it to the collective, then the sdf half
+            self._call("usl_field_bwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), v(self.d_raw), ptr(fs.g_sdf_table),
+                       ptr(fs.g_rgb_table), fs.g_mlp, ptr(fs.scratch), 2, st)
+            self.rgb_grads_hook(fs.g_rgb_table)
+            self._call("usl_field_bwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), v(self.d_raw), ptr(fs.g_sdf_table),
+                       ptr(fs.g_rgb_table), fs.g_mlp, ptr(fs.scratch), 1, st)
         if joint:
             self._call("usl_pose_reduce", v(self.d_rays_o), v(self.d_rays_d), v(self.dirs), v(self.frame_id), v(self.valid), R, K, ptr(self.d_c2w), st)
             call("usl_pose_matrix_bwd", ptr(cam_poses), ptr(self.d_c2w[1:K]), K - 1, ptr(self.d_pose[:K - 1]), st)
