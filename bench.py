@@ -136,14 +136,18 @@ def run_reference(args, rank, world):
     torch.set_num_threads(cores)
     dev_build = "cuda:0" if torch.cuda.is_available() else "cpu"
     scale = 1.0 if dev_build != "cpu" else 0.25       # CPU-only container: smaller frames to build the store quickly
-    wl = wlmod.build_mapping_workload(syn.REPLICA_ROOM0, dev_build, scale_hw=scale)
+    wl = wlmod.build_mapping_workload(syn.CONFIGS[args.config], dev_build, scale_hw=scale)
     wl_cpu = _to_cpu(wl)
     g = torch.Generator().manual_seed(0)
     cfg = wl.cfg
     from oracle import grid_ref
     specs_n = [grid_ref.make_grid_spec(cfg.log2_hash_sdf, wl.per_level_scale).n_params, grid_ref.make_grid_spec(cfg.log2_hash_color, wl.per_level_scale).n_params]
     tabs = [((torch.rand(n, generator=g) * 2 - 1) * 1e-4) for n in specs_n]
-    dec = [torch.cat([((torch.rand(16, 32, generator=g) * 2 - 1) * 0.35).reshape(-1), ((torch.rand(16, 16, generator=g) * 2 - 1) * 0.43).reshape(-1)]) for _ in range(2)]
+    if cfg.decoder_variant == "B":
+        dec = [torch.cat([((torch.rand(16, 32, generator=g) * 2 - 1) * 0.35).reshape(-1), ((torch.rand(16, 16, generator=g) * 2 - 1) * 0.43).reshape(-1)]) for _ in range(2)]
+    else:
+        lin = lambda o, i: [(torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5, (torch.rand(o, generator=g) * 2 - 1) / i ** 0.5]
+        dec = lin(16, 32) + lin(16, 16) + lin(1, 16) + lin(16, 32) + lin(16, 16) + lin(3, 16)
     field = _oracle_field(wl_cpu, tabs, dec, torch.full((1,), 10.0))
     gen = torch.Generator().manual_seed(1)
     times, n_s = [], 0
@@ -196,7 +200,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(dev))
-    cfg = syn.REPLICA_ROOM0
+    cfg = syn.CONFIGS[args.config]
     wl = wlmod.build_mapping_workload(cfg, dev, seed=1 + rank)        # weak scaling: every rank its own ray batch
     meta, tabs, dec, beta = wlmod.init_field_tensors(cfg, wl.bound, wl.per_level_scale, dev, seed=0)
     R, S = wl.n_rays, wl.S
@@ -442,7 +446,7 @@ def run_ours(args, rank, world, local_rank):
             cpu_base = cpu_baseline_leg(wl, tabs, dec, beta)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": {"workload": WORKLOAD, "l2": "flushed between timed steps (256 MiB write)",
+                "data": "synthetic", "config": {"workload": WORKLOAD if args.config == "replica_room0" else f"{args.config} mapping iteration: {wl.K}-frame window, {R} rays x {S} samples, joint_opt, fp32", "l2": "flushed between timed steps (256 MiB write)",
                                                 "cuda_graph": graph is not None, "rays": R, "samples_per_ray": S, "frames": wl.K},
                 "clocks": clocks, "roofline": roofline, "kernels": kern, "kernel_ms_all": kms,
                 "cpu_baseline": cpu_base,
@@ -590,6 +594,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-joint", action="store_true", help="ablation: no joint pose optimisation (no Jacobian in the forward pass)")
+    ap.add_argument("--config", default="replica_room0", choices=["replica_room0", "scannet_scene0000"],
+                    help="workload: BASELINE configs[1] (default, the metric's config) or configs[2] (ScanNet-shaped; extra)")
     ap.add_argument("--overlap", action="store_true", help="N>1: all-reduce the colour-table gradient on a side stream while the sdf half of "
                     "field_bwd runs (measured SLOWER at N=2: 0.80 vs 0.75 ms/step -- NCCL's reduction and the atomics contend for L2)")
     ap.add_argument("--quick", action="store_true", help="mapping step only (used under ncu): skip e2e / tracking / dense query / Adam / cpu baseline")

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256, (WITH_JAC ? USL_FWD_MINB : 4)) field_fwd_
         A.raw[i * 4 + 3] = out[0];
         if (WITH_JAC) {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) A.jac[(int64_t)(9 + d) * A.p.n + i] = tout[0][d] * gate[d];   // component-major: coalesced
+            for (int d = 0; d < 3; ++d) __stcs(A.jac + (int64_t)(9 + d) * A.p.n + i, tout[0][d] * gate[d]);   // component-major: coalesced
         }
     } else {
 #pragma unroll
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256, (WITH_JAC ? USL_FWD_MINB : 4)) field_fwd_
             A.raw[i * 4 + o] = out[o];
             if (WITH_JAC) {
 #pragma unroll
-                for (int d = 0; d < 3; ++d) A.jac[(int64_t)(o * 3 + d) * A.p.n + i] = tout[o][d] * gate[d];
+                for (int d = 0; d < 3; ++d) __stcs(A.jac + (int64_t)(o * 3 + d) * A.p.n + i, tout[o][d] * gate[d]);
             }
         }
     }
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field
     } else {
         const float *hin = A.feat + (int64_t)2 * USL_IN * n + ((int64_t)gi * USL_HID) * n + (active ? i : 0);
 #pragma unroll
-        for (int j = 0; j < USL_HID; ++j) h1[j] = active ? __ldg(hin + (int64_t)j * n) : 0.f;
+        for (int j = 0; j < USL_HID; ++j) h1[j] = active ? __ldcs(hin + (int64_t)j * n) : 0.f;
     }
     // output-side gradient
     float du[4] = {0.f, 0.f, 0.f, 0.f};
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field
 #pragma unroll
         for (int q = 0; q < 8; ++q) {     // features go global -> shared without living in registers
             float2 u0 = make_float2(0.f, 0.f), u1 = u0;
-            if (active) { u0 = __ldg(fin + (int64_t)(2 * q) * fstride); u1 = __ldg(fin + (int64_t)(2 * q + 1) * fstride); }
+            if (active) { u0 = __ldcs(fin + (int64_t)(2 * q) * fstride); u1 = __ldcs(fin + (int64_t)(2 * q + 1) * fstride); }   // read-once stream
             row[4 + q] = make_float4(u0.x, u0.y, u1.x, u1.y);
         }
         __syncwarp();
@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field
     }
 
     // ---- hash-table gradient scatter: d f_l = W1[:, 2l:2l+2]^T dh1, then 8 vector atomics ----
+    // (issuing the scatter BEFORE the weight-gradient tiles was measured slower: 329 vs 316 us)
     if (!(A.dbg & 1) && (STANDALONE ? (active && A.dh != nullptr) : (active && A.grad_table[gi] != nullptr))) {
         float2 *gt = STANDALONE ? nullptr : reinterpret_cast<float2 *>(A.grad_table[gi]);
         // warps walk the levels in rotated order so the atomics in flight at any instant spread over all levels'

@@ -90,7 +90,7 @@ __device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *
     for (int l = 0; l < g.n_levels; ++l) {
         float2 f, df[3];
         level_interp<WITH_JAC>(g.levels[l], table, xc[0], xc[1], xc[2], f, df);
-        if (SAVE_FEAT) feat_out[(int64_t)l * feat_stride] = f;
+        if (SAVE_FEAT) __stcs(feat_out + (int64_t)l * feat_stride, f);    // streaming store: the stash must not evict the tables from L2
         const float4 *wa = reinterpret_cast<const float4 *>(sm.w1t[2 * l]);
         const float4 *wb = reinterpret_cast<const float4 *>(sm.w1t[2 * l + 1]);
 #pragma unroll
@@ -114,7 +114,7 @@ __device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *
     }
     if (SAVE_FEAT && h1_out) {   // hidden pre-activations kept for the backward pass: [16][n]
 #pragma unroll
-        for (int j = 0; j < USL_HID; ++j) h1_out[(int64_t)j * feat_stride] = h[j];
+        for (int j = 0; j < USL_HID; ++j) __stcs(h1_out + (int64_t)j * feat_stride, h[j]);
     }
     mlp_tail<WITH_JAC>(m, sm, h, th, out, tout);
 }
