@@ -326,7 +326,8 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field
 
     // ---- hash-table gradient scatter: d f_l = W1[:, 2l:2l+2]^T dh1, then 8 vector atomics ----
     // (issuing the scatter BEFORE the weight-gradient tiles was measured slower: 329 vs 316 us)
-    if (!(A.dbg & 1) && (STANDALONE ? (active && A.dh != nullptr) : (active && A.grad_table[gi] != nullptr))) {
+    // the table scatter is warp-collective (lane pairing): the condition must be warp-uniform, inactive lanes are predicated
+    if (!(A.dbg & 1) && (STANDALONE ? (active && A.dh != nullptr) : (A.grad_table[gi] != nullptr))) {
         float2 *gt = STANDALONE ? nullptr : reinterpret_cast<float2 *>(A.grad_table[gi]);
         // warps walk the levels in rotated order so the atomics in flight at any instant spread over all levels'
         // sectors instead of hammering the few sectors of one coarse level (L2 same-sector RMW turnaround)
@@ -364,7 +365,8 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field
             const uint32_t R = A.scratch ? A.rep_count[gi][l] : 1u;
             float2 *tab = (R > 1u) ? reinterpret_cast<float2 *>(A.scratch) + A.rep_offset[gi][l] + (size_t)(wid & (R - 1u)) * lv.size
                                    : gt + lv.offset;
-            scatter_level(tab, idx, wt, dfx, dfy);
+            if (A.dbg & 4) { if (active) scatter_level(tab, idx, wt, dfx, dfy); }   // USL_DEBUG_BWD=4: per-lane 16-byte pairing (A/B)
+            else scatter_level_paired(tab, idx, wt, dfx, dfy, active, lane);
         }
     }
 

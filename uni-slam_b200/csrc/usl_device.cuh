@@ -102,6 +102,27 @@ __device__ __forceinline__ void scatter_level(float2 *__restrict__ tab, const ui
     }
 }
 
+// Lane-paired variant: the whole warp takes part (inactive lanes pass act=false).  Lanes (2k, 2k+1) serve ONE point's
+// x-pair per instruction -- the even lane its own first corner, the odd lane its partner's second corner (then the roles
+// swap) -- so the two corners, which share a 32-byte sector in 75 % of the cases (16-byte slot in 50 %), travel in the same
+// instruction and are merged into one L2 atomic sector operation: ~5 instead of 6 (pairing by 16-byte slot) or 8.
+__device__ __forceinline__ void scatter_level_paired(float2 *__restrict__ tab, const uint32_t idx[8], const float wt[8],
+                                                     float dfx, float dfy, bool act, int lane) {
+    const bool odd = (lane & 1) != 0;
+    const bool pact = __shfl_xor_sync(0xffffffffu, act ? 1 : 0, 1) != 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const uint32_t i0 = idx[2 * p], i1 = idx[2 * p + 1];
+        const float v0x = wt[2 * p] * dfx, v0y = wt[2 * p] * dfy;
+        const float v1x = wt[2 * p + 1] * dfx, v1y = wt[2 * p + 1] * dfy;
+        const uint32_t pi1 = __shfl_xor_sync(0xffffffffu, i1, 1);
+        const float pv1x = __shfl_xor_sync(0xffffffffu, v1x, 1), pv1y = __shfl_xor_sync(0xffffffffu, v1y, 1);
+        // A: the even lane's point; B: the odd lane's point
+        if (odd ? pact : act) atomicAdd(tab + (odd ? pi1 : i0), odd ? make_float2(pv1x, pv1y) : make_float2(v0x, v0y));
+        if (odd ? act : pact) atomicAdd(tab + (odd ? i0 : pi1), odd ? make_float2(v0x, v0y) : make_float2(pv1x, pv1y));
+    }
+}
+
 // Gather the 8 corners of one level and interpolate; optionally the d f / d x tangents.
 // TCNN_ORDER = true reproduces tcnn's corner loop (8 weights, fma chain) for the stand-alone Encoding seam;
 // false evaluates the same trilinear polynomial as nested lerps (x, then y, then z): 14 ops per feature instead
