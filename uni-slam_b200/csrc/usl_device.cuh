@@ -128,7 +128,10 @@ __device__ __forceinline__ void scatter_level_paired(float2 *__restrict__ tab, c
 // false evaluates the same trilinear polynomial as nested lerps (x, then y, then z): 14 ops per feature instead
 // of ~26, and the tangents fall out of the differences already formed (6+2+0 extra ops). Results agree to a few
 // ulp (the <=1e-6 feature tolerance of the parity gate); cell indices are identical by construction.
-template <bool WITH_JAC, bool TCNN_ORDER = false>
+// PAIRED = true (warp-collective, every lane of the warp must call it): lanes (2k, 2k+1) fetch ONE point's x-pair per
+// load instruction, so the two corners -- same 32-byte sector in 75 % of the cases -- are served by one L1 wavefront /
+// L2 sector request; the values are handed back to their owner with two shuffles.
+template <bool WITH_JAC, bool TCNN_ORDER = false, bool PAIRED = false>
 __device__ __forceinline__ void level_interp(const usl_level_t &lv, const float2 *__restrict__ table,
                                              float x0, float x1, float x2, float2 &f, float2 df[3]) {
     const Cell c = make_cell(lv, x0, x1, x2);
@@ -139,8 +142,22 @@ __device__ __forceinline__ void level_interp(const usl_level_t &lv, const float2
     // (128-bit loads for x-pairs that share a 16-byte slot were measured: divergent 200 us, predicated 183 us vs
     // 182 us for plain loads -- the gather is bound by the L1 data pipe + latency, not by sector lookups -- so the
     // gather stays 8 x 64-bit; the same pairing does pay off for the atomics, see scatter_level.)
+    if (PAIRED) {
+        const bool odd = (threadIdx.x & 1) != 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = ldg2(tab + idx[k]);
+        for (int p = 0; p < 4; ++p) {
+            const uint32_t i0 = idx[2 * p], i1 = idx[2 * p + 1];
+            const uint32_t pi1 = __shfl_xor_sync(0xffffffffu, i1, 1);
+            const float2 a = ldg2(tab + (odd ? pi1 : i0));     // the even lane's point: (own corner 2p | partner's corner 2p+1)
+            const float2 b = ldg2(tab + (odd ? i0 : pi1));     // the odd lane's point
+            const float2 give = odd ? a : b;                   // the partner's second corner, fetched on its behalf
+            v[2 * p] = odd ? b : a;
+            v[2 * p + 1] = make_float2(__shfl_xor_sync(0xffffffffu, give.x, 1), __shfl_xor_sync(0xffffffffu, give.y, 1));
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = ldg2(tab + idx[k]);
+    }
     if (TCNN_ORDER) {
         float wt[8];
         corner_weights(c, wt);

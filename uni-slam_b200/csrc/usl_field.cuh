@@ -74,7 +74,7 @@ __device__ __forceinline__ void mlp_tail(const usl_mlp_t &m, const MlpSmem &sm, 
 }
 
 // One decoder on one point. out[o] activated outputs; tout[o][d] = d out / d xc.
-template <bool WITH_JAC, bool SAVE_FEAT, int UNR = 1>
+template <bool WITH_JAC, bool SAVE_FEAT, int UNR = 1, bool PAIRED = false>
 __device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *__restrict__ table,
                                              const usl_mlp_t &m, const MlpSmem &sm, const float xc[3],
                                              float2 *__restrict__ feat_out, int64_t feat_stride,
@@ -89,8 +89,8 @@ __device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *
 #pragma unroll UNR
     for (int l = 0; l < g.n_levels; ++l) {
         float2 f, df[3];
-        level_interp<WITH_JAC>(g.levels[l], table, xc[0], xc[1], xc[2], f, df);
-        if (SAVE_FEAT) __stcs(feat_out + (int64_t)l * feat_stride, f);    // streaming store: the stash must not evict the tables from L2
+        level_interp<WITH_JAC, false, PAIRED>(g.levels[l], table, xc[0], xc[1], xc[2], f, df);
+        if (SAVE_FEAT && feat_out) __stcs(feat_out + (int64_t)l * feat_stride, f);    // streaming store: the stash must not evict the tables from L2
         const float4 *wa = reinterpret_cast<const float4 *>(sm.w1t[2 * l]);
         const float4 *wb = reinterpret_cast<const float4 *>(sm.w1t[2 * l + 1]);
 #pragma unroll
