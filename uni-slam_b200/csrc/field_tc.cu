@@ -101,7 +101,10 @@ __device__ __forceinline__ bool tc_load_point(const usl_points_t &p, const usl_f
 }
 
 template <bool SAVE_FEAT>
-__global__ void __launch_bounds__(TC_CTA_THREADS, 4) field_fwd_tc_kernel(const __grid_constant__ FieldTcArgs A) {
+#ifndef USL_TC_MINB
+#define USL_TC_MINB 5
+#endif
+__global__ void __launch_bounds__(TC_CTA_THREADS, USL_TC_MINB) field_fwd_tc_kernel(const __grid_constant__ FieldTcArgs A) {
     __shared__ TcSmem S;
     const int gi = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -164,13 +167,17 @@ __global__ void __launch_bounds__(TC_CTA_THREADS, 4) field_fwd_tc_kernel(const _
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
         const int buf = c & 1;
-        uint32_t tv[3][8];
-#pragma unroll
+        if (c >= 2) mbar_wait(&S.empty[buf], 0);           // the MMAs of chunk c-2 have consumed this operand buffer
+#ifndef USL_TC_LEVEL_UNROLL
+#define USL_TC_LEVEL_UNROLL 4
+#endif
+        constexpr int kLevelUnroll = USL_TC_LEVEL_UNROLL;
+#pragma unroll kLevelUnroll
         for (int q = 0; q < 4; ++q) {
             const int l = 4 * c + q;
             float2 f = make_float2(0.f, 0.f), df[3] = {f, f, f};
             if (active) level_interp<true>(g.levels[l], table, xc[0], xc[1], xc[2], f, df);
-            if (SAVE_FEAT && active) fo[(int64_t)l * n] = f;
+            if (SAVE_FEAT && active) __stcs(fo + (int64_t)l * n, f);
             const float4 *wa = reinterpret_cast<const float4 *>(S.mlp.w1t[2 * l]);
             const float4 *wb = reinterpret_cast<const float4 *>(S.mlp.w1t[2 * l + 1]);
 #pragma unroll
@@ -181,14 +188,10 @@ __global__ void __launch_bounds__(TC_CTA_THREADS, 4) field_fwd_tc_kernel(const _
                 h[4 * e + 2] = fmaf(b.z, f.y, fmaf(a.z, f.x, h[4 * e + 2]));
                 h[4 * e + 3] = fmaf(b.w, f.y, fmaf(a.w, f.x, h[4 * e + 3]));
             }
+            // this level's two K columns (k = 2q, 2q+1 of the chunk) go straight to the operand tile: no tangent registers
 #pragma unroll
-            for (int d = 0; d < 3; ++d) { tv[d][2 * q] = to_tf32(df[d].x); tv[d][2 * q + 1] = to_tf32(df[d].y); }
-        }
-        if (c >= 2) mbar_wait(&S.empty[buf], 0);           // the MMAs of chunk c-2 have consumed this operand buffer
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            *reinterpret_cast<uint4 *>(&S.a[buf][d][rg][0][rr][0]) = make_uint4(tv[d][0], tv[d][1], tv[d][2], tv[d][3]);
-            *reinterpret_cast<uint4 *>(&S.a[buf][d][rg][1][rr][0]) = make_uint4(tv[d][4], tv[d][5], tv[d][6], tv[d][7]);
+            for (int d = 0; d < 3; ++d)
+                *reinterpret_cast<uint2 *>(&S.a[buf][d][rg][q >> 1][rr][2 * (q & 1)]) = make_uint2(to_tf32(df[d].x), to_tf32(df[d].y));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
         mbar_arrive(&S.full[buf]);
@@ -196,29 +199,76 @@ __global__ void __launch_bounds__(TC_CTA_THREADS, 4) field_fwd_tc_kernel(const _
     if (SAVE_FEAT && active) {
         float *ho = A.feat + (int64_t)2 * USL_IN * n + ((int64_t)gi * USL_HID) * n + i;
 #pragma unroll
-        for (int j = 0; j < USL_HID; ++j) ho[(int64_t)j * n] = h[j];
+        for (int j = 0; j < USL_HID; ++j) __stcs(ho + (int64_t)j * n, h[j]);
     }
     mbar_wait(&S.done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float th[3][USL_HID];
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // ---- tail: value path first, then ONE tangent direction at a time (16 TMEM columns -> 16 registers) so the
+    //      accumulators never occupy 48 registers at once ----
+    uint32_t m1 = 0, m2 = 0;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) tmem_ld16(tmem + lane_base + d * 16, th[d]);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-
-    float out[4], tout[4][3];
-    mlp_tail<true>(m, S.mlp, h, th, out, tout);
+    for (int j = 0; j < USL_HID; ++j) { if (h[j] > 0.f) m1 |= 1u << j; h[j] = fmaxf(h[j], 0.f); }
+    float out[4], tout[4][3], da[4];
+    {
+        float u[4] = {S.mlp.bo[0], S.mlp.bo[1], S.mlp.bo[2], S.mlp.bo[3]};
+        if (m.n_hidden == 2) {
+            for (int q = 0; q < USL_HID; ++q) {
+                float sacc = S.mlp.b2[q];
+#pragma unroll
+                for (int j = 0; j < USL_HID; ++j) sacc = fmaf(S.mlp.w2[q][j], h[j], sacc);
+                if (sacc > 0.f) {
+                    m2 |= 1u << q;
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) u[o] = fmaf(S.mlp.wo[o][q], sacc, u[o]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int j = 0; j < USL_HID; ++j) u[o] = fmaf(S.mlp.wo[o][j], h[j], u[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) { out[o] = act_fwd(m.out_act, u[o]); da[o] = act_bwd(m.out_act, out[o]); }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float t1[USL_HID];
+        tmem_ld16(tmem + lane_base + d * 16, t1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < USL_HID; ++j) t1[j] = ((m1 >> j) & 1u) ? t1[j] : 0.f;
+        float tu[4] = {0.f, 0.f, 0.f, 0.f};
+        if (m.n_hidden == 2) {
+            for (int q = 0; q < USL_HID; ++q) {
+                if (!((m2 >> q) & 1u)) continue;
+                float ts = 0.f;
+#pragma unroll
+                for (int j = 0; j < USL_HID; ++j) ts = fmaf(S.mlp.w2[q][j], t1[j], ts);
+#pragma unroll
+                for (int o = 0; o < 4; ++o) tu[o] = fmaf(S.mlp.wo[o][q], ts, tu[o]);
+            }
+        } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int j = 0; j < USL_HID; ++j) tu[o] = fmaf(S.mlp.wo[o][j], t1[j], tu[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) tout[o][d] = da[o] * tu[o];
+    }
     if (active) {
         if (gi == 0) {
             A.raw[i * 4 + 3] = out[0];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) A.jac[(int64_t)(9 + d) * n + i] = tout[0][d] * gate[d];   // component-major: coalesced
+            for (int d = 0; d < 3; ++d) __stcs(A.jac + (int64_t)(9 + d) * n + i, tout[0][d] * gate[d]);   // component-major: coalesced
         } else {
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
                 A.raw[i * 4 + o] = out[o];
 #pragma unroll
-                for (int d = 0; d < 3; ++d) A.jac[(int64_t)(o * 3 + d) * n + i] = tout[o][d] * gate[d];
+                for (int d = 0; d < 3; ++d) __stcs(A.jac + (int64_t)(o * 3 + d) * n + i, tout[o][d] * gate[d]);
             }
         }
     }
