@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field
             const Cell c = make_cell(lv, xc[0], xc[1], xc[2]);
             uint32_t idx[8];
             float wt[8];
-            corner_indices(lv, c, idx);
+            corner_indices<true>(lv, c, idx);           // xc is clamped to [0,1]
             corner_weights(c, wt);
             const uint32_t R = A.scratch ? A.rep_count[gi][l] : 1u;
             float2 *tab = (R > 1u) ? reinterpret_cast<float2 *>(A.scratch) + A.rep_offset[gi][l] + (size_t)(wid & (R - 1u)) * lv.size

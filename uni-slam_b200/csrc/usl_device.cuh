@@ -38,29 +38,30 @@ __device__ __forceinline__ Cell make_cell(const usl_level_t &lv, float x0, float
 }
 
 // Entry indices (within the level) of the 8 corners; corner c: bit d set -> g_d + 1.
-// tcnn grid_index<3, CoherentPrime> with `% size`: hashed levels have power-of-two size (mask),
-// dense levels only wrap at the x==1 boundary (or for out-of-range inputs) -> rare slow path.
+// tcnn grid_index<3, CoherentPrime> with `% size`: hashed levels have power-of-two size (mask).  Dense levels only
+// wrap at the x == 1 boundary: for coordinates clamped to [0,1] (CLAMPED = true: every fused field kernel) the linear
+// index is < 2*size, so one conditional subtract is the exact modulo; un-clamped callers (stand-alone Encoding seam)
+// keep the general `%`.
+template <bool CLAMPED = false>
 __device__ __forceinline__ void corner_indices(const usl_level_t &lv, const Cell &c, uint32_t idx[8]) {
     if (lv.hashed) {
         const uint32_t mask = lv.size - 1u;
         const uint32_t hx0 = c.g[0], hx1 = c.g[0] + 1u;
         const uint32_t hy0 = c.g[1] * USL_PRIME_Y, hy1 = hy0 + USL_PRIME_Y;
         const uint32_t hz0 = c.g[2] * USL_PRIME_Z, hz1 = hz0 + USL_PRIME_Z;
-        idx[0] = (hx0 ^ hy0 ^ hz0) & mask;
-        idx[1] = (hx1 ^ hy0 ^ hz0) & mask;
-        idx[2] = (hx0 ^ hy1 ^ hz0) & mask;
-        idx[3] = (hx1 ^ hy1 ^ hz0) & mask;
-        idx[4] = (hx0 ^ hy0 ^ hz1) & mask;
-        idx[5] = (hx1 ^ hy0 ^ hz1) & mask;
-        idx[6] = (hx0 ^ hy1 ^ hz1) & mask;
-        idx[7] = (hx1 ^ hy1 ^ hz1) & mask;
+        const uint32_t h00 = hy0 ^ hz0, h10 = hy1 ^ hz0, h01 = hy0 ^ hz1, h11 = hy1 ^ hz1;
+        idx[0] = (hx0 ^ h00) & mask; idx[1] = (hx1 ^ h00) & mask;
+        idx[2] = (hx0 ^ h10) & mask; idx[3] = (hx1 ^ h10) & mask;
+        idx[4] = (hx0 ^ h01) & mask; idx[5] = (hx1 ^ h01) & mask;
+        idx[6] = (hx0 ^ h11) & mask; idx[7] = (hx1 ^ h11) & mask;
     } else {
         const uint32_t res = lv.res, res2 = lv.res * lv.res;
         const uint32_t base = c.g[0] + c.g[1] * res + c.g[2] * res2;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             uint32_t i = base + (k & 1) + ((k >> 1) & 1) * res + ((k >> 2) & 1) * res2;
-            if (i >= lv.size) i %= lv.size;
+            if (CLAMPED) { if (i >= lv.size) i -= lv.size; }
+            else { if (i >= lv.size) i %= lv.size; }
             idx[k] = i;
         }
     }
@@ -136,7 +137,7 @@ __device__ __forceinline__ void level_interp(const usl_level_t &lv, const float2
                                              float x0, float x1, float x2, float2 &f, float2 df[3]) {
     const Cell c = make_cell(lv, x0, x1, x2);
     uint32_t idx[8];
-    corner_indices(lv, c, idx);
+    corner_indices<!TCNN_ORDER>(lv, c, idx);      // the fused kernels (TCNN_ORDER = false) always pass clamped coordinates
     const float2 *tab = table + lv.offset;
     float2 v[8];
     // (128-bit loads for x-pairs that share a 16-byte slot were measured: divergent 200 us, predicated 183 us vs
