@@ -32,8 +32,7 @@ def attach_mapping_collectives(step, group=None, overlap: bool = False):
     fs = step.fs
     if not overlap:
         def reduce_all():
-            dist.all_reduce(fs.g_grads, group=group)
-            dist.all_reduce(step.d_pose, group=group)
+            dist.all_reduce(fs.g_grads, group=group)          # tables + decoders + beta + pose gradients: one collective
         return reduce_all
     side = torch.cuda.Stream()
 
@@ -46,7 +45,6 @@ def attach_mapping_collectives(step, group=None, overlap: bool = False):
     def reduce_rest():
         dist.all_reduce(fs.g_sdf_table, group=group)
         dist.all_reduce(fs.g_flat, group=group)
-        dist.all_reduce(step.d_pose, group=group)
         torch.cuda.current_stream().wait_stream(side)
     return reduce_rest
 

@@ -55,7 +55,7 @@ class _FieldState:
             # clears it and (multi-GPU) a single all-reduce sums it.  Table sizes are multiples of 16 floats, so the
             # 16-byte vector atomics stay aligned.
             n_scratch = ops.bwd_scratch_floats(self.field)
-            sizes = [sdf_table.numel(), rgb_table.numel()] + [t.numel() for t in self.dec] + [1]
+            sizes = [sdf_table.numel(), rgb_table.numel()] + [t.numel() for t in self.dec] + [1, max_frames * 7]   # ..., beta, d pose
             pad = (-sum(sizes)) % 32                                  # keep the scratch block 128-byte aligned (16-byte vector atomics)
             sizes += [pad, max(n_scratch, 4), L.LOSS_SLOTS, max_frames * 12]   # + loss accumulators + d c2w: one memset clears all
             self.g_all = torch.zeros(sum(sizes), device=sdf_table.device, dtype=torch.float32)
@@ -64,14 +64,15 @@ class _FieldState:
                 views.append(self.g_all[o:o + s_])
                 o += s_
             self.g_sdf_table, self.g_rgb_table = views[0], views[1]
-            self.g_dec = [v.view(t.shape) for v, t in zip(views[2:-5], self.dec)]
-            self.g_beta = views[-5]
+            self.g_dec = [v.view(t.shape) for v, t in zip(views[2:-6], self.dec)]
+            self.g_beta = views[-6]
+            self.d_pose = views[-5].view(max_frames, 7)             # inside the gradient block: one all-reduce covers it
             self.scratch = views[-3]                                 # replicated coarse levels (usl_field_bwd workspace)
             self.acc = views[-2]
             self.d_c2w = views[-1].view(max_frames, 12)
             self.n_grad = sum(sizes[:-4])
             self.g_grads = self.g_all[:self.n_grad]                  # what a multi-GPU all-reduce must sum
-            self.g_flat = self.g_all[sizes[0] + sizes[1]:self.n_grad]   # decoder + beta gradients
+            self.g_flat = self.g_all[sizes[0] + sizes[1]:self.n_grad]   # decoder + beta + pose gradients
             self.g_mlp = meta.pack_grads(self.g_dec)
 
     def repack(self):
@@ -104,7 +105,7 @@ class MappingStep(_Profiled):
         self.acc = self.fs.acc; self.loss = torch.zeros((1,), **f32)
         self.d_raw = torch.empty((R, S, 4), **f32)
         self.d_rays_o = torch.empty((R, 3), **f32); self.d_rays_d = torch.empty((R, 3), **f32)
-        self.d_c2w = self.fs.d_c2w; self.d_pose = torch.zeros((max_frames, 7), **f32)
+        self.d_c2w = self.fs.d_c2w; self.d_pose = self.fs.d_pose
         self.n_rays = 0
         self.acc_hook = None      # multi-GPU: called with self.acc between loss_fwd and loss_bwd (all-reduce of sums/counts)
         self.rgb_grads_hook = None  # multi-GPU: called with the colour-table gradient as soon as its half of field_bwd is queued
