@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(256, (WITH_JAC ? USL_FWD_MINB : 4)) field_fwd_
     // no early exit: the paired gather is warp-collective; inactive lanes run on a dummy point and write nothing
     float xc[3] = {0.f, 0.f, 0.f}, gate[3] = {0.f, 0.f, 0.f};
     const bool active = (i < A.p.n) && load_point(A.p, A.f, i, xc, gate);
+    if (!__any_sync(0xffffffffu, active)) return;           // warps made only of filtered rays cost nothing
     const usl_grid_t &g = A.f.grid[gi];
     float out[4], tout[4][3];
     // stash layout: features [2][L][n][2] then hidden pre-activations [2][16][n]

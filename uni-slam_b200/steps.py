@@ -12,6 +12,7 @@ because rays are masked instead of compacted, the draws are indexed by ray slot:
 t_rand_uni (R,n_stratified), u_pdf (R,n_importance).  (The drop-in ``modules.Renderer`` keeps the
 reference's compacted draw shapes instead.)
 """
+import os
 from ctypes import byref
 from typing import List, Optional, Sequence
 
@@ -109,7 +110,15 @@ class MappingStep(_Profiled):
         self.n_rays = 0
         self.acc_hook = None      # multi-GPU: called with self.acc between loss_fwd and loss_bwd (all-reduce of sums/counts)
         self.rgb_grads_hook = None  # multi-GPU: called with the colour-table gradient as soon as its half of field_bwd is queued
+        # independent pieces (gradient zero-fill; pose-gradient reduction) run on a side stream next to the critical path
+        self.side_branches = os.environ.get("USL_SIDE_BRANCHES", "1") != "0"
+        self._side = None
         self._init_prof()
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        return self._side
 
     # gradients, in the order Mapper.create_optimizer groups the parameters (Mapper.py:111-139)
     @property
@@ -125,7 +134,17 @@ class MappingStep(_Profiled):
         fs, S = self.fs, self.S
         joint = cam_poses is not None
         K = (cam_poses.shape[0] + 1) if joint else 0
-        fs.g_all.zero_()                                   # gradients, replica scratch, loss accumulators, d c2w: one memset
+        fork = self.side_branches and not self.profile
+        cur = torch.cuda.current_stream()
+        side = self._side_stream() if fork else None
+        # gradients, replica scratch, loss accumulators, d c2w: one memset -- first needed by usl_loss_fwd, so it runs
+        # beside ray set-up / z-sampling instead of in front of them
+        if fork:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                fs.g_all.zero_()
+        else:
+            fs.g_all.zero_()
         # ---- a-3 + a-4 + a-5 (+ pose -> matrix): one launch ----
         rs = L.RaySetup()
         rs.mode, rs.n_batches = 0, len(batches)
@@ -157,6 +176,8 @@ class MappingStep(_Profiled):
         self._call("usl_field_fwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), ptr(self.jac) if joint else None, st)
         self._call("usl_composite_fwd", v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), R, S, v(self.term), v(self.punc), v(self.depth),
                    v(self.rgb), v(self.dunc), None, st)
+        if fork:
+            cur.wait_stream(side)
         # ---- a-9: losses, phase 1 (sums + counts) ----
         self._call("usl_loss_fwd", byref(self.loss_args), v(self.raw), v(self.z), v(self.gt_depth), v(self.gt_color), v(self.valid), v(self.punc),
                    v(self.depth), v(self.rgb), None, R, S, ptr(self.acc), v(self.mask), st)
@@ -167,6 +188,14 @@ class MappingStep(_Profiled):
                    v(self.gt_depth), v(self.gt_color), v(self.depth), v(self.rgb), ptr(self.acc), None, ptr(self.jac) if joint else None,
                    byref(fs.meta.bound), v(self.d_raw), ptr(fs.g_beta), v(self.d_rays_o) if joint else None,
                    v(self.d_rays_d) if joint else None, ptr(self.loss), st)
+        def pose_grads(st_):
+            self._call("usl_pose_reduce", v(self.d_rays_o), v(self.d_rays_d), v(self.dirs), v(self.frame_id), v(self.valid), R, K, ptr(self.d_c2w), st_)
+            call("usl_pose_matrix_bwd", ptr(cam_poses), ptr(self.d_c2w[1:K]), K - 1, ptr(self.d_pose[:K - 1]), st_)
+
+        if joint and fork:                                 # needs only the ray gradients: runs beside the table scatter
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                pose_grads(side.cuda_stream)
         if self.rgb_grads_hook is None:
             self._call("usl_field_bwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), v(self.d_raw), ptr(fs.g_sdf_table),
                        ptr(fs.g_rgb_table), fs.g_mlp, ptr(fs.scratch), 3, st)
@@ -178,8 +207,10 @@ class MappingStep(_Profiled):
             self._call("usl_field_bwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), v(self.d_raw), ptr(fs.g_sdf_table),
                        ptr(fs.g_rgb_table), fs.g_mlp, ptr(fs.scratch), 1, st)
         if joint:
-            self._call("usl_pose_reduce", v(self.d_rays_o), v(self.d_rays_d), v(self.dirs), v(self.frame_id), v(self.valid), R, K, ptr(self.d_c2w), st)
-            call("usl_pose_matrix_bwd", ptr(cam_poses), ptr(self.d_c2w[1:K]), K - 1, ptr(self.d_pose[:K - 1]), st)
+            if fork:
+                cur.wait_stream(side)
+            else:
+                pose_grads(st)
         return self.loss
 
 
