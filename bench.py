@@ -437,8 +437,10 @@ def run_ours(args, rank, world, local_rank):
         extra["fused_adam_ms_per_step"] = e0.elapsed_time(e1) / 10     # usl_adam_step (f1)
         extra.update(bench_tracking(P, wl, meta, tabs, dec, beta, cfg, dev, args))
     dq = bench_dense_query(P, wl, meta, tabs, dec, dev, rank, world, dist)      # every rank: its y-slab
+    ri = bench_render_img(P, cfg, meta, tabs, dec, beta, dev, rank, world, dist)  # every rank: its rows of the frame
     if rank == 0:
         extra.update(dq)
+        extra.update(ri)
 
     if rank == 0:
         cpu_base = None
@@ -564,6 +566,59 @@ def bench_dense_query(P, wl, meta, tabs, dec, dev, rank, world, dist=None):
     return {"dense_query_points": npts, "dense_query_ms": ms, "dense_query_points_per_s": npts / (ms * 1e-3),
             "dense_query_alg_gbs": npts * 1028 / (ms * 1e-3) / 1e9, "dense_query_frac_of_hbm_peak_per_gpu": npts * 1028 / (ms * 1e-3) / 1e9 / peak / world,
             "dense_query_gather_ms": gather_ms}
+
+
+def bench_render_img(P, cfg, meta, tabs, dec, beta, dev, rank, world, dist=None, frames=3):
+    """Renderer.render_img over a full-resolution frame (Replica: 680x1200 = 816 000 rays x 40 samples),
+    forward only, rows sharded across the ranks (no data-path collective), torch.rand draws inside the timed region
+    as in the reference (one set per chunk); time = max over ranks; the rank slabs are then gathered to rank 0."""
+    par = importlib.import_module("uni-slam_b200.parallel")
+    syn = P.synthetic
+    seq = syn.SyntheticSequence(cfg, n_frames=8, device=dev, seed=1)
+    _, dep, c2w = seq.frame(3)
+    cam = seq.cam
+    step = P.RenderImageStep(meta, tabs[0].detach(), tabs[1].detach(), [d.detach() for d in dec], beta.detach(),
+                             n_stratified=cfg.n_stratified, n_importance=cfg.n_importance, truncation=cfg.truncation,
+                             H=cam.H, W=cam.W, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy)
+    r0, r1 = par.slab_range(cam.H, rank, world)
+    p0, p1 = r0 * cam.W, r1 * cam.W
+    n, S = p1 - p0, step.S
+    out = step.alloc_outputs(n)
+    C = step.chunk
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    t_rand = torch.empty((C, S), device=dev); t_uni = torch.empty((C, cfg.n_stratified), device=dev); u_pdf = torch.empty((C, cfg.n_importance), device=dev)
+
+    def frame():
+        for c0 in range(0, n, C):                        # chunk by chunk so the draws stay chunk-sized, like the reference's
+            m = min(C, n - c0)
+            t_rand.uniform_(generator=gen); t_uni.uniform_(generator=gen); u_pdf.uniform_(generator=gen)
+            step.run(c2w, dep, t_rand[:m], t_uni[:m], u_pdf[:m], pixel_begin=p0 + c0, pixel_end=p0 + c0 + m,
+                     out={k: v[c0:c0 + m] for k, v in out.items()})
+
+    frame(); frame()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(frames):
+        frame()
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / frames], device=dev, dtype=torch.float64)
+    gather_ms = None
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for _ in range(2):
+            g0 = time.perf_counter()
+            img = par.gather_slabs(out["color"].reshape(-1), cam.H, cam.W, 3, rank, world)
+            torch.cuda.synchronize(); dist.barrier()
+            gather_ms = (time.perf_counter() - g0) * 1e3
+            del img
+    ms = float(t[0])
+    rays = cam.H * cam.W
+    return {"render_img_rays": rays, "render_img_ms_per_frame": ms, "render_img_rays_per_s": rays / (ms * 1e-3),
+            "render_img_samples_per_s": rays * S / (ms * 1e-3), "render_img_mean_depth": float(out["depth"].mean()),
+            "render_img_gather_ms": gather_ms}
 
 
 def cpu_baseline_leg(wl, tabs, dec, beta):

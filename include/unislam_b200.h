@@ -171,7 +171,9 @@ typedef struct usl_ray_batch {          /* one get_samples_all call (src/Mapper.
     int32_t K, n, frame_base, _pad;
 } usl_ray_batch_t;
 typedef struct usl_ray_setup {
-    int32_t mode;                       /* 0: keyframe batches (mapper), 1: image window (tracker) */
+    int32_t mode;                       /* 0: keyframe batches (mapper), 1: image window (tracker), 2: n_rays consecutive
+                                         * pixels of the full frame from pixel_begin (render_img, src/utils/Renderer.py:160-223:
+                                         * get_rays over the image, no bbox prefilter, valid = 1) */
     int32_t n_batches;
     usl_ray_batch_t batch[2];
     const float *depth_img, *color_img; /* mode 1: [H,W], [H,W,3] */
@@ -191,6 +193,7 @@ typedef struct usl_ray_setup {
     int32_t *frame_id;                  /* nullable */
     uint8_t *valid;
     float *z;                           /* [n_rays,S]; rows of depth-less rays are left for usl_zsample_nodepth */
+    int64_t pixel_begin;                /* mode 2: row-major index (j*W + i) of the first pixel; gt_color / dirs_out nullable */
 } usl_ray_setup_t;
 USL_API int usl_ray_setup(const usl_ray_setup_t *a, usl_stream_t stream);
 

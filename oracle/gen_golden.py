@@ -31,6 +31,9 @@ CASES = {
     "map_scannet_k23": dict(yaml="configs/ScanNet/scene0000.yaml", H=46, W=62, s=0.1, n_kf=22, pixels=230, lr_factor=1),
     "track_replica": dict(yaml="configs/Replica/room0.yaml", H=60, W=80, s=1 / 15.0, pixels=200, edge=6),
     "track_scannet": dict(yaml="configs/ScanNet/scene0000.yaml", H=46, W=62, s=0.1, pixels=200, edge=5),
+    # Renderer.render_img (Renderer.py:160-223): whole frame in ray_batch_size chunks, last chunk ragged
+    "img_replica": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, ray_batch=500),
+    "img_scannet": dict(yaml="configs/ScanNet/scene0000.yaml", H=23, W=31, s=0.05, ray_batch=300),
 }
 
 
@@ -353,12 +356,54 @@ def gen_tracking(name, case):
     print(name, "rays", r["gt_depth"].numel(), "loss", loss, "gradT", out["grad_T"], "gradR", out["grad_R"])
 
 
+def gen_render_img(name, case):
+    from src.utils.Renderer import Renderer
+    cfg = _load_cfg(case)
+    bound, grids, dec = _build_world(cfg, 80)
+    H, W = case["H"], case["W"]
+    cam = cfg["cam"]
+    frames, _ = _frames(cfg, case, 3, seed=13)
+    col, dep, c2w = frames[2]
+    fake = types.SimpleNamespace(bound=bound, device="cpu", H=H, W=W, fx=cam["fx"], fy=cam["fy"], cx=cam["cx"], cy=cam["cy"])
+    renderer = Renderer(cfg, fake, ray_batch_size=case["ray_batch"])
+    rec = Recorder(); rec.install()
+    try:
+        torch.manual_seed(5)
+        ret = renderer.render_img(([grids[0]], [grids[1]]), dec, c2w, cfg["model"]["truncation"], "cpu", gt_depth=dep)
+    finally:
+        rec.uninstall()
+    out = {}
+    out["meta_H_W_fx_fy_cx_cy"] = np.array([H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"]], dtype=np.float64)
+    out["bound"] = _np(bound); out["truncation"] = np.array(cfg["model"]["truncation"]); out["ray_batch"] = np.array(case["ray_batch"])
+    out["n_stratified"] = np.array(cfg["rendering"]["n_stratified"]); out["n_importance"] = np.array(cfg["rendering"]["n_importance"])
+    out["log2_hash"] = np.array([cfg["grid"]["hash_size_sdf"], cfg["grid"]["hash_size_color"]])
+    out["per_level_scale"] = np.array([grids[0].spec.per_level_scale, grids[1].spec.per_level_scale])
+    out["variant"] = np.array("B" if cfg["grid"]["tcnn_network"] else "A")
+    out["c2w"] = _np(c2w); out["depth_img"] = _np(dep)
+    # torch.rand draws in consumption order: per chunk (n_valid,S) then, if the chunk has holes, (n0,n_strat), (n0,n_imp)
+    rands = [t for k, t in rec.draws if k == "rand"]
+    out["n_draws"] = np.array(len(rands))
+    out["draw_shapes"] = np.array([list(t.shape) for t in rands], dtype=np.int64)
+    out["draws_flat"] = np.concatenate([_np(t).reshape(-1) for t in rands])
+    for nm, o in zip(("depth", "color", "term", "pixel_unc", "depth_unc"), ret):
+        out["ret_" + nm] = _np(o)
+        out["dtype_" + nm] = np.array(str(o.dtype))
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "pixels", H * W, "holes", int((dep == 0).sum()), "draws", len(rands), "mean depth", float(ret[0].mean()))
+
+
 def main():
     _setup_paths()
     torch.set_num_threads(8)
+    only = sys.argv[1:]
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         if name.startswith("map"):
             gen_mapping(name, case)
+        elif name.startswith("img"):
+            gen_render_img(name, case)
         else:
             gen_tracking(name, case)
 

@@ -348,6 +348,33 @@ def render_batch_ray(field: Field, rays_d, rays_o, gt_depth, n_stratified, n_imp
     return composite(raw, z_vals, field.beta)
 
 
+def render_img(field: Field, H, W, fx, fy, cx, cy, c2w, gt_depth, n_stratified, n_importance, truncation,
+               ray_batch_size, draw_rand):
+    """Renderer.render_img (Renderer.py:160-223): get_rays over the whole frame, render_batch_ray per chunk of
+    ray_batch_size rays (the last one ragged), outputs concatenated; everything but colour is returned as float64
+    (Renderer.py:205-209).  draw_rand(shape) supplies torch.rand draws in the reference's consumption order: per chunk
+    (n_valid,S), then -- only if the chunk has depth-less rays -- (n0,n_stratified) and (n0,n_importance).
+    Returns (depth, color, termination_prob, pixel_unc, depth_unc) shaped (H,W[,3])."""
+    S = n_stratified + n_importance
+    with torch.no_grad():
+        rays_o, rays_d = full_image_rays(H, W, fx, fy, cx, cy, c2w)
+        rays_o = rays_o.reshape(-1, 3); rays_d = rays_d.reshape(-1, 3)
+        gt_depth = gt_depth.reshape(-1)
+        outs = [[] for _ in range(5)]
+        for i in range(0, rays_d.shape[0], ray_batch_size):
+            gt = gt_depth[i:i + ray_batch_size]
+            n_valid = int((gt > 0).sum()); n0 = gt.numel() - n_valid
+            t_rand = draw_rand((n_valid, S))
+            t_uni = draw_rand((n0, n_stratified)) if n0 > 0 else None
+            u_pdf = draw_rand((n0, n_importance)) if n0 > 0 else None
+            term, punc, depth, color, _, _, dunc = render_batch_ray(field, rays_d[i:i + ray_batch_size], rays_o[i:i + ray_batch_size], gt,
+                                                                    n_stratified, n_importance, truncation, t_rand, t_uni, u_pdf)
+            for lst, v in zip(outs, (depth.double(), color, term.double(), punc.double(), dunc.double())):
+                lst.append(v)
+        depth, color, term, punc, dunc = [torch.cat(o, dim=0) for o in outs]
+        return depth.reshape(H, W), color.reshape(H, W, 3), term.reshape(H, W), punc.reshape(H, W), dunc.reshape(H, W)
+
+
 # ----------------------------------------------------------------------------------------------
 # losses  (src/Mapper.py:141-175,412-440; src/Tracker.py:113-147,208-238)
 # ----------------------------------------------------------------------------------------------

@@ -73,3 +73,34 @@ def rel_err(a, b):
 def max_rel(a, b, floor=1e-6):
     a = torch.as_tensor(a, dtype=torch.float64); b = torch.as_tensor(b, dtype=torch.float64)
     return float(((a - b).abs() / b.abs().clamp_min(floor)).max())
+
+
+def golden_img_draws(g):
+    """The recorded torch.rand draws of a render_img fixture, in consumption order."""
+    flat = torch.from_numpy(g["draws_flat"])
+    out, o = [], 0
+    for shp in g["draw_shapes"]:
+        n = int(shp[0]) * int(shp[1])
+        out.append(flat[o:o + n].reshape(int(shp[0]), int(shp[1]))); o += n
+    assert o == flat.numel()
+    return out
+
+
+def img_draws_by_ray_slot(g):
+    """Re-index the per-chunk compacted draws of a render_img fixture by ray slot, the layout the fused
+    steps consume: t_rand (R,S), t_uni (R,n_strat), u_pdf (R,n_imp); rows of the other ray class stay 0."""
+    ns, ni = int(g["n_stratified"]), int(g["n_importance"])
+    S = ns + ni
+    gt = torch.from_numpy(g["depth_img"]).reshape(-1)
+    R, B = gt.numel(), int(g["ray_batch"])
+    t_rand = torch.zeros((R, S)); t_uni = torch.zeros((R, ns)); u_pdf = torch.zeros((R, ni))
+    draws = golden_img_draws(g)
+    for i in range(0, R, B):
+        m = gt[i:i + B] > 0
+        rows = torch.arange(i, min(i + B, R))
+        t_rand[rows[m]] = draws.pop(0)
+        if int((~m).sum()) > 0:
+            t_uni[rows[~m]] = draws.pop(0)
+            u_pdf[rows[~m]] = draws.pop(0)
+    assert not draws
+    return t_rand, t_uni, u_pdf

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from oracle import grid_ref, path_ref
-from helpers import DrawQueue, golden_field, load_golden, max_rel, pkg, rel_err
+from helpers import DrawQueue, golden_field, golden_img_draws, img_draws_by_ray_slot, load_golden, max_rel, pkg, rel_err
 import gpu_cases
 
 pytestmark = pytest.mark.gpu
@@ -232,6 +232,83 @@ def test_dropin_renderer_matches_reference(name, monkeypatch):
     for pre, e in (("grad_sdf_table", encs[0]), ("grad_rgb_table", encs[1])):
         assert rel_err(e.params.grad.cpu()[T(g[pre + "_idx"])], g[pre + "_val"]) < 1e-3
     assert rays_o.grad is not None and torch.isfinite(rays_o.grad).all() and torch.isfinite(rays_d.grad).all()
+
+
+def _dropin_modules(P, g, seed_salt):
+    variant = str(g["variant"])
+    cfg = {"grid_mode": "hash_grid", "grid": {"tcnn_network": variant == "B"}, "scale": 1,
+           "rendering": {"perturb": True, "n_stratified": int(g["n_stratified"]), "n_importance": int(g["n_importance"])}}
+    meta, tabs, dec, beta = gpu_cases.cuda_field(g, seed_salt, DEV)
+    encs = []
+    for i in range(2):
+        e = P.Encoding(3, {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": int(g["log2_hash"][i]),
+                           "base_resolution": 16, "per_level_scale": float(g["per_level_scale"][i])}, dtype=torch.float).to(DEV)
+        with torch.no_grad():
+            e.params.copy_(tabs[i])
+        encs.append(e)
+    decoders = P.Decoders(cfg, c_dim=32, truncation=float(g["truncation"]), learnable_beta=True).to(DEV)
+    with torch.no_grad():
+        for t, src in zip(decoders.decoder_tensors(), dec):
+            t.copy_(src)
+    return cfg, encs, decoders
+
+
+def _check_img(ret, g, where):
+    """depth / colour / termination / uncertainties of a rendered frame vs the reference's render_img output."""
+    for nm, t in zip(("depth", "color", "term", "pixel_unc", "depth_unc"), ret):
+        ref = T(g["ret_" + nm]).double().reshape(-1)
+        got = t.detach().cpu().double().reshape(-1)
+        # 1e-4 relative on the rendered values (north-star tolerance); the two uncertainties are differences of nearly
+        # equal numbers (1 - sum w, depth - z), so they get the same tolerance on an absolute floor of their scale
+        floor = 1e-3 if nm in ("pixel_unc", "depth_unc") else 1e-4
+        assert max_rel(got, ref, floor) < 1e-4, (where, nm)
+
+
+@pytest.mark.parametrize("name", ["img_replica", "img_scannet"])
+def test_dropin_render_img_matches_reference(name, monkeypatch):
+    """f3 / B4: modules.Renderer.render_img (whole frame in ray_batch_size chunks, reference RNG order) vs the
+    unmodified reference's Renderer.render_img output (tests/golden/img_*.npz)."""
+    P = pkg()
+    g = load_golden(name)
+    cfg, encs, decoders = _dropin_modules(P, g, 80)
+    H, W, fx, fy, cx, cy = [float(v) for v in g["meta_H_W_fx_fy_cx_cy"]]
+    fake = type("U", (), dict(bound=T(g["bound"]), device=DEV, H=int(H), W=int(W), fx=fx, fy=fy, cx=cx, cy=cy))()
+    renderer = P.Renderer(cfg, fake, ray_batch_size=int(g["ray_batch"]))
+    q = DrawQueue([d.to(DEV) for d in golden_img_draws(g)])
+    monkeypatch.setattr(torch, "rand", lambda shape, device=None, **k: q(tuple(shape)))
+    ret = renderer.render_img(([encs[0]], [encs[1]]), decoders, T(g["c2w"]), float(g["truncation"]), DEV, gt_depth=T(g["depth_img"]).to(DEV))
+    monkeypatch.undo()
+    assert not q.draws                                                            # consumed exactly the reference's draws
+    for nm, t in zip(("depth", "color", "term", "pixel_unc", "depth_unc"), ret):
+        assert str(t.dtype) == str(g["dtype_" + nm]) and tuple(t.shape) == g["ret_" + nm].shape, nm
+    _check_img(ret, g, "drop-in")
+
+
+@pytest.mark.parametrize("name", ["img_replica", "img_scannet"])
+def test_render_image_step_matches_reference(name):
+    """f3: the fused forward-only frame renderer (in-kernel get_rays, masks instead of compaction) vs the reference's
+    render_img output; ragged chunks, and a row-sharded render (two pixel ranges) must give the same frame."""
+    P = pkg()
+    g = load_golden(name)
+    meta, tabs, dec, beta = gpu_cases.cuda_field(g, 80, DEV)
+    H, W, fx, fy, cx, cy = [float(v) for v in g["meta_H_W_fx_fy_cx_cy"]]
+    H, W = int(H), int(W)
+    t_rand, t_uni, u_pdf = [t.to(DEV) for t in img_draws_by_ray_slot(g)]
+    c2w, dep = T(g["c2w"]).to(DEV), T(g["depth_img"]).to(DEV)
+    kw = dict(n_stratified=int(g["n_stratified"]), n_importance=int(g["n_importance"]), truncation=float(g["truncation"]),
+              H=H, W=W, fx=fx, fy=fy, cx=cx, cy=cy)
+    keys = ("depth", "color", "term", "pixel_unc", "depth_unc")
+    whole = P.RenderImageStep(meta, tabs[0], tabs[1], dec, beta, chunk_rays=H * W, **kw).run(c2w, dep, t_rand, t_uni, u_pdf)
+    _check_img([whole[k] for k in keys], g, "one chunk")
+    step = P.RenderImageStep(meta, tabs[0], tabs[1], dec, beta, chunk_rays=257, **kw)      # ragged chunks
+    chunked = step.run(c2w, dep, t_rand, t_uni, u_pdf)
+    for k in keys:
+        assert torch.equal(chunked[k], whole[k]), k                                # chunking must not change a bit
+    cut = (H // 2) * W                                                             # row shard, as parallel.slab_range cuts it
+    a = step.run(c2w, dep, t_rand[:cut], t_uni[:cut], u_pdf[:cut], pixel_begin=0, pixel_end=cut)
+    b = step.run(c2w, dep, t_rand[cut:], t_uni[cut:], u_pdf[cut:], pixel_begin=cut, pixel_end=H * W)
+    for k in keys:
+        assert torch.equal(torch.cat([a[k], b[k]]), whole[k]), k
 
 
 def test_dense_sdf_query_matches_oracle():

@@ -83,3 +83,19 @@ def test_tracking_iteration_matches_reference(name):
     loss.backward()
     assert rel_err(cam_pose.grad[:, 4:], g["grad_T"]) < 1e-5
     assert rel_err(cam_pose.grad[:, :4], g["grad_R"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["img_replica", "img_scannet"])
+def test_render_img_matches_reference(name):
+    """Renderer.render_img (Renderer.py:160-223) of the unmodified reference vs oracle/path_ref.render_img."""
+    from helpers import golden_img_draws
+    g = load_golden(name)
+    field = golden_field(g, 80, requires_grad=False)
+    H, W, fx, fy, cx, cy = g["meta_H_W_fx_fy_cx_cy"]
+    H, W = int(H), int(W)
+    ret = path_ref.render_img(field, H, W, fx, fy, cx, cy, T(g["c2w"]), T(g["depth_img"]), int(g["n_stratified"]),
+                              int(g["n_importance"]), float(g["truncation"]), int(g["ray_batch"]), DrawQueue(golden_img_draws(g)))
+    for nm, t in zip(("depth", "color", "term", "pixel_unc", "depth_unc"), ret):
+        assert str(t.dtype) == str(g["dtype_" + nm]), nm                          # float64 except colour (Renderer.py:205-209)
+        assert tuple(t.shape) == g["ret_" + nm].shape
+        assert max_rel(t, g["ret_" + nm], 1e-4) < 1e-5, nm

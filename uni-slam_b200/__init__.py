@@ -9,6 +9,7 @@ Public surface (mirrors the reference's operator API for the path, SURVEY.md sec
   Decoders, Renderer        src/networks/decoders.py, src/utils/Renderer.py drop-ins (B3, B4)
   MappingStep, TrackingStep fused per-iteration drivers            (B5, B6 + a-3 .. a-10)
   DenseSdfQuery             dense SDF query for meshing            (a-11)
+  RenderImageStep           forward-only whole-frame renderer      (f3, Renderer.render_img)
   FusedAdam                 one-launch torch.optim.Adam equivalent (a-12 / f1)
   ops                       thin per-kernel wrappers over the C-ABI
 There is no CPU path: every op raises RuntimeError if lib/libunislam_b200.so is missing.
@@ -16,6 +17,6 @@ There is no CPU path: every op raises RuntimeError if lib/libunislam_b200.so is 
 from . import _lib, ops, synthetic  # noqa: F401
 from .modules import Decoders, Encoding, Network, Renderer  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
-from .steps import DenseSdfQuery, MappingStep, TrackingStep  # noqa: F401
+from .steps import DenseSdfQuery, MappingStep, RenderImageStep, TrackingStep  # noqa: F401
 
-__all__ = ["Encoding", "Network", "Decoders", "Renderer", "MappingStep", "TrackingStep", "DenseSdfQuery", "FusedAdam", "ops", "synthetic"]
+__all__ = ["Encoding", "Network", "Decoders", "Renderer", "MappingStep", "TrackingStep", "DenseSdfQuery", "RenderImageStep", "FusedAdam", "ops", "synthetic"]

@@ -64,7 +64,7 @@ class RaySetup(Structure):
                 ("bound", Bound), ("require_depth", c_int32), ("_pad2", c_int32),
                 ("zs", ZSampleArgs), ("t_rand", c_void_p), ("n_rays", c_int64),
                 ("rays_o", c_void_p), ("rays_d", c_void_p), ("gt_depth", c_void_p), ("gt_color", c_void_p), ("dirs_out", c_void_p),
-                ("frame_id", c_void_p), ("valid", c_void_p), ("z", c_void_p)]
+                ("frame_id", c_void_p), ("valid", c_void_p), ("z", c_void_p), ("pixel_begin", c_int64)]
 
 
 class LossArgs(Structure):

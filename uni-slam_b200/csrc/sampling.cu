@@ -199,12 +199,19 @@ __global__ void ray_setup_kernel(const __grid_constant__ usl_ray_setup_t A) {
                     for (int q = 0; q < 12; ++q) c2w[q] = B.c2ws[(int64_t)kf * 16 + q];
                 }
             } else {
-                const int64_t idx = A.win_indices[r];
-                const int Wc = A.W1 - A.W0;
-                const int pi = (int)(idx % Wc) + A.W0, pj = (int)(idx / Wc) + A.H0;
+                int pi, pj;
+                if (A.mode == 2) {                                   // whole frame, row-major (get_rays, common.py:210-228)
+                    const int64_t pix = A.pixel_begin + r;
+                    pi = (int)(pix % A.W); pj = (int)(pix / A.W);
+                } else {
+                    const int64_t idx = A.win_indices[r];
+                    const int Wc = A.W1 - A.W0;
+                    pi = (int)(idx % Wc) + A.W0; pj = (int)(idx / Wc) + A.H0;
+                }
                 pixel_dir((float)pi, (float)pj, A.fx, A.fy, A.cx, A.cy, d);
                 const int64_t src = (int64_t)pj * A.W + pi;
-                col[0] = A.color_img[src * 3]; col[1] = A.color_img[src * 3 + 1]; col[2] = A.color_img[src * 3 + 2];
+                if (A.color_img) { col[0] = A.color_img[src * 3]; col[1] = A.color_img[src * 3 + 1]; col[2] = A.color_img[src * 3 + 2]; }
+                else col[0] = col[1] = col[2] = 0.f;
                 gt = A.depth_img[src];
                 if (A.cam_poses) pose_to_c2w(A.cam_poses, c2w);
                 else {
@@ -218,11 +225,12 @@ __global__ void ray_setup_kernel(const __grid_constant__ usl_ray_setup_t A) {
                 rd[a] = __fadd_rn(__fadd_rn(__fmul_rn(d[0], c2w[a * 4]), __fmul_rn(d[1], c2w[a * 4 + 1])), __fmul_rn(d[2], c2w[a * 4 + 2]));
                 o[a] = c2w[a * 4 + 3];
                 A.rays_d[r * 3 + a] = rd[a]; A.rays_o[r * 3 + a] = o[a];
-                A.gt_color[r * 3 + a] = col[a]; A.dirs_out[r * 3 + a] = d[a];
+                if (A.gt_color) A.gt_color[r * 3 + a] = col[a];
+                if (A.dirs_out) A.dirs_out[r * 3 + a] = d[a];
             }
             A.gt_depth[r] = gt;
             if (A.frame_id) A.frame_id[r] = frame;
-            bool v = bbox_exit(o, rd, A.bound) >= gt;
+            bool v = (A.mode == 2) || bbox_exit(o, rd, A.bound) >= gt;
             if (A.require_depth) v = v && (gt > 0.f);
             A.valid[r] = v ? 1 : 0;
             live = (v && gt > 0.f) ? 1 : 0;
@@ -432,6 +440,8 @@ int usl_ray_setup(const usl_ray_setup_t *a, usl_stream_t stream) {
     if (S < 2 || S > 128) { set_error("usl_ray_setup: n_stratified + n_importance must be in 2..128"); return 1; }
     if (a->mode == 0 && (a->n_batches < 1 || a->n_batches > 2)) { set_error("usl_ray_setup: 1 or 2 keyframe batches"); return 1; }
     if (a->mode == 1 && (a->H0 < 0 || a->H1 > a->H || a->W0 < 0 || a->W1 > a->W || a->H1 <= a->H0 || a->W1 <= a->W0)) { set_error("usl_ray_setup: bad window"); return 1; }
+    if (a->mode == 2 && (a->pixel_begin < 0 || a->pixel_begin + a->n_rays > (int64_t)a->H * a->W || !a->depth_img)) { set_error("usl_ray_setup: pixel range outside the frame"); return 1; }
+    if (a->mode != 2 && (!a->gt_color || !a->dirs_out)) { set_error("usl_ray_setup: gt_color / dirs_out are required in modes 0 and 1"); return 1; }
     ray_setup_kernel<<<(unsigned)((a->n_rays + ZS_RAYS_PER_BLOCK - 1) / ZS_RAYS_PER_BLOCK), ZS_RAYS_PER_BLOCK * S,
                        ZS_RAYS_PER_BLOCK * S * sizeof(float), (cudaStream_t)stream>>>(*a);
     return check_launch("usl_ray_setup");

@@ -286,6 +286,77 @@ class TrackingStep(_Profiled):
         return self.loss
 
 
+class RenderImageStep(_Profiled):
+    """Forward-only rendering of whole frames (Renderer.render_img, src/utils/Renderer.py:160-223; used for the
+    visualisations and the end-of-run eval_rendering): get_rays -> depth-guided / no-depth z-sampling -> field query
+    (no activation stash, no Jacobian) -> compositing, in chunks of ``chunk_rays`` consecutive pixels on preallocated
+    buffers.  A pixel range [pixel_begin, pixel_end) can be rendered instead of the whole frame: that is the unit the
+    multi-GPU path shards (rows of the image, no collective on the data path).
+
+    RNG contract as for the other fused steps: draws are indexed by ray slot of the rendered range
+    (t_rand (n,S), t_rand_uni (n,n_stratified), u_pdf (n,n_importance)); the drop-in modules.Renderer.render_img keeps
+    the reference's per-chunk compacted draw order instead."""
+
+    def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec, beta, *, n_stratified, n_importance, truncation,
+                 H, W, fx, fy, cx, cy, chunk_rays: int = 131072, perturb: bool = True):
+        dev = sdf_table.device
+        self.fs = _FieldState(meta, sdf_table, rgb_table, dec, beta, with_grads=False)
+        self.zs = ops.ZSampler(n_stratified, n_importance, truncation, dev)
+        self.S = self.zs.S
+        self.perturb = perturb
+        self.cam = (int(H), int(W), float(fx), float(fy), float(cx), float(cy))
+        C = self.chunk = int(min(chunk_rays, H * W))
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.rays_o = torch.empty((C, 3), **f32); self.rays_d = torch.empty((C, 3), **f32)
+        self.gt_depth = torch.empty((C,), **f32); self.valid = torch.empty((C,), device=dev, dtype=torch.uint8)
+        self.z = torch.zeros((C, self.S), **f32); self.raw = torch.empty((C, self.S, 4), **f32)
+        self._init_prof()
+
+    def alloc_outputs(self, n):
+        dev = self.z.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        return dict(depth=torch.empty((n,), **f32), color=torch.empty((n, 3), **f32), term=torch.empty((n,), **f32),
+                    pixel_unc=torch.empty((n,), **f32), depth_unc=torch.empty((n,), **f32))
+
+    def run(self, c2w, depth_img, t_rand, t_rand_uni=None, u_pdf=None, pixel_begin: int = 0, pixel_end: Optional[int] = None,
+            out: Optional[dict] = None, has_holes: bool = True):
+        """c2w (4,4); depth_img (H,W) sensor depth (0 = hole). Returns dict of fp32 tensors over the pixel range:
+        depth, color (n,3), term, pixel_unc, depth_unc (the reference converts all but colour to float64 on return)."""
+        st = stream()
+        fs, S = self.fs, self.S
+        H, W, fx, fy, cx, cy = self.cam
+        pixel_end = H * W if pixel_end is None else pixel_end
+        n_total = pixel_end - pixel_begin
+        out = out if out is not None else self.alloc_outputs(n_total)
+        c2w = L.f32c(c2w); depth_img = L.f32c(depth_img)
+        for c0 in range(0, n_total, self.chunk):
+            n = min(self.chunk, n_total - c0)
+            sl = lambda t: ptr(t[c0:c0 + n]) if t is not None else None
+            rs = L.RaySetup()
+            rs.mode, rs.n_batches = 2, 0
+            rs.depth_img, rs.color_img, rs.win_indices = ptr(depth_img), None, None
+            rs.H, rs.W = H, W
+            rs.fx, rs.fy, rs.cx, rs.cy = fx, fy, cx, cy
+            rs.c2w = ptr(c2w)
+            rs.bound, rs.require_depth, rs.zs = fs.meta.bound, 0, self.zs.args
+            rs.t_rand = sl(t_rand) if self.perturb else None
+            rs.n_rays, rs.pixel_begin = n, pixel_begin + c0
+            rs.rays_o, rs.rays_d, rs.gt_depth = ptr(self.rays_o), ptr(self.rays_d), ptr(self.gt_depth)
+            rs.gt_color, rs.dirs_out, rs.frame_id = None, None, None
+            rs.valid, rs.z = ptr(self.valid), ptr(self.z)
+            self._call("usl_ray_setup", byref(rs), st)
+            if has_holes:
+                self._call("usl_zsample_nodepth", byref(self.zs.args), byref(fs.field), ptr(fs.beta), ptr(self.rays_o), ptr(self.rays_d),
+                           ptr(self.gt_depth), None, sl(t_rand_uni) if self.perturb else None, sl(u_pdf), None, n, ptr(self.z), None, st)
+            pts = L.Points()
+            pts.x = None; pts.rays_o, pts.rays_d, pts.z, pts.valid = ptr(self.rays_o), ptr(self.rays_d), ptr(self.z), None
+            pts.S, pts.n = S, n * S
+            self._call("usl_field_fwd", byref(fs.field), byref(pts), ptr(self.raw), None, None, st)
+            self._call("usl_composite_fwd", ptr(self.raw), ptr(self.z), ptr(fs.beta), None, n, S, sl(out["term"]), sl(out["pixel_unc"]),
+                       sl(out["depth"]), sl(out["color"]), sl(out["depth_unc"]), None, st)
+        return out
+
+
 class DenseSdfQuery:
     """Mesher.get_grid_uniform + eval_points (SDF channel) over a y-slab of the 1 cm query grid
     (src/utils/Mesher.py:134-195,219-227); points are generated in-kernel from the per-axis coordinates."""
