@@ -31,6 +31,9 @@ CASES = {
     "map_scannet_k23": dict(yaml="configs/ScanNet/scene0000.yaml", H=46, W=62, s=0.1, n_kf=22, pixels=230, lr_factor=1),
     "track_replica": dict(yaml="configs/Replica/room0.yaml", H=60, W=80, s=1 / 15.0, pixels=200, edge=6),
     "track_scannet": dict(yaml="configs/ScanNet/scene0000.yaml", H=46, W=62, s=0.1, pixels=200, edge=5),
+    # keyframe bookkeeping: full (tiny) frames + every randperm draw, so the device-resident KeyframeStore can be checked
+    # against the tensors optimize_mapping stacks from its list of dicts (Mapper.py:315-351)
+    "map_replica_kfstore": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, n_kf=3, pixels=120, lr_factor=1, save_frames=True),
     # Renderer.render_img (Renderer.py:160-223): whole frame in ray_batch_size chunks, last chunk ragged
     "img_replica": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, ray_batch=500),
     "img_scannet": dict(yaml="configs/ScanNet/scene0000.yaml", H=23, W=31, s=0.05, ray_batch=300),
@@ -217,10 +220,12 @@ def gen_mapping(name, case):
     torch.manual_seed(11)
     m.keyframe_dict, m.keyframe_list = [], []
     est = torch.zeros(4 * (n_kf + 1) + 1, 4, 4)
+    kf_inds = []
     for k in range(n_kf):
         col, dep, c2w = frames[k]
         idx = 4 * k
         ind = torch.randperm(H * W)[: int(H * W * 0.1)]
+        kf_inds.append(ind)
         noisy = c2w.clone(); noisy[:3, 3] += 0.01 * torch.randn(3)
         est[idx] = noisy
         m.keyframe_list.append(idx)
@@ -275,6 +280,14 @@ def gen_mapping(name, case):
     for nm, o in zip(("term", "pixel_unc", "depth", "rgb", "sdf", "z_vals", "depth_unc"), r["out"]):
         out["ret_" + nm] = _np(o)
     out["loss"] = _np(rec.losses[-1])
+    if case.get("save_frames"):
+        out["frames_color"] = np.stack([_np(f[0]) for f in frames]); out["frames_depth"] = np.stack([_np(f[1]) for f in frames])
+        out["frames_gt_c2w"] = np.stack([_np(f[2]) for f in frames]); out["dirs_cam"] = _np(rays_d_cam)
+        out["kf_indices"] = np.stack([_np(i) for i in kf_inds]); out["kf_frame_idx"] = np.array(m.keyframe_list)
+        out["kf_est_c2w"] = np.stack([_np(d["est_c2w"]) for d in m.keyframe_dict]); out["cur_c2w"] = _np(cur_c2w)
+        perms = [t for k, t in rec.draws if k == "randperm"]
+        assert len(perms) == 1                                    # the current frame's subset (Mapper.py:332)
+        out["cur_randperm"] = _np(perms[0])
     grads = rec.steps[-1]; pvals = rec.params_at_step
     dec_names = [n for n, _ in dec.named_parameters()]
     for n_, g in zip(dec_names, grads[0]):

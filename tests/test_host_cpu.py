@@ -106,3 +106,44 @@ print("ok")
     import subprocess
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_keyframe_store_matches_reference_bookkeeping():
+    """f2: the device-resident KeyframeStore must hand MappingStep the very tensors the unmodified reference's
+    optimize_mapping stacks from its keyframe_dict + the current frame's randperm subset (Mapper.py:315-351;
+    fixture recorded from the reference by oracle/gen_golden.py), as views, and sampling from them must reproduce
+    get_samples_all bit for bit."""
+    from oracle import path_ref
+    from helpers import load_golden
+    KeyframeStore = importlib.import_module("uni-slam_b200.keyframes").KeyframeStore
+    g = load_golden("map_replica_kfstore")
+    T = torch.from_numpy
+    H, W = int(g["meta_H_W_fx_fy_cx_cy"][0]), int(g["meta_H_W_fx_fy_cx_cy"][1])
+    col, dep, gtc = T(g["frames_color"]), T(g["frames_depth"]), T(g["frames_gt_c2w"])
+    dirs = T(g["dirs_cam"])
+    n_kf = g["kf_indices"].shape[0]
+    store = KeyframeStore(capacity=8, H=H, W=W, device="cpu")
+    assert store.P == g["kf_indices"].shape[1] == int(H * W * 0.1)
+    for k in range(n_kf):
+        store.append(int(g["kf_frame_idx"][k]), col[k], dep[k], dirs, T(g["kf_est_c2w"][k]), gtc[k], indices=T(g["kf_indices"][k]))
+    store.stage_current(col[n_kf], dep[n_kf], dirs, T(g["cur_c2w"]), gtc[n_kf], indices=T(g["cur_randperm"])[:store.P])
+    c2ws, depths, colors, rays_d = store.window()
+    for got, key in ((c2ws, "call0_c2ws"), (depths, "call0_depths"), (colors, "call0_colors"), (rays_d, "call0_rays_d_cam")):
+        assert torch.equal(got, T(g[key])), key
+        assert got.untyped_storage().data_ptr() in {t.untyped_storage().data_ptr() for t in (store.est_c2w, store.depth, store.color, store.rays_d)}   # a view, not a copy
+    (cw, dp, cl, rd, idx, n, base), = store.mapping_batches(T(g["call0_indices"]), int(g["call0_n"]))
+    out = path_ref.sample_mapping_rays(cw, dp, cl, rd, idx)
+    for nm, t in zip(("rays_o", "rays_d", "depth", "color"), out):
+        assert torch.equal(t, T(g["call0_out_" + nm])), nm
+    # wire format + non-contiguous selection (loop-closure style) + pose write-back
+    d = store.as_dicts()
+    assert [x["idx"] for x in d] == list(g["kf_frame_idx"]) and set(d[0]) == {"gt_c2w", "idx", "color", "depth", "est_c2w", "rays_d"}
+    sel = store.window([0, 2])
+    assert torch.equal(sel[1], torch.stack([store.depth[0], store.depth[2], store.depth[n_kf]]))
+    new = torch.randn(n_kf, 4, 4)
+    cur = store.write_back_poses(new)
+    assert torch.equal(store.est_c2w[1], new[0]) and torch.equal(store.est_c2w[2], new[1]) and torch.equal(cur, new[-1])
+    assert torch.equal(store.est_c2w[0], T(g["kf_est_c2w"][0]))                    # the oldest frame stays fixed
+    with pytest.raises(RuntimeError):
+        for k in range(20):
+            store.promote_staged(100 + k)

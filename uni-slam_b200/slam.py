@@ -19,6 +19,7 @@ import torch
 
 from . import synthetic as syn
 from . import workload as wlmod
+from .keyframes import KeyframeStore
 from .optim import FusedAdam
 from .steps import MappingStep, TrackingStep
 
@@ -65,11 +66,7 @@ def run_slam(cfg: syn.SceneCfg = syn.REPLICA_ROOM0, n_frames: int = 40, device="
     grads = [mstep.fs.g_sdf_table, mstep.fs.g_rgb_table, mstep.fs.g_beta] + mstep.fs.g_dec
     for p_, g_ in zip(params, grads):
         p_.requires_grad_(True); p_.grad = g_
-    dirs_full = seq.dirs.reshape(-1, 3)
-    # keyframe store (Mapper.py:528-541): 10 % pixel subsets, device resident
-    kf_depth = torch.zeros((max_kf, P), device=device); kf_color = torch.zeros((max_kf, P, 3), device=device)
-    kf_dirs = torch.zeros((max_kf, P, 3), device=device); kf_c2w = torch.zeros((max_kf, 4, 4), device=device)
-    n_kf = 0
+    store = KeyframeStore(max_kf, H, W, device)         # Mapper.py:528-541: 10 % pixel subsets, device resident
     est = torch.zeros((n_frames, 4, 4), device=device); gt = torch.zeros((n_frames, 4, 4), device=device)
     prior = torch.zeros((n_frames, 4, 4), device=device)
     n_track = n_map = map_samples = 0
@@ -109,10 +106,10 @@ def run_slam(cfg: syn.SceneCfg = syn.REPLICA_ROOM0, n_frames: int = 40, device="
             est[k] = _pose_to_c2w(best_pose)
         # ---------------- mapping (Mapper.py:485-541) ----------------
         if k % cfg.map_every == 0:
-            ind = torch.randperm(H * W, device=device)[:P]
+            n_kf = len(store)
             K = n_kf + 1
-            kf_depth[n_kf] = dep.reshape(-1)[ind]; kf_color[n_kf] = col.reshape(-1, 3)[ind]; kf_dirs[n_kf] = dirs_full[ind]
-            kf_c2w[n_kf] = est[k]
+            store.stage_current(col, dep, seq.dirs, est[k], c2w_gt, indices=torch.randperm(H * W, device=device)[:P])
+            kf_c2w = store.est_c2w
             joint = n_kf > 4                                                  # Mapper.py:519
             first = k == 0
             lr_f = 5.0 if first else 1.0                                       # lr_first_factor / lr_factor
@@ -130,10 +127,8 @@ def run_slam(cfg: syn.SceneCfg = syn.REPLICA_ROOM0, n_frames: int = 40, device="
             iters = map_iters_first if first else map_iters
             for it in range(iters):
                 idx_main = torch.randint(P, (K * n_main,), device=device)
-                batches = [(kf_c2w[:K], kf_depth[:K], kf_color[:K], kf_dirs[:K], idx_main, n_main, 0)]
-                if n_rec:
-                    idx_rec = torch.randint(P, (10 * n_rec,), device=device)
-                    batches.append((kf_c2w[K - 10:K], kf_depth[K - 10:K], kf_color[K - 10:K], kf_dirs[K - 10:K], idx_rec, n_rec, K - 10))
+                idx_rec = torch.randint(P, (10 * n_rec,), device=device) if n_rec else None
+                batches = store.mapping_batches(idx_main, n_main, idx_rec, n_rec)   # views into the store, no stacking
                 loss = mstep.run(batches, torch.rand((R, S), device=device), torch.rand((R, cfg.n_stratified), device=device),
                                  torch.rand((R, cfg.n_importance), device=device),
                                  cam_poses=cam_poses.detach() if joint else None, c2w_fixed=kf_c2w[0] if joint else None)
@@ -143,9 +138,8 @@ def run_slam(cfg: syn.SceneCfg = syn.REPLICA_ROOM0, n_frames: int = 40, device="
                     loss_first = float(loss)
             loss_last = float(loss)
             if joint:                                                          # Mapper.py:447-457
-                kf_c2w[1:K] = _pose_to_c2w(cam_poses.detach())
-                est[k] = kf_c2w[K - 1]
-            n_kf += 1                                                          # keyframe_every == map_every in every config
+                est[k] = store.write_back_poses(_pose_to_c2w(cam_poses.detach()))
+            store.promote_staged(k)                                            # keyframe_every == map_every in every config
             if verbose:
                 print(f"frame {k}: mapped K={K} loss={loss_last:.4f}")
     torch.cuda.synchronize()
