@@ -247,7 +247,8 @@ typedef struct usl_loss_args {
     float truncation;
     float truncation_center; /* (float)(0.4*truncation), product taken in double by the caller (Mapper.py:160-161) */
     float w_sdf_fs, w_sdf_center, w_sdf_tail, w_depth, w_color;
-    int32_t mode;      /* 0 mapping ('original'), 1 tracking ('original': 10x-median mask, masked colour) */
+    int32_t mode;      /* 0 mapping ('original'), 1 tracking ('original': 10x-median mask, masked colour),
+                        * 2 'no_mask' of either (every term over every valid ray; Mapper.py:432-440, Tracker.py:230-238) */
 } usl_loss_args_t;
 #define USL_LOSS_SLOTS 16
 /* acc[USL_LOSS_SLOTS] (zeroed by caller; ADDED): 0 fs_sum 1 center_sum 2 tail_sum 3 depth_sum 4 color_sum

@@ -31,6 +31,9 @@ CASES = {
     "map_scannet_k23": dict(yaml="configs/ScanNet/scene0000.yaml", H=46, W=62, s=0.1, n_kf=22, pixels=230, lr_factor=1),
     "track_replica": dict(yaml="configs/Replica/room0.yaml", H=60, W=80, s=1 / 15.0, pixels=200, edge=6),
     "track_scannet": dict(yaml="configs/ScanNet/scene0000.yaml", H=46, W=62, s=0.1, pixels=200, edge=5),
+    # m_mask_mode / t_mask_mode "no_mask" (Mapper.py:432-440, Tracker.py:230-238)
+    "map_replica_nomask": dict(yaml="configs/Replica/room0.yaml", H=60, W=80, s=1 / 15.0, n_kf=0, pixels=160, lr_factor=5, mask_mode="no_mask"),
+    "track_scannet_nomask": dict(yaml="configs/ScanNet/scene0000.yaml", H=46, W=62, s=0.1, pixels=120, edge=5, mask_mode="no_mask"),
     # keyframe bookkeeping: full (tiny) frames + every randperm draw, so the device-resident KeyframeStore can be checked
     # against the tensors optimize_mapping stacks from its list of dicts (Mapper.py:315-351)
     "map_replica_kfstore": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, n_kf=3, pixels=120, lr_factor=1, save_frames=True),
@@ -192,6 +195,7 @@ def gen_mapping(name, case):
     from src.utils.Renderer import Renderer
     from src.common import get_camera_rays
     cfg = _load_cfg(case)
+    cfg["m_mask_mode"] = case.get("mask_mode", cfg["m_mask_mode"])
     cfg["mapping"]["pixels"] = case["pixels"]
     bound, grids, dec = _build_world(cfg, 0)
     H, W = case["H"], case["W"]
@@ -257,7 +261,7 @@ def gen_mapping(name, case):
     out["log2_hash"] = np.array([cfg["grid"]["hash_size_sdf"], cfg["grid"]["hash_size_color"]])
     out["per_level_scale"] = np.array([grids[0].spec.per_level_scale, grids[1].spec.per_level_scale])
     out["variant"] = np.array("B" if cfg["grid"]["tcnn_network"] else "A")
-    out["joint_opt"] = np.array(int(m.joint_opt))
+    out["joint_opt"] = np.array(int(m.joint_opt)); out["mask_mode"] = np.array(m.m_mask_mode)
     # sampling calls (first = main batch; optional second = the 200px x last-10-frames batch)
     calls = [s for s in rec.samples if s["kind"] == "all"]
     out["n_sample_calls"] = np.array(len(calls))
@@ -306,6 +310,7 @@ def gen_tracking(name, case):
     from src.utils.Renderer import Renderer
     from src.common import matrix_to_cam_pose
     cfg = _load_cfg(case)
+    cfg["t_mask_mode"] = case.get("mask_mode", cfg["t_mask_mode"])
     bound, grids, dec = _build_world(cfg, 50)
     H, W = case["H"], case["W"]
     cam = cfg["cam"]
@@ -352,7 +357,7 @@ def gen_tracking(name, case):
     out["log2_hash"] = np.array([cfg["grid"]["hash_size_sdf"], cfg["grid"]["hash_size_color"]])
     out["per_level_scale"] = np.array([grids[0].spec.per_level_scale, grids[1].spec.per_level_scale])
     out["variant"] = np.array("B" if cfg["grid"]["tcnn_network"] else "A")
-    out["color_img"] = _np(col); out["depth_img"] = _np(dep); out["cam_pose"] = _np(cam_pose0)
+    out["color_img"] = _np(col); out["depth_img"] = _np(dep); out["cam_pose"] = _np(cam_pose0); out["mask_mode"] = np.array(t.t_mask_mode)
     out["indices"] = _np([t_ for k, t_ in rec.draws if k == "randint"][-1])
     out["t_rand"] = _np([t_ for k, t_ in rec.draws if k == "rand"][-1])
     s = rec.samples[-1]

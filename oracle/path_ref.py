@@ -409,8 +409,23 @@ def sdf_losses(sdf, z_vals, gt_depth, truncation, lw: LossWeights, parts: Option
     return lw.w_sdf_fs * fs + lw.w_sdf_center * ce + lw.w_sdf_tail * ta
 
 
-def mapping_loss(ret, gt_depth, gt_color, truncation, lw: LossWeights = MAP_WEIGHTS, parts=None):
-    """Mapper.py:412-430 ('original' mask mode)."""
+def _no_mask_loss(ret, gt_depth, gt_color, truncation, lw, parts):
+    """m_mask_mode / t_mask_mode == "no_mask" (Mapper.py:432-440, Tracker.py:230-238): every term over every ray.
+    (The tracker writes (w*x).mean() where the mapper writes w*x.mean(): the same number.)"""
+    term, pixel_unc, depth, color, sdf, z_vals, _ = ret
+    gtd = gt_depth.to(depth.dtype)
+    loss = sdf_losses(sdf, z_vals, gtd, truncation, lw, parts)
+    col = torch.square(gt_color.to(color.dtype) - color).mean()
+    dep = torch.square(gtd - depth).mean()
+    if parts is not None:
+        parts.update(color=col, depth=dep, n_mask=int(gtd.numel()), depth_mask=torch.ones_like(gtd, dtype=torch.bool))
+    return loss + lw.w_color * col + lw.w_depth * dep
+
+
+def mapping_loss(ret, gt_depth, gt_color, truncation, lw: LossWeights = MAP_WEIGHTS, parts=None, mask_mode="original"):
+    """Mapper.py:412-440."""
+    if mask_mode == "no_mask":
+        return _no_mask_loss(ret, gt_depth, gt_color, truncation, lw, parts)
     term, pixel_unc, depth, color, sdf, z_vals, _ = ret
     alpha_mask = (1 - pixel_unc.detach()).to(torch.float32) > 0.99
     depth_mask = (gt_depth > 0) & alpha_mask
@@ -423,8 +438,10 @@ def mapping_loss(ret, gt_depth, gt_color, truncation, lw: LossWeights = MAP_WEIG
     return loss + lw.w_color * col + lw.w_depth * dep
 
 
-def tracking_loss(ret, gt_depth, gt_color, truncation, lw: LossWeights = TRACK_WEIGHTS, parts=None):
-    """Tracker.py:208-228 ('original' mask mode): 10x-median depth-error mask, colour over masked rays."""
+def tracking_loss(ret, gt_depth, gt_color, truncation, lw: LossWeights = TRACK_WEIGHTS, parts=None, mask_mode="original"):
+    """Tracker.py:208-238. 'original': 10x-median depth-error mask, colour over masked rays."""
+    if mask_mode == "no_mask":
+        return _no_mask_loss(ret, gt_depth, gt_color, truncation, lw, parts)
     term, pixel_unc, depth, color, sdf, z_vals, _ = ret
     alpha_mask = (1 - pixel_unc.detach()).to(torch.float32) > 0.99
     gtd = gt_depth.to(depth.dtype)
@@ -444,7 +461,7 @@ def tracking_loss(ret, gt_depth, gt_color, truncation, lw: LossWeights = TRACK_W
 # whole iterations (sample -> prefilter -> render -> loss), RNG passed in
 # ----------------------------------------------------------------------------------------------
 def mapping_iteration(field: Field, batches, truncation, n_stratified, n_importance, draw_rand,
-                      lw: LossWeights = MAP_WEIGHTS, parts=None):
+                      lw: LossWeights = MAP_WEIGHTS, parts=None, mask_mode="original"):
     """Mapper.optimize_mapping body, Mapper.py:379-430. batches = [(c2ws, depths, colors, rays_d_cam,
     indices), ...]: the main get_samples_all call (:379) and, when >20 keyframes, the 200 px x last-10
     frames call (:385-393), concatenated in that order. draw_rand(shape) supplies the torch.rand
@@ -463,13 +480,13 @@ def mapping_iteration(field: Field, batches, truncation, n_stratified, n_importa
                            t_rand, t_uni, u_pdf)
     if parts is not None:
         parts.update(inside=inside, ret=ret, gt_depth=gt_depth, gt_color=gt_color, rays_o=rays_o, rays_d=rays_d)
-    return mapping_loss(ret, gt_depth, gt_color, truncation, lw, parts)
+    return mapping_loss(ret, gt_depth, gt_color, truncation, lw, parts, mask_mode)
 
 
 def tracking_iteration(field: Field, cam_pose, depth_img, color_img, H, W, fx, fy, cx, cy, edge_h, edge_w,
                        indices, truncation, n_stratified, n_importance, draw_rand,
-                       lw: LossWeights = TRACK_WEIGHTS, parts=None):
-    """Tracker.optimize_tracking, Tracker.py:170-228. cam_pose (1,7) requires grad."""
+                       lw: LossWeights = TRACK_WEIGHTS, parts=None, mask_mode="original"):
+    """Tracker.optimize_tracking, Tracker.py:170-238. cam_pose (1,7) requires grad."""
     c2w = cam_pose_to_matrix(cam_pose)
     rays_o, rays_d, gt_all, gt_color = sample_tracking_rays(edge_h, H - edge_h, edge_w, W - edge_w, indices.numel(),
                                                             fx, fy, cx, cy, c2w, depth_img, color_img, indices)
@@ -481,7 +498,7 @@ def tracking_iteration(field: Field, cam_pose, depth_img, color_img, H, W, fx, f
     ret = render_batch_ray(field, rays_d, rays_o, gt_depth, n_stratified, n_importance, truncation, t_rand)
     if parts is not None:
         parts.update(inside=inside, ret=ret, gt_depth=gt_depth, gt_color=gt_color, rays_o=rays_o, rays_d=rays_d)
-    return tracking_loss(ret, gt_depth, gt_color, truncation, lw, parts), ret[1]
+    return tracking_loss(ret, gt_depth, gt_color, truncation, lw, parts, mask_mode), ret[1]
 
 
 # ----------------------------------------------------------------------------------------------

@@ -59,7 +59,7 @@ def run_mapping_case(name, device="cuda:0"):
     inside = path_ref.bbox_exit(ro_all, rd_all, T(g["bound"])) >= depth_all
     t_rand, t_uni, u_pdf, has_holes = _slot_draws(g, inside, depth_all, S, ns, ni, device)
     step = P.MappingStep(meta, tabs[0], tabs[1], dec, beta, n_stratified=ns, n_importance=ni, truncation=tr,
-                         max_rays=R, max_frames=K)
+                         max_rays=R, max_frames=K, mask_mode=str(g["mask_mode"]) if "mask_mode" in g else "original")
     cam_poses = T(g["cam_poses"]).to(device).contiguous() if joint else None
     loss = step.run(batches, t_rand, t_uni, u_pdf, cam_poses=cam_poses,
                     c2w_fixed=T(g["call0_c2ws"][0]).to(device) if joint else None, has_holes=has_holes)
@@ -117,7 +117,8 @@ def run_tracking_case(name, device="cuda:0"):
     inside = (path_ref.bbox_exit(T(g["sample_out_rays_o"]), T(g["sample_out_rays_d"]), T(g["bound"])) >= gt_all) & (gt_all > 0)
     t_rand = torch.zeros((R, S)); t_rand[inside] = T(g["t_rand"])
     step = P.TrackingStep(meta, tabs[0], tabs[1], dec, beta, n_stratified=ns, n_importance=ni, truncation=float(g["truncation"]),
-                          H=H, W=W, fx=fx, fy=fy, cx=cx, cy=cy, ignore_edge_h=e, ignore_edge_w=e, n_rays=R)
+                          H=H, W=W, fx=fx, fy=fy, cx=cx, cy=cy, ignore_edge_h=e, ignore_edge_w=e, n_rays=R,
+                          mask_mode=str(g["mask_mode"]) if "mask_mode" in g else "original")
     cam_pose = T(g["cam_pose"]).to(device).contiguous()
     loss = step.run(cam_pose, T(g["depth_img"]).to(device).contiguous(), T(g["color_img"]).to(device).contiguous(),
                     idx.to(device), t_rand.to(device))

@@ -151,7 +151,7 @@ def test_network_matches_torch(variant):
             assert rel_err(hp.grad.cpu(), hr.grad) < 1e-4
 
 
-@pytest.mark.parametrize("name", ["map_replica_k1", "map_replica_k7", "map_scannet_k23"])
+@pytest.mark.parametrize("name", ["map_replica_k1", "map_replica_k7", "map_scannet_k23", "map_replica_nomask", "map_replica_kfstore"])
 def test_mapping_step_matches_reference(name):
     r = gpu_cases.run_mapping_case(name, DEV)
     print(name, r)
@@ -166,7 +166,7 @@ def test_mapping_step_matches_reference(name):
         assert r[pre + "_support_miss"] == 0 and r[pre + "_nnz_excess"] == 0, pre
 
 
-@pytest.mark.parametrize("name", ["track_replica", "track_scannet"])
+@pytest.mark.parametrize("name", ["track_replica", "track_scannet", "track_scannet_nomask"])
 def test_tracking_step_matches_reference(name):
     r = gpu_cases.run_tracking_case(name, DEV)
     print(name, r)
@@ -401,3 +401,60 @@ def test_slam_loop_runs_and_stays_on_track():
     r = slam.run_slam(pkg().synthetic.REPLICA_ROOM0, n_frames=24, scale_hw=0.25)
     assert r.loss_last_map < 0.05 * r.loss_first_map
     assert r.ate_rmse < 0.03 and r.tracking_iters == 23 * 8 and r.mapping_iters == 10 + 5 * 15
+
+
+def test_empty_and_degenerate_inputs():
+    """Edge cases of the seams: zero points / rays (tcnn pads an empty batch to nothing), an all-holes ray batch
+    (n_valid == 0: the reference draws torch.rand((0,S)) and takes the no-depth branch for every ray), a batch in which
+    no ray survives the mask (torch.mean over an empty selection: the loss is NaN in the reference),
+    and argument errors raised as RuntimeError."""
+    P = pkg()
+    g = load_golden("map_replica_k7")
+    meta, tabs, dec, beta = gpu_cases.cuda_field(g, 0, DEV)
+    ns, ni, tr = int(g["n_stratified"]), int(g["n_importance"]), float(g["truncation"])
+    S = ns + ni
+    # -- zero-sized batches through every differentiable seam
+    enc = P.Encoding(3, {"otype": "HashGrid", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 16, "base_resolution": 16,
+                         "per_level_scale": float(g["per_level_scale"][0])}, dtype=torch.float).to(DEV)
+    x0 = torch.empty((0, 3), device=DEV, requires_grad=True)
+    y0 = enc(x0)
+    assert y0.shape == (0, 32)
+    y0.sum().backward()
+    assert enc.params.grad is not None and float(enc.params.grad.abs().sum()) == 0.0 and x0.grad.shape == (0, 3)
+    assert P.ops.field_sdf_points(meta, torch.empty((0, 3), device=DEV), tabs[0], tabs[1], dec).shape == (0,)
+    e3 = torch.empty((0, 3), device=DEV)
+    ret = P.ops.render_rays(meta, e3, e3, torch.empty((0, S), device=DEV), beta, tabs[0], tabs[1], dec)
+    assert ret[0].shape == (0,) and ret[3].shape == (0, 3) and ret[4].shape == (0, S)
+    # -- all-holes batch through the fused renderer vs the oracle (no-depth branch for every ray)
+    R = 37
+    gen = torch.Generator().manual_seed(4)
+    c2w = T(g["call0_c2ws"][1])
+    dirs = T(g["call0_rays_d_cam"][1][:R])
+    rays_d = torch.sum(dirs[:, None, :] * c2w[:3, :3], -1); rays_o = c2w[:3, 3].expand(R, 3).contiguous()
+    t_uni, u_pdf = torch.rand((R, ns), generator=gen), torch.rand((R, ni), generator=gen)
+    field = golden_field(g, 0, requires_grad=False)
+    want = path_ref.render_batch_ray(field, rays_d, rays_o, torch.zeros(R), ns, ni, tr, torch.empty((0, S)), t_uni, u_pdf)
+    zs = P.ops.ZSampler(ns, ni, tr, DEV)
+    z = torch.zeros((R, S), device=DEV)
+    gt0 = torch.zeros(R, device=DEV)
+    zs.depth_guided(gt0, z, t_rand=torch.empty((0, S), device=DEV))
+    zs.no_depth(meta.pack(tabs[0], tabs[1], dec), beta, rays_o.to(DEV), rays_d.to(DEV), gt0, z, u_pdf.to(DEV), t_rand_uni=t_uni.to(DEV))
+    assert float((z.cpu() - want[5]).abs().max()) < 1e-4
+    got = P.ops.render_rays(meta, rays_o.to(DEV), rays_d.to(DEV), z, beta, tabs[0], tabs[1], dec)
+    assert max_rel(got[2].cpu(), want[2], 1e-3) < 1e-3 and max_rel(got[3].cpu(), want[3], 1e-3) < 1e-3
+    # -- no ray survives the mask: NaN loss like torch.mean(empty), and nothing is scattered
+    K = g["call0_c2ws"].shape[0]
+    n = int(g["call0_n"])
+    step = P.MappingStep(meta, tabs[0], tabs[1], dec, beta, n_stratified=ns, n_importance=ni, truncation=tr, max_rays=K * n, max_frames=K)
+    far = torch.full_like(T(g["call0_depths"]), 1e4).to(DEV)                       # beyond the bbox exit: every ray is filtered
+    batch = (T(g["call0_c2ws"]).to(DEV).contiguous(), far, T(g["call0_colors"]).to(DEV), T(g["call0_rays_d_cam"]).to(DEV),
+             T(g["call0_indices"]).to(DEV), n, 0)
+    loss = step.run([batch], torch.rand((K * n, S), device=DEV), torch.rand((K * n, ns), device=DEV), torch.rand((K * n, ni), device=DEV))
+    assert int(step.valid[:K * n].sum()) == 0 and torch.isnan(loss).all()
+    assert float(step.fs.g_sdf_table.abs().sum()) == 0.0 and float(step.fs.g_rgb_table.abs().sum()) == 0.0
+    # -- argument errors
+    with pytest.raises(RuntimeError):
+        P.ops.ZSampler(120, 20, tr, DEV).depth_guided(torch.ones(4, device=DEV), torch.zeros((4, 140), device=DEV))   # S > 128
+    with pytest.raises(RuntimeError):
+        P.MappingStep(meta, tabs[0], tabs[1], dec, beta, n_stratified=ns, n_importance=ni, truncation=tr, max_rays=8).run(
+            [batch], torch.rand((K * n, S), device=DEV))                              # more rays than the step was sized for

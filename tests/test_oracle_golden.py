@@ -17,7 +17,7 @@ def _draws(g):
     return DrawQueue(d)
 
 
-@pytest.mark.parametrize("name", ["map_replica_k1", "map_replica_k7", "map_scannet_k23"])
+@pytest.mark.parametrize("name", ["map_replica_k1", "map_replica_k7", "map_scannet_k23", "map_replica_nomask", "map_replica_kfstore"])
 def test_mapping_iteration_matches_reference(name):
     g = load_golden(name)
     field = golden_field(g, 0)
@@ -37,7 +37,8 @@ def test_mapping_iteration_matches_reference(name):
             assert torch.equal(t.detach(), T(g[f"call{ci}_out_{nm}"])), nm       # bit-exact sampling
     parts = {}
     loss = path_ref.mapping_iteration(field, batches, float(g["truncation"]), int(g["n_stratified"]),
-                                      int(g["n_importance"]), _draws(g), parts=parts)
+                                      int(g["n_importance"]), _draws(g), parts=parts,
+                                      mask_mode=str(g["mask_mode"]) if "mask_mode" in g else "original")
     assert torch.equal(parts["rays_o"].detach(), T(g["render_rays_o"]))
     assert torch.equal(parts["gt_depth"], T(g["render_gt_depth"]))
     ret = parts["ret"]
@@ -61,7 +62,7 @@ def test_mapping_iteration_matches_reference(name):
         assert rel_err(cam_poses.grad, g["grad_cam_poses"]) < 1e-5
 
 
-@pytest.mark.parametrize("name", ["track_replica", "track_scannet"])
+@pytest.mark.parametrize("name", ["track_replica", "track_scannet", "track_scannet_nomask"])
 def test_tracking_iteration_matches_reference(name):
     g = load_golden(name)
     field = golden_field(g, 50, requires_grad=False)
@@ -73,7 +74,7 @@ def test_tracking_iteration_matches_reference(name):
     loss, punc = path_ref.tracking_iteration(field, cam_pose, T(g["depth_img"])[None], T(g["color_img"])[None],
                                              H, W, fx, fy, cx, cy, e, e, T(g["indices"]), float(g["truncation"]),
                                              int(g["n_stratified"]), int(g["n_importance"]), DrawQueue([T(g["t_rand"])]),
-                                             parts=parts)
+                                             parts=parts, mask_mode=str(g["mask_mode"]) if "mask_mode" in g else "original")
     assert torch.equal(parts["rays_o"].detach(), T(g["render_rays_o"]))
     assert torch.equal(parts["rays_d"].detach(), T(g["render_rays_d"]))
     assert torch.equal(parts["ret"][5], T(g["ret_z_vals"]))

@@ -507,7 +507,9 @@ static int check_field(const usl_field_t *f, const usl_points_t *p) {
             set_error("unsupported decoder shape"); return 1;
         }
     }
-    if (!p->x && (!p->rays_o || !p->rays_d || !p->z || p->S <= 0)) { set_error("points: need x or (rays_o, rays_d, z, S)"); return 1; }
+    if (p->n > 0 && !p->x && (!p->rays_o || !p->rays_d || !p->z || p->S <= 0)) {     // an empty batch carries no pointers
+        set_error("points: need x or (rays_o, rays_d, z, S)"); return 1;
+    }
     return 0;
 }
 

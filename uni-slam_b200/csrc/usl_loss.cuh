@@ -8,6 +8,7 @@ namespace usl {
 enum { A_FS = 0, A_CENTER, A_TAIL, A_DEPTH, A_COLOR, N_FRONT, N_CENTER, N_TAIL, N_MASK, N_RAYS, N_COLOR, A_PUNC };
 
 __device__ __forceinline__ bool ray_mask(const usl_loss_args_t &a, float gt, float punc, float depth, const float *median) {
+    if (a.mode == 2) return true;                                           // "no_mask" (Mapper.py:432-440, Tracker.py:230-238)
     const bool alpha_mask = (1.0f - punc) > 0.99f;                          // Mapper.py:414-415 / Tracker.py:210-211
     if (a.mode == 0) return (gt > 0.f) && alpha_mask;                       // Mapper.py:417-420
     const float err = fabsf(gt - depth);

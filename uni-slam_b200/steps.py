@@ -23,6 +23,15 @@ from . import ops
 from ._lib import call, ptr, stream
 
 
+def _mask_mode(mask_mode: str, original: int) -> int:
+    """cfg['m_mask_mode'] / cfg['t_mask_mode'] -> usl_loss_args_t.mode."""
+    if mask_mode == "original":
+        return original
+    if mask_mode == "no_mask":
+        return 2
+    raise ValueError(f"mask_mode must be 'original' or 'no_mask', got {mask_mode!r}")
+
+
 class _Profiled:
     """Optional per-kernel CUDA-event timing on the launching stream (bench.py's roofline leg)."""
     profile = False
@@ -84,13 +93,15 @@ class MappingStep(_Profiled):
     """One mapping iteration (sample -> prefilter -> z-sample -> render -> loss -> backward)."""
 
     def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec, beta, *, n_stratified, n_importance, truncation,
-                 weights=(5.0, 200.0, 10.0, 0.1, 5.0), max_rays: int, max_frames: int = 1, perturb: bool = True):
+                 weights=(5.0, 200.0, 10.0, 0.1, 5.0), max_rays: int, max_frames: int = 1, perturb: bool = True,
+                 mask_mode: str = "original"):
         dev = sdf_table.device
         self.fs = _FieldState(meta, sdf_table, rgb_table, dec, beta, with_grads=True, max_frames=max_frames)
         self.zs = ops.ZSampler(n_stratified, n_importance, truncation, dev)
         self.S = self.zs.S
         self.perturb = perturb
-        self.loss_args = ops.make_loss_args(truncation, weights[0], weights[1], weights[2], weights[3], weights[4], 0)
+        self.loss_args = ops.make_loss_args(truncation, weights[0], weights[1], weights[2], weights[3], weights[4],
+                                            _mask_mode(mask_mode, 0))                       # cfg['m_mask_mode'], Mapper.py:94
         R, S = max_rays, self.S
         f32 = dict(device=dev, dtype=torch.float32)
         self.max_rays = R
@@ -155,7 +166,8 @@ class MappingStep(_Profiled):
             b_.depths, b_.colors, b_.dirs_cam, b_.indices = ptr(depths), ptr(colors), ptr(dirs_cam), ptr(indices)
             b_.P, b_.K, b_.n, b_.frame_base = P, Kb, n, frame_base
             R += Kb * n
-        assert R <= self.max_rays
+        if R > self.max_rays:
+            raise RuntimeError(f"MappingStep: {R} rays requested, buffers sized for max_rays={self.max_rays}")
         self.n_rays = R
         v = lambda t: ptr(t[:R]) if t is not None else None
         rs.cam_poses = ptr(cam_poses) if joint else None
@@ -220,7 +232,7 @@ class TrackingStep(_Profiled):
 
     def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec, beta, *, n_stratified, n_importance, truncation,
                  H, W, fx, fy, cx, cy, ignore_edge_h, ignore_edge_w, n_rays: int,
-                 weights=(10.0, 200.0, 50.0, 1.0, 5.0), perturb: bool = True):
+                 weights=(10.0, 200.0, 50.0, 1.0, 5.0), perturb: bool = True, mask_mode: str = "original"):
         dev = sdf_table.device
         self.fs = _FieldState(meta, sdf_table, rgb_table, dec, beta, with_grads=False)
         self.zs = ops.ZSampler(n_stratified, n_importance, truncation, dev)
@@ -228,7 +240,8 @@ class TrackingStep(_Profiled):
         self.perturb = perturb
         self.cam = (H, W, float(fx), float(fy), float(cx), float(cy))
         self.win = (ignore_edge_h, H - ignore_edge_h, ignore_edge_w, W - ignore_edge_w)
-        self.loss_args = ops.make_loss_args(truncation, weights[0], weights[1], weights[2], weights[3], weights[4], 1)
+        self.loss_args = ops.make_loss_args(truncation, weights[0], weights[1], weights[2], weights[3], weights[4],
+                                            _mask_mode(mask_mode, 1))                       # cfg['t_mask_mode']
         R, S = n_rays, self.S
         self.R = R
         f32 = dict(device=dev, dtype=torch.float32)
