@@ -497,7 +497,9 @@ def bench_tracking(P, wl, meta, tabs, dec, beta, cfg, dev, args):
     wlmod = importlib.import_module("uni-slam_b200.workload")
     pose = wlmod._matrix_to_cam_pose(c2w[None]).contiguous()
     pose[:, 4:] += 0.01
-    T_ = pose[:, 4:].clone().requires_grad_(True); R_ = pose[:, :4].clone().requires_grad_(True)
+    # cam_pose = cat([R, T]) (Tracker.py:333) without the per-iteration cat: R and T are the two halves of ONE (1,7) tensor
+    cam_pose = pose.clone().contiguous()
+    T_ = cam_pose[:, 4:].requires_grad_(True); R_ = cam_pose[:, :4].requires_grad_(True)
     T_.grad = trk.d_pose[:, 4:]; R_.grad = trk.d_pose[:, :4]           # persistent .grad views of the step's output
     # Tracker.py:324-329: Adam(T lr_T, R lr_R, betas (0.5, 0.999)) -- here the one-launch fused equivalent
     opt = P.FusedAdam([{"params": [T_], "lr": cfg.lr_T, "betas": (0.5, 0.999)}, {"params": [R_], "lr": cfg.lr_R, "betas": (0.5, 0.999)}])
@@ -505,15 +507,11 @@ def bench_tracking(P, wl, meta, tabs, dec, beta, cfg, dev, args):
     npx = (cam.H - 2 * e) * (cam.W - 2 * e)
     idx = torch.empty((cfg.track_pixels,), device=dev, dtype=torch.int64)
     t_rand = torch.empty((cfg.track_pixels, trk.S), device=dev)
-    cam_pose = torch.empty((1, 7), device=dev)
     best_loss = torch.full((1,), float("inf"), device=dev); best_pose = torch.zeros((1, 7), device=dev)
 
     def it():
         idx.random_(0, npx); t_rand.uniform_()                          # common.py:116, Renderer.py:55 (host-side RNG)
-        cam_pose.copy_(torch.cat([R_.detach(), T_.detach()], -1))       # Tracker.py:333
-        trk.run(cam_pose, dep, col, idx, t_rand)
-        better = trk.loss < best_loss                                    # Tracker.py:346-348, kept on the device (no .item() sync)
-        best_pose.copy_(torch.where(better, cam_pose, best_pose)); best_loss.copy_(torch.where(better, trk.loss, best_loss))
+        trk.run(cam_pose, dep, col, idx, t_rand, best_loss, best_pose)  # incl. Tracker.py:346-348 on the device (no .item() sync)
         opt.step()
 
     s_ = torch.cuda.Stream(); s_.wait_stream(torch.cuda.current_stream())

@@ -285,6 +285,11 @@ USL_API int usl_pose_to_matrix(const float *pose, int K, float *c2w, usl_stream_
 /* d_pose[K,7] = chain of d_c2w[K,12] through quaternion_to_matrix (un-normalised quaternion). */
 USL_API int usl_pose_matrix_bwd(const float *pose, const float *d_c2w, int K, float *d_pose, usl_stream_t stream);
 
+/* Tracker.py:346-348 on the device (no .item() sync): if (loss[0] < best_loss[0]) { best_loss[0] = loss[0];
+ * best_pose[0..7) = cam_pose[0..7) }  -- "best pose = the pose at which the minimal loss was evaluated". */
+USL_API int usl_track_keep_best(const float *loss, const float *cam_pose, float *best_loss, float *best_pose,
+                                usl_stream_t stream);
+
 /* ---- a-11: dense SDF query for meshing (src/utils/Mesher.py:134-195) ----------------------- */
 /* points generated in-kernel from the per-axis coordinate arrays ax/ay/az (np.linspace -> fp32),
  * ordering of torch.meshgrid(indexing='xy') flattened: idx = (iy*nx + ix)*nz + iz for iy in

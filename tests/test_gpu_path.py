@@ -458,3 +458,34 @@ def test_empty_and_degenerate_inputs():
     with pytest.raises(RuntimeError):
         P.MappingStep(meta, tabs[0], tabs[1], dec, beta, n_stratified=ns, n_importance=ni, truncation=tr, max_rays=8).run(
             [batch], torch.rand((K * n, S), device=DEV))                              # more rays than the step was sized for
+
+
+def test_median_select_and_keep_best():
+    """torch.median (lower middle) of |gt - depth| over valid rays for ragged sizes, ties, NaN; and the tracker's
+    on-device best-pose bookkeeping (Tracker.py:346-348)."""
+    P = pkg()
+    L = P._lib
+    gen = torch.Generator().manual_seed(3)
+    for n in (1, 2, 5, 255, 256, 2000, 4097):
+        gt = torch.rand(n, generator=gen) * 3; dep = torch.rand(n, generator=gen) * 3
+        if n >= 5:
+            dep[1] = dep[0] = gt[0] - 0.25; gt[1] = gt[0]                            # ties
+        valid = (torch.rand(n, generator=gen) > 0.2).to(torch.uint8)
+        valid[0] = 1
+        want = (gt - dep).abs()[valid.bool()].median()
+        ws = torch.empty(n, device=DEV); med = torch.zeros(1, device=DEV)
+        gd, dd, vd = gt.to(DEV), dep.to(DEV), valid.to(DEV)                         # keep the device copies alive across the call
+        L.call("usl_depth_error_median", L.ptr(gd), L.ptr(dd), L.ptr(vd), n, L.ptr(ws), L.ptr(med), L.stream())
+        assert float(med) == float(want), n                                          # selection: bit-exact
+    dep[3] = float("nan"); valid[3] = 1
+    gd, dd, vd = gt.to(DEV), dep.to(DEV), valid.to(DEV)
+    L.call("usl_depth_error_median", L.ptr(gd), L.ptr(dd), L.ptr(vd), n, L.ptr(ws), L.ptr(med), L.stream())
+    assert torch.isnan(med).all()                                                    # torch.median propagates NaN
+    best_loss = torch.full((1,), float("inf"), device=DEV); best_pose = torch.zeros((1, 7), device=DEV)
+    poses = torch.randn(4, 1, 7, device=DEV)
+    for loss, keep in ((3.0, True), (5.0, False), (float("nan"), False), (1.0, True)):
+        i = [3.0, 5.0, float("nan"), 1.0].index(loss) if loss == loss else 2
+        lt = torch.tensor([loss], device=DEV)
+        L.call("usl_track_keep_best", L.ptr(lt), L.ptr(poses[i]), L.ptr(best_loss), L.ptr(best_pose), L.stream())
+        assert torch.equal(best_pose, poses[i]) == keep
+    assert float(best_loss) == 1.0

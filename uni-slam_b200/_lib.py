@@ -107,6 +107,7 @@ _SIGS = {
     "usl_pose_reduce": [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P],
     "usl_pose_to_matrix": [_P, c_int, _P, _P],
     "usl_pose_matrix_bwd": [_P, _P, c_int, _P, _P],
+    "usl_track_keep_best": [_P, _P, _P, _P, _P],
     "usl_sdf_query_grid": [POINTER(Field), _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "usl_ray_setup": [POINTER(RaySetup), _P],
     "usl_composite_loss_bwd": [POINTER(LossArgs), _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, POINTER(Bound),

@@ -11,5 +11,5 @@ for f in encode field field_tc sampling composite loss adam; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-nvcc -shared -o "$OUT/libunislam_b200.so" "$HERE"/_obj/{encode,field,field_tc,sampling,composite,loss,adam}.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libunislam_b200.so" "$HERE"/_obj/{encode,field,field_tc,sampling,composite,loss,adam}.o -lcudart
 echo "built $OUT/libunislam_b200.so"

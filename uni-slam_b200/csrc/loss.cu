@@ -139,16 +139,41 @@ __global__ void __launch_bounds__(MED_THREADS) depth_error_median_kernel(const f
             if ((b & himask) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (t == 0) {
-            unsigned int k = s_k, c = 0;
-            int bin = 0;
-            for (; bin < 256; ++bin) { if (c + hist[bin] > k) break; c += hist[bin]; }
-            s_k = k - c;
-            s_prefix = prefix | ((unsigned int)bin << shift);
+        if (t < 32) {                                    // warp 0: lane l owns bins 8l..8l+7, exclusive scan of the lane sums
+            unsigned int own = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) own += hist[t * 8 + q];
+            unsigned int inc = own;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (t >= o) inc += v;
+            }
+            const unsigned int k = s_k, before = inc - own;
+            __syncwarp();                                 // every lane has read s_k before one of them replaces it
+            if (k >= before && k < inc) {                 // exactly one lane: the k-th element falls into its bins
+                unsigned int c = before;
+                int bin = t * 8;
+                for (; bin < t * 8 + 8; ++bin) { if (c + hist[bin] > k) break; c += hist[bin]; }
+                s_k = k - c;
+                s_prefix = prefix | ((unsigned int)bin << shift);
+            }
         }
         __syncthreads();
     }
     if (t == 0) median[0] = __uint_as_float(s_prefix);
+}
+
+// Tracker.py:346-348: keep the pose at which the minimal loss was evaluated
+__global__ void track_keep_best_kernel(const float *__restrict__ loss, const float *__restrict__ pose,
+                                       float *__restrict__ best_loss, float *__restrict__ best_pose) {
+    const bool better = loss[0] < best_loss[0];          // false for a NaN loss, as in the reference
+    __syncwarp();
+    if (better) {
+        if (threadIdx.x < 7) best_pose[threadIdx.x] = pose[threadIdx.x];
+        __syncwarp();
+        if (threadIdx.x == 0) best_loss[0] = loss[0];
+    }
 }
 
 // ---- pose gradient ------------------------------------------------------------------------------
@@ -265,6 +290,12 @@ int usl_depth_error_median(const float *gt_depth, const float *depth, const uint
     if (R <= 0) { set_error("usl_depth_error_median: empty input"); return 1; }
     depth_error_median_kernel<<<1, MED_THREADS, 0, (cudaStream_t)stream>>>(gt_depth, depth, valid, R, workspace, median);
     return check_launch("usl_depth_error_median");
+}
+
+int usl_track_keep_best(const float *loss, const float *cam_pose, float *best_loss, float *best_pose, usl_stream_t stream) {
+    if (!loss || !cam_pose || !best_loss || !best_pose) { set_error("usl_track_keep_best: null argument"); return 1; }
+    track_keep_best_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss, cam_pose, best_loss, best_pose);
+    return check_launch("usl_track_keep_best");
 }
 
 int usl_pose_reduce(const float *d_rays_o, const float *d_rays_d, const float *dirs_cam, const int32_t *frame_id,

@@ -90,17 +90,15 @@ def run_slam(cfg: syn.SceneCfg = syn.REPLICA_ROOM0, n_frames: int = 40, device="
             if prior_noise_m > 0:                                              # perturbed initial guess: the tracker has to pull it back
                 pose0 = pose0.clone(); pose0[:, 4:] += prior_noise_m * torch.randn(3, device=device)
             prior[k] = _pose_to_c2w(pose0)
-            T_ = pose0[:, 4:].clone().contiguous().requires_grad_(True); R_ = pose0[:, :4].clone().contiguous().requires_grad_(True)
+            cam_pose = pose0.clone().contiguous()                              # cat([R, T]) (Tracker.py:333): R, T are its two halves
+            T_ = cam_pose[:, 4:].requires_grad_(True); R_ = cam_pose[:, :4].requires_grad_(True)
             T_.grad = tstep.d_pose[:, 4:]; R_.grad = tstep.d_pose[:, :4]
             opt = FusedAdam([{"params": [T_], "lr": cfg.lr_T, "betas": (0.5, 0.999)}, {"params": [R_], "lr": cfg.lr_R, "betas": (0.5, 0.999)}])
             best_loss = torch.full((1,), float("inf"), device=device); best_pose = pose0.clone()
             for _ in range(track_iters):
-                cam_pose = torch.cat([R_.detach(), T_.detach()], -1).contiguous()
                 idx = torch.randint(npx_win, (cfg.track_pixels,), device=device)
                 t_rand = torch.rand((cfg.track_pixels, S), device=device)
-                loss = tstep.run(cam_pose, dep, col, idx, t_rand)
-                better = loss < best_loss
-                best_pose = torch.where(better, cam_pose, best_pose); best_loss = torch.where(better, loss, best_loss)
+                tstep.run(cam_pose, dep, col, idx, t_rand, best_loss, best_pose)   # keeps the best pose on the device (Tracker.py:346-348)
                 opt.step()
                 n_track += 1
             est[k] = _pose_to_c2w(best_pose)

@@ -261,10 +261,12 @@ class TrackingStep(_Profiled):
         self.d_pose = torch.zeros((1, 7), **f32)
         self._init_prof()
 
-    def run(self, cam_pose, depth_img, color_img, indices, t_rand):
+    def run(self, cam_pose, depth_img, color_img, indices, t_rand, best_loss=None, best_pose=None):
         """cam_pose (1,7) = [quat(real first), trans] (common.py:196-208); depth_img (H,W); color_img (H,W,3);
         indices: torch.randint(window_pixels, (R,)) (common.py:116); t_rand (R,S). Returns loss (1,);
-        d loss/d cam_pose in self.d_pose; mean pixel uncertainty = acc[11]/acc[9]."""
+        d loss/d cam_pose in self.d_pose; mean pixel uncertainty = acc[11]/acc[9].
+        best_loss (1,) / best_pose (1,7), when given, are updated on the device the way Tracker.py:346-348 keeps its
+        candidate pose (before the optimiser moves cam_pose)."""
         st = stream()
         fs, S, R = self.fs, self.S, self.R
         H, W, fx, fy, cx, cy = self.cam
@@ -296,6 +298,8 @@ class TrackingStep(_Profiled):
                    byref(fs.meta.bound), ptr(self.d_raw), None, ptr(self.d_rays_o), ptr(self.d_rays_d), ptr(self.loss), st)
         self._call("usl_pose_reduce", ptr(self.d_rays_o), ptr(self.d_rays_d), ptr(self.dirs), None, ptr(self.valid), R, 1, ptr(self.d_c2w), st)
         call("usl_pose_matrix_bwd", ptr(cam_pose), ptr(self.d_c2w), 1, ptr(self.d_pose), st)
+        if best_loss is not None:
+            call("usl_track_keep_best", ptr(self.loss), ptr(cam_pose), ptr(best_loss), ptr(best_pose), st)
         return self.loss
 
 
