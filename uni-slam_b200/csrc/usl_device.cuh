@@ -103,24 +103,41 @@ __device__ __forceinline__ void scatter_level(float2 *__restrict__ tab, const ui
     }
 }
 
-// Lane-paired variant: the whole warp takes part (inactive lanes pass act=false).  Lanes (2k, 2k+1) serve ONE point's
-// x-pair per instruction -- the even lane its own first corner, the odd lane its partner's second corner (then the roles
-// swap) -- so the two corners, which share a 32-byte sector in 75 % of the cases (16-byte slot in 50 %), travel in the same
-// instruction and are merged into one L2 atomic sector operation: ~5 instead of 6 (pairing by 16-byte slot) or 8.
-__device__ __forceinline__ void scatter_level_paired(float2 *__restrict__ tab, const uint32_t idx[8], const float wt[8],
-                                                     float dfx, float dfy, bool act, int lane) {
-    const bool odd = (lane & 1) != 0;
-    const bool pact = __shfl_xor_sync(0xffffffffu, act ? 1 : 0, 1) != 0;
+// Half-cell scatter for the lane-pair scheme of field_bwd: this lane serves the 4 corners on x-side `side` (0: g_x,
+// 1: g_x + 1) of the point at (x0,x1,x2).  Lanes (2k, 2k+1) call it with the SAME point and side = lane & 1, so corner q of
+// both sides -- neighbouring entries, one 32-byte sector in 75 % of the cases -- travels in one instruction and the L2
+// merges the pair into one atomic sector operation.  Only the point's coordinates and its two level gradients cross
+// the lane pair (2 shuffles per level); indices and weights are computed where they are used.  Index and weight
+// arithmetic is corner_indices<true> / corner_weights restricted to one x-side (bit-identical values).
+__device__ __forceinline__ void scatter_level_side(float2 *__restrict__ tab, const usl_level_t &lv, float x0, float x1, float x2,
+                                                   uint32_t side, float dfx, float dfy, bool act) {
+    const Cell c = make_cell(lv, x0, x1, x2);
+    uint32_t idx[4];
+    if (lv.hashed) {
+        const uint32_t mask = lv.size - 1u;
+        const uint32_t hx = c.g[0] + side;
+        const uint32_t hy0 = c.g[1] * USL_PRIME_Y, hy1 = hy0 + USL_PRIME_Y;
+        const uint32_t hz0 = c.g[2] * USL_PRIME_Z, hz1 = hz0 + USL_PRIME_Z;
+        idx[0] = (hx ^ hy0 ^ hz0) & mask; idx[1] = (hx ^ hy1 ^ hz0) & mask;
+        idx[2] = (hx ^ hy0 ^ hz1) & mask; idx[3] = (hx ^ hy1 ^ hz1) & mask;
+    } else {
+        const uint32_t res = lv.res, res2 = lv.res * lv.res;
+        const uint32_t base = c.g[0] + side + c.g[1] * res + c.g[2] * res2;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const uint32_t i0 = idx[2 * p], i1 = idx[2 * p + 1];
-        const float v0x = wt[2 * p] * dfx, v0y = wt[2 * p] * dfy;
-        const float v1x = wt[2 * p + 1] * dfx, v1y = wt[2 * p + 1] * dfy;
-        const uint32_t pi1 = __shfl_xor_sync(0xffffffffu, i1, 1);
-        const float pv1x = __shfl_xor_sync(0xffffffffu, v1x, 1), pv1y = __shfl_xor_sync(0xffffffffu, v1y, 1);
-        // A: the even lane's point; B: the odd lane's point
-        if (odd ? pact : act) atomicAdd(tab + (odd ? pi1 : i0), odd ? make_float2(pv1x, pv1y) : make_float2(v0x, v0y));
-        if (odd ? act : pact) atomicAdd(tab + (odd ? i0 : pi1), odd ? make_float2(v0x, v0y) : make_float2(pv1x, pv1y));
+        for (int q = 0; q < 4; ++q) {
+            uint32_t i = base + (q & 1) * res + (q >> 1) * res2;
+            if (i >= lv.size) i -= lv.size;               // clamped coordinates: one conditional subtract is the exact modulo
+            idx[q] = i;
+        }
+    }
+    const float wx = side ? c.w[0] : 1.0f - c.w[0];
+    const float a1 = 1.0f - c.w[1], a2 = 1.0f - c.w[2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float w = wx;                                      // tcnn's multiplication order: ((f0) * f1) * f2
+        w *= (q & 1) ? c.w[1] : a1;
+        w *= (q & 2) ? c.w[2] : a2;
+        if (act) atomicAdd(tab + idx[q], make_float2(w * dfx, w * dfy));
     }
 }
 
