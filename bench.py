@@ -216,7 +216,9 @@ def run_ours(args, rank, world, local_rank):
     opt = torch.optim.Adam([{"params": dec + [beta], "lr": 1e-3}, {"params": [tabs[0]], "lr": cfg.hash_lr},
                             {"params": [tabs[1]], "lr": cfg.hash_lr}, {"params": [cam_poses], "lr": 1e-3}])
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
-    bufs = list(wl.draw(gen))                                          # static input buffers (graph replays read them)
+    flat_idx, flat_u, bufs = wl.alloc_draws()                          # static input buffers (graph replays read them)
+    bufs = list(bufs)
+    flat_idx.random_(0, wl.P, generator=gen); flat_u.uniform_(generator=gen)
 
     reduce_grads = None
     if world > 1:
@@ -225,11 +227,10 @@ def run_ours(args, rank, world, local_rank):
 
     def one_step():
         idx_main, idx_recent, t_rand, t_uni, u_pdf = bufs
-        # host-code side of the iteration: the RNG draws (torch.randint / torch.rand, common.py:155, Renderer.py:55)
-        idx_main.random_(0, wl.P, generator=gen)
-        if idx_recent is not None:
-            idx_recent.random_(0, wl.P, generator=gen)
-        t_rand.uniform_(generator=gen); t_uni.uniform_(generator=gen); u_pdf.uniform_(generator=gen)
+        # host-code side of the iteration: the RNG draws (torch.randint / torch.rand, common.py:155, Renderer.py:55) --
+        # one index fill and one uniform fill over the two flat buffers that hold the five slot-indexed tensors
+        flat_idx.random_(0, wl.P, generator=gen)
+        flat_u.uniform_(generator=gen)
         if args.no_joint:
             step.run(wl.batches(idx_main, idx_recent), t_rand, t_uni, u_pdf)
         else:

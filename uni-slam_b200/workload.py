@@ -53,6 +53,20 @@ class MappingWorkload:
         u_pdf = torch.rand((R, self.cfg.n_importance), device=dev, generator=gen)
         return idx_main, idx_recent, t_rand, t_uni, u_pdf
 
+    def alloc_draws(self):
+        """Static input buffers for the iteration's draws, laid out so that ONE torch.randint-style fill and ONE
+        torch.rand-style fill produce all of them (the fused driver indexes draws by ray slot, so the five tensors
+        the reference draws separately can live in two flat buffers).  Returns (flat_idx, flat_u, views) with
+        views = (idx_main, idx_recent|None, t_rand, t_uni, u_pdf) in draw() order."""
+        dev = self.depths.device
+        R, S, ns, ni = self.n_rays, self.S, self.cfg.n_stratified, self.cfg.n_importance
+        n_main, n_rec = self.K * self.n_main, (10 * self.n_recent if self.n_recent else 0)
+        flat_idx = torch.zeros((n_main + n_rec,), device=dev, dtype=torch.int64)
+        flat_u = torch.zeros((R * (S + ns + ni),), device=dev, dtype=torch.float32)
+        views = (flat_idx[:n_main], flat_idx[n_main:] if n_rec else None, flat_u[:R * S].view(R, S),
+                 flat_u[R * S:R * (S + ns)].view(R, ns), flat_u[R * (S + ns):].view(R, ni))
+        return flat_idx, flat_u, views
+
     def batches(self, idx_main, idx_recent):
         b = [(self.c2ws, self.depths, self.colors, self.dirs_cam, idx_main, self.n_main, 0)]
         if self.n_recent:
