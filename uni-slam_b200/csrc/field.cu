@@ -107,16 +107,27 @@ struct QueryArgs {
     float *out;
 };
 
+// CTA = tile of 32 (x) x 8 (z) grid points of one y row; lane = x.  The dense levels store entries x-fastest and the
+// hash's x coefficient is 1, so the 32 lanes of a gather hit neighbouring entries (a few 32-byte sectors) instead of 32
+// sectors a z-line of points would touch -- the kernel is bound by L1TEX sector requests, not by FLOPs or DRAM.  The 8
+// warps of the CTA cover 8 consecutive z, i.e. exactly one 32-byte sector of the z-fastest output per (y, x): the
+// partial stores of a CTA combine in L2.
+#define QT_X 32
+#define QT_Z 8
 __global__ void __launch_bounds__(256) sdf_query_grid_kernel(const __grid_constant__ QueryArgs A) {
     __shared__ MlpSmem sm;
     stage_mlp(A.f.mlp[0], sm);
     __syncthreads();
-    const int64_t total = (int64_t)(A.y_end - A.y_begin) * A.nx * A.nz;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int iz = (int)(i % A.nz);
-        const int64_t t = i / A.nz;
-        const int ix = (int)(t % A.nx);
-        const int iy = (int)(t / A.nx) + A.y_begin;
+    const int tx = (A.nx + QT_X - 1) / QT_X, tz = (A.nz + QT_Z - 1) / QT_Z;
+    const int64_t tiles = (int64_t)(A.y_end - A.y_begin) * tx * tz;
+    const int lx = threadIdx.x & (QT_X - 1), lz = threadIdx.x / QT_X;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int bz = (int)(t % tz);
+        const int64_t r = t / tz;
+        const int bx = (int)(r % tx);
+        const int iy = (int)(r / tx) + A.y_begin;
+        const int ix = bx * QT_X + lx, iz = bz * QT_Z + lz;
+        if (ix >= A.nx || iz >= A.nz) continue;
         const float p[3] = {A.ax[ix], A.ay[iy], A.az[iz]};
         bool inside = true;
         float xc[3];
@@ -133,7 +144,8 @@ __global__ void __launch_bounds__(256) sdf_query_grid_kernel(const __grid_consta
                                        xc, nullptr, 0, out, tout);
             v = out[0];
         }
-        __stcs(A.out + i, v);
+        // idx = (iy*nx + ix)*nz + iz within the slab (torch.meshgrid(indexing='xy') flattened, Mesher.py:192-193)
+        __stcs(A.out + ((int64_t)(iy - A.y_begin) * A.nx + ix) * A.nz + iz, v);
     }
 }
 
@@ -662,7 +674,7 @@ int usl_sdf_query_grid(const usl_field_t *f, const float *ax, const float *ay, c
     if (total <= 0) return 0;
     QueryArgs A;
     A.f = *f; A.ax = ax; A.ay = ay; A.az = az; A.nx = nx; A.ny = ny; A.nz = nz; A.y_begin = y_begin; A.y_end = y_end; A.out = out;
-    int64_t blocks = (total + 255) / 256;
+    int64_t blocks = (int64_t)(y_end - y_begin) * ((nx + QT_X - 1) / QT_X) * ((nz + QT_Z - 1) / QT_Z);   // one tile per CTA and pass
     const int64_t cap = 148 * 64;
     if (blocks > cap) blocks = cap;
     sdf_query_grid_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A);
