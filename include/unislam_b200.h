@@ -205,6 +205,10 @@ typedef struct usl_points {
     const float *z;       /* [R,S] */
     const uint8_t *valid; /* [R] or NULL */
     int32_t S;
+    int32_t sample_major; /* built from rays only. 0: thread i = (ray i / S, sample i % S). 1: thread i = (ray i % R, sample i / R),
+                           * R = n / S -- a warp then holds the SAME sample index of 32 consecutive rays; when consecutive rays
+                           * are neighbouring pixels (whole-frame rendering) its points are centimetres apart and share cells.
+                           * Outputs are written in ray-major order either way. */
     int64_t n;            /* number of points (= R*S when built from rays) */
 } usl_points_t;
 /* raw[n,4] = (r,g,b,sdf). feat (nullable): activation stash for the backward pass, 2*n*48 floats:

@@ -42,7 +42,7 @@ class Bound(Structure):
 
 class Points(Structure):
     _fields_ = [("x", c_void_p), ("rays_o", c_void_p), ("rays_d", c_void_p), ("z", c_void_p), ("valid", c_void_p),
-                ("S", c_int32), ("n", c_int64)]
+                ("S", c_int32), ("sample_major", c_int32), ("n", c_int64)]
 
 
 class ZSampleArgs(Structure):

@@ -22,16 +22,24 @@ struct FieldArgs {
 };
 
 // Loads point i: clamped normalised coordinate xc, clamp gate (1 inside [0,1], else 0).
+// oi (optional): index of the point in the ray-major output arrays (differs from i only in sample-major mode).
 __device__ __forceinline__ bool load_point(const usl_points_t &p, const usl_field_t &f, int64_t i, float xc[3],
-                                           float gate[3]) {
+                                           float gate[3], int64_t *oi = nullptr) {
     float x[3];
+    if (oi) *oi = i;
     if (p.x) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) x[d] = p.x[i * 3 + d];
     } else {
-        const int64_t r = i / p.S;
+        int64_t r = i / p.S, zi = i;
+        if (p.sample_major) {
+            const int64_t R = p.n / p.S;
+            r = i % R;
+            zi = r * p.S + i / R;
+            if (oi) *oi = zi;
+        }
         if (p.valid && !p.valid[r]) return false;
-        const float z = p.z[i];
+        const float z = p.z[zi];
 #pragma unroll
         for (int d = 0; d < 3; ++d) x[d] = norm_coord(p.rays_o[r * 3 + d], p.rays_d[r * 3 + d], z, f.bound_lo[d], f.bound_hi[d]);
     }
@@ -52,11 +60,11 @@ __global__ void __launch_bounds__(256, (WITH_JAC ? USL_FWD_MINB : 4)) field_fwd_
     const int gi = blockIdx.y;
     stage_mlp(A.f.mlp[gi], sm);
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // no early exit: the paired gather is warp-collective; inactive lanes run on a dummy point and write nothing
     float xc[3] = {0.f, 0.f, 0.f}, gate[3] = {0.f, 0.f, 0.f};
-    const bool active = (i < A.p.n) && load_point(A.p, A.f, i, xc, gate);
+    int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // thread's point; i below = its slot in the ray-major outputs
+    const bool active = (ti < A.p.n) && load_point(A.p, A.f, ti, xc, gate, &ti);
     if (!__any_sync(0xffffffffu, active)) return;           // warps made only of filtered rays cost nothing
+    const int64_t i = ti;
     const usl_grid_t &g = A.f.grid[gi];
     float out[4], tout[4][3];
     // stash layout: features [2][L][n][2] then hidden pre-activations [2][16][n]
@@ -565,7 +573,8 @@ int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float
     // and profiled, but not the default: the kernel is bound by L1 sector lookups of the gather,
     // so moving 57 % of the FMA-pipe work to the tensor pipe does not shorten it (196 us vs 182 us measured).
     const char *tc_env = getenv("USL_TCGEN05");
-    if (jac && tc_env && tc_env[0] == '1') return usl_field_fwd_tc_launch(f, p, raw, feat, jac, s);
+    if (p->sample_major && !p->x && (p->n % p->S)) { set_error("usl_field_fwd: sample_major needs n == R * S"); return 1; }
+    if (jac && tc_env && tc_env[0] == '1' && !p->sample_major) return usl_field_fwd_tc_launch(f, p, raw, feat, jac, s);
     if (jac && feat) field_fwd_kernel<true, true><<<grid, 256, 0, s>>>(A);
     else if (jac) field_fwd_kernel<true, false><<<grid, 256, 0, s>>>(A);
     else if (feat) field_fwd_kernel<false, true><<<grid, 256, 0, s>>>(A);
@@ -576,6 +585,7 @@ int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float
 int usl_field_sdf(const usl_field_t *f, const usl_points_t *p, float *sdf, usl_stream_t stream) {
     if (check_field(f, p)) return 1;
     if (p->n <= 0) return 0;
+    if (p->sample_major) { set_error("usl_field_sdf: sample_major point order is only supported by usl_field_fwd"); return 1; }
     FieldArgs A;
     A.f = *f; A.p = *p; A.raw = nullptr; A.feat = nullptr; A.jac = nullptr; A.sdf = sdf;
     field_sdf_kernel<<<(unsigned)((p->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A);
@@ -597,6 +607,7 @@ int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw,
     if (check_field(f, p)) return 1;
     if (p->n <= 0) return 0;
     if (!feat || !raw || !d_raw) { set_error("usl_field_bwd: raw, feat and d_raw are required"); return 1; }
+    if (p->sample_major) { set_error("usl_field_bwd: sample_major point order is only supported by usl_field_fwd"); return 1; }
     if (f->mlp[0].n_hidden != f->mlp[1].n_hidden) { set_error("usl_field_bwd: decoders must share n_hidden"); return 1; }
     FieldBwdArgs A;
     A.f = *f; A.p = *p; A.raw = raw; A.feat = feat; A.d_raw = d_raw;

@@ -323,6 +323,7 @@ class RenderImageStep(_Profiled):
         self.perturb = perturb
         self.cam = (int(H), int(W), float(fx), float(fy), float(cx), float(cy))
         C = self.chunk = int(min(chunk_rays, H * W))
+        self.sample_major = os.environ.get("USL_RENDER_SAMPLE_MAJOR", "1") != "0"
         f32 = dict(device=dev, dtype=torch.float32)
         self.rays_o = torch.empty((C, 3), **f32); self.rays_d = torch.empty((C, 3), **f32)
         self.gt_depth = torch.empty((C,), **f32); self.valid = torch.empty((C,), device=dev, dtype=torch.uint8)
@@ -368,6 +369,7 @@ class RenderImageStep(_Profiled):
             pts = L.Points()
             pts.x = None; pts.rays_o, pts.rays_d, pts.z, pts.valid = ptr(self.rays_o), ptr(self.rays_d), ptr(self.z), None
             pts.S, pts.n = S, n * S
+            pts.sample_major = 1 if self.sample_major else 0   # consecutive rays = neighbouring pixels: a warp's points share cells
             self._call("usl_field_fwd", byref(fs.field), byref(pts), ptr(self.raw), None, None, st)
             self._call("usl_composite_fwd", ptr(self.raw), ptr(self.z), ptr(fs.beta), None, n, S, sl(out["term"]), sl(out["pixel_unc"]),
                        sl(out["depth"]), sl(out["color"]), sl(out["depth_unc"]), None, st)
