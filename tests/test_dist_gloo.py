@@ -55,6 +55,13 @@ def _worker(rank, world, port, q):
     b, e = par.slab_range(ny, rank, world)
     out = par.gather_slabs(full[b * nx * nz:e * nx * nz].clone(), ny, nx, nz, rank, world)
     ok_slab = True if rank != 0 else bool(torch.equal(out, full))
+    # image rows sharded the same way (frame renderer): an (H,W,3) colour image in row slabs of pixel ranges
+    H, W = 5, 4
+    img = torch.arange(H * W * 3, dtype=torch.float32)
+    r0, r1 = par.slab_range(H, rank, world)
+    p0, p1 = r0 * W, r1 * W                                     # the pixel range RenderImageStep.run(pixel_begin, pixel_end) takes
+    out = par.gather_slabs(img[p0 * 3:p1 * 3].clone(), H, W, 3, rank, world)
+    ok_slab = ok_slab and (True if rank != 0 else bool(torch.equal(out, img)))
     q.put((rank, ok_loss, ok_slab))
     dist.barrier()
     dist.destroy_process_group()

@@ -147,3 +147,26 @@ def test_keyframe_store_matches_reference_bookkeeping():
     with pytest.raises(RuntimeError):
         for k in range(20):
             store.promote_staged(100 + k)
+
+
+def test_workload_draw_buffers_and_mask_modes():
+    """Host logic of the fused drivers: the two flat draw buffers expose the five slot-indexed tensors as views in draw()
+    order (one index fill + one uniform fill reach all of them), and the loss mask modes map onto the C-ABI enum."""
+    wl = importlib.import_module("uni-slam_b200.workload")
+    syn = importlib.import_module("uni-slam_b200.synthetic")
+    steps = importlib.import_module("uni-slam_b200.steps")
+    w = wl.build_mapping_workload(syn.REPLICA_ROOM0, "cpu", n_keyframes=21, scale_hw=0.05)
+    flat_idx, flat_u, (idx_main, idx_recent, t_rand, t_uni, u_pdf) = w.alloc_draws()
+    assert idx_main.shape == (w.K * w.n_main,) and idx_recent.shape == (10 * w.n_recent,)
+    assert t_rand.shape == (w.n_rays, w.S) and t_uni.shape == (w.n_rays, 32) and u_pdf.shape == (w.n_rays, 8)
+    ref = w.draw(torch.Generator().manual_seed(0))
+    assert [tuple(t.shape) for t in ref] == [tuple(t.shape) for t in (idx_main, idx_recent, t_rand, t_uni, u_pdf)]
+    flat_idx.fill_(7); flat_u.fill_(0.5)
+    assert all(bool((t == 7).all()) for t in (idx_main, idx_recent)) and all(bool((t == 0.5).all()) for t in (t_rand, t_uni, u_pdf))
+    assert flat_idx.numel() == idx_main.numel() + idx_recent.numel()
+    assert flat_u.numel() == t_rand.numel() + t_uni.numel() + u_pdf.numel()
+    w1 = wl.build_mapping_workload(syn.REPLICA_ROOM0, "cpu", n_keyframes=3, scale_hw=0.05)   # <= 20 keyframes: no recent-frame batch
+    assert w1.alloc_draws()[2][1] is None and w1.n_recent == 0
+    assert steps._mask_mode("original", 0) == 0 and steps._mask_mode("original", 1) == 1 and steps._mask_mode("no_mask", 0) == 2
+    with pytest.raises(ValueError):
+        steps._mask_mode("alpha", 0)
