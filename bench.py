@@ -122,7 +122,7 @@ def cpu_mapping_iteration(wl_cpu, field, draws):
     loss = path_ref.mapping_iteration(field, batches, wl_cpu.cfg.truncation, wl_cpu.cfg.n_stratified, wl_cpu.cfg.n_importance,
                                       lambda shape: queue.pop(0))
     loss.backward()
-    return float(loss), int(inside.sum())
+    return float(loss.detach()), int(inside.sum())
 
 
 def run_reference(args, rank, world):
