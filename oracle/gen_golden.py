@@ -37,6 +37,9 @@ CASES = {
     # keyframe bookkeeping: full (tiny) frames + every randperm draw, so the device-resident KeyframeStore can be checked
     # against the tensors optimize_mapping stacks from its list of dicts (Mapper.py:315-351)
     "map_replica_kfstore": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, n_kf=3, pixels=120, lr_factor=1, save_frames=True),
+    # Mesher.get_grid_uniform + eval_points (Mesher.py:134-195): the dense SDF query seam, coarse grids (ragged counts)
+    "mesh_replica": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, resolution=0.37),
+    "mesh_scannet": dict(yaml="configs/ScanNet/scene0000.yaml", H=23, W=31, s=0.05, resolution=0.53),
     # Renderer.render_img (Renderer.py:160-223): whole frame in ray_batch_size chunks, last chunk ragged
     "img_replica": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, ray_batch=500),
     "img_scannet": dict(yaml="configs/ScanNet/scene0000.yaml", H=23, W=31, s=0.05, ray_batch=300),
@@ -374,6 +377,37 @@ def gen_tracking(name, case):
     print(name, "rays", r["gt_depth"].numel(), "loss", loss, "gradT", out["grad_T"], "gradR", out["grad_R"])
 
 
+def gen_mesh_query(name, case):
+    from src.utils.Mesher import Mesher
+    cfg = _load_cfg(case)
+    bound, grids, dec = _build_world(cfg, 120)
+    m = object.__new__(Mesher)                                   # __init__ opens the dataset; the two methods need only these
+    m.cfg = cfg; m.bound = bound; m.points_batch_size = 700      # several ragged chunks
+    m.marching_cubes_bound = torch.from_numpy(np.array(cfg["mapping"]["marching_cubes_bound"]) * cfg["scale"])   # Mesher.py:56-57
+    # numpy >= 2 hands torch 0-d tensors back from np.linspace as Tensors (the reference predates that): give linspace the
+    # same float64 endpoints as python floats for the duration of the call -- the arithmetic is unchanged
+    orig_linspace = np.linspace
+    np.linspace = lambda a, b, n, **k: orig_linspace(float(a), float(b), int(n), **k)
+    try:
+        grid = m.get_grid_uniform(case["resolution"])
+    finally:
+        np.linspace = orig_linspace
+    pts = grid["grid_points"]
+    with torch.no_grad():
+        ret = m.eval_points(pts, ([grids[0]], [grids[1]]), dec, "cpu")
+    out = {}
+    out["bound"] = _np(bound); out["mc_bound"] = _np(m.marching_cubes_bound); out["resolution"] = np.array(case["resolution"])
+    out["log2_hash"] = np.array([cfg["grid"]["hash_size_sdf"], cfg["grid"]["hash_size_color"]])
+    out["per_level_scale"] = np.array([grids[0].spec.per_level_scale, grids[1].spec.per_level_scale])
+    out["variant"] = np.array("B" if cfg["grid"]["tcnn_network"] else "A")
+    for a, nm in zip(grid["xyz"], "xyz"):
+        out["axis_" + nm] = np.asarray(a)                        # float64 np.linspace, as the reference keeps them
+    out["points"] = _np(pts); out["sdf"] = _np(ret[:, 3]); out["rgb"] = _np(ret[:, :3])
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "points", pts.shape[0], "dims", [len(a) for a in grid["xyz"]], "outside", int((ret[:, 3] == -1).sum()))
+
+
 def gen_render_img(name, case):
     from src.utils.Renderer import Renderer
     cfg = _load_cfg(case)
@@ -422,6 +456,8 @@ def main():
             gen_mapping(name, case)
         elif name.startswith("img"):
             gen_render_img(name, case)
+        elif name.startswith("mesh"):
+            gen_mesh_query(name, case)
         else:
             gen_tracking(name, case)
 

@@ -331,6 +331,24 @@ def test_dense_sdf_query_matches_oracle():
     assert (out - ref).abs().max() < 2e-5
 
 
+@pytest.mark.parametrize("name", ["mesh_replica", "mesh_scannet"])
+def test_dense_sdf_query_matches_reference(name):
+    """a-11 against the unmodified reference: Mesher.get_grid_uniform + eval_points output (tests/golden/mesh_*.npz),
+    both decoder variants, ragged tile edges of the x-tiled kernel, slabs of uneven height."""
+    P = pkg()
+    g = load_golden(name)
+    meta, tabs, dec, beta = gpu_cases.cuda_field(g, 120, DEV)
+    axes = [T(g["axis_" + nm]).float().to(DEV) for nm in "xyz"]
+    q = P.DenseSdfQuery(meta, tabs[0], tabs[1], dec, axes)
+    ny = q.ny
+    cuts = [0, 1, ny // 2, ny]
+    out = torch.cat([q.run(a, b) for a, b in zip(cuts[:-1], cuts[1:])]).cpu()
+    ref = T(g["sdf"])
+    assert out.shape == ref.shape
+    assert torch.equal(out == -1, ref == -1)                              # strict in-bound mask identical
+    assert (out - ref).abs().max() < 2e-5
+
+
 def test_fused_adam_matches_torch_adam():
     """a-12 / f1: usl_adam_step vs torch.optim.Adam with the host code's group structure (Mapper.py:111-139; Tracker betas)."""
     P = pkg()

@@ -100,3 +100,21 @@ def test_render_img_matches_reference(name):
         assert str(t.dtype) == str(g["dtype_" + nm]), nm                          # float64 except colour (Renderer.py:205-209)
         assert tuple(t.shape) == g["ret_" + nm].shape
         assert max_rel(t, g["ret_" + nm], 1e-4) < 1e-5, nm
+
+
+@pytest.mark.parametrize("name", ["mesh_replica", "mesh_scannet"])
+def test_mesh_query_matches_reference(name):
+    """Mesher.get_grid_uniform + eval_points (Mesher.py:134-195) of the unmodified reference vs the oracle's restatement:
+    axis sample counts and coordinates, point ordering of meshgrid(indexing='xy'), strict in-bound mask, SDF values."""
+    g = load_golden(name)
+    field = golden_field(g, 120, requires_grad=False)
+    axes = path_ref.mesh_grid_axes(g["mc_bound"], resolution=float(g["resolution"]))
+    for a, nm in zip(axes, "xyz"):
+        assert torch.equal(a, T(g["axis_" + nm]).float()), nm                    # counts and fp32 coordinates bit-exact
+    pts = path_ref.mesh_grid_points(axes)
+    assert torch.equal(pts, T(g["points"]))
+    with torch.no_grad():
+        sdf = path_ref.eval_points_sdf(field, pts)
+    ref = T(g["sdf"])
+    assert torch.equal(sdf == -1, ref == -1)
+    assert (sdf - ref).abs().max() < 1e-6
