@@ -85,44 +85,14 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU path (the one place bench.py runs oracle/)
 # ------------------------------------------------------------------------------------------------
-def _oracle_field(wl, tabs, dec, beta):
-    from oracle import grid_ref, path_ref
-    cfg = wl.cfg
-    specs = [grid_ref.make_grid_spec(cfg.log2_hash_sdf, wl.per_level_scale), grid_ref.make_grid_spec(cfg.log2_hash_color, wl.per_level_scale)]
-    if cfg.decoder_variant == "B":
-        w = {"sdf_decoder.params": dec[0], "color_decoder.params": dec[1]}
-    else:
-        names = ["linears.0.weight", "linears.0.bias", "linears.1.weight", "linears.1.bias", "output_linear.weight", "output_linear.bias",
-                 "c_linears.0.weight", "c_linears.0.bias", "c_linears.1.weight", "c_linears.1.bias", "c_output_linear.weight", "c_output_linear.bias"]
-        w = dict(zip(names, dec))
-    f = path_ref.Field(specs[0], specs[1], tabs[0], tabs[1], cfg.decoder_variant, w, beta, wl.bound)
-    for t in f.parameters():
-        t.requires_grad_(True)
-    return f
-
-
-def cpu_mapping_iteration(wl_cpu, field, draws):
-    """One reference-path mapping iteration on the host CPU (fwd + backward), RNG draws shared with the GPU arm."""
-    from oracle import path_ref
-    idx_main, idx_recent, t_rand, t_uni, u_pdf = draws
-    cam_poses = wl_cpu.cam_poses.clone().requires_grad_(True)
-    c2ws = torch.cat([wl_cpu.c2ws[0:1], path_ref.cam_pose_to_matrix(cam_poses)], dim=0)
-    batches = [(c2ws, wl_cpu.depths, wl_cpu.colors, wl_cpu.dirs_cam, idx_main)]
-    if wl_cpu.n_recent:
-        K = wl_cpu.K
-        batches.append((c2ws[K - 10:], wl_cpu.depths[K - 10:], wl_cpu.colors[K - 10:], wl_cpu.dirs_cam[K - 10:], idx_recent))
-    # slot-indexed draws -> the compacted draws the reference would have made
-    outs = [path_ref.sample_mapping_rays(*b) for b in batches]
-    ro = torch.cat([o[0] for o in outs]).detach(); rd = torch.cat([o[1] for o in outs]).detach(); gd = torch.cat([o[2] for o in outs])
-    inside = path_ref.bbox_exit(ro, rd, field.bound) >= gd
-    has = inside & (gd > 0); holes = inside & ~(gd > 0)
-    queue = [t_rand[has]] + ([t_uni[holes], u_pdf[holes]] if holes.any() else [])
-    for p in field.parameters():
-        p.grad = None
-    loss = path_ref.mapping_iteration(field, batches, wl_cpu.cfg.truncation, wl_cpu.cfg.n_stratified, wl_cpu.cfg.n_importance,
-                                      lambda shape: queue.pop(0))
-    loss.backward()
-    return float(loss.detach()), int(inside.sum())
+def _fullsize():
+    """tests/fullsize_cases.py: the oracle-side helpers (oracle field over the arm's tensors, slot-indexed draws, one
+    reference-path mapping iteration) shared by the parity tests, the cpu_baseline leg and the reference arm."""
+    tdir = os.path.join(REPO, "tests")
+    if tdir not in sys.path:
+        sys.path.insert(0, tdir)
+    import fullsize_cases
+    return fullsize_cases
 
 
 def run_reference(args, rank, world):
@@ -137,7 +107,8 @@ def run_reference(args, rank, world):
     dev_build = "cuda:0" if torch.cuda.is_available() else "cpu"
     scale = 1.0 if dev_build != "cpu" else 0.25       # CPU-only container: smaller frames to build the store quickly
     wl = wlmod.build_mapping_workload(syn.CONFIGS[args.config], dev_build, scale_hw=scale)
-    wl_cpu = _to_cpu(wl)
+    F = _fullsize()
+    wl_cpu = F.to_cpu(wl)
     g = torch.Generator().manual_seed(0)
     cfg = wl.cfg
     from oracle import grid_ref
@@ -148,13 +119,26 @@ def run_reference(args, rank, world):
     else:
         lin = lambda o, i: [(torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5, (torch.rand(o, generator=g) * 2 - 1) / i ** 0.5]
         dec = lin(16, 32) + lin(16, 16) + lin(1, 16) + lin(16, 32) + lin(16, 16) + lin(3, 16)
-    field = _oracle_field(wl_cpu, tabs, dec, torch.full((1,), 10.0))
+    field = F.oracle_field(wl_cpu, tabs, dec, torch.full((1,), 10.0))
     gen = torch.Generator().manual_seed(1)
+    # the same untimed pre-fit as the GPU arm (same Adam groups, Mapper.py:111-139), so both arms are timed on a field
+    # whose masks (alpha_mask / depth_mask populations) are in the same regime
+    cam_poses = wl_cpu.cam_poses
+    opt = torch.optim.Adam([{"params": list(field.w.values()) + [field.beta], "lr": 1e-3}, {"params": [field.sdf_table], "lr": cfg.hash_lr},
+                            {"params": [field.rgb_table], "lr": cfg.hash_lr}])
+    t_pre = time.perf_counter()
+    n_prefit = 0
+    for it in range(args.prefit):
+        F.oracle_mapping_iteration(wl_cpu, field, F.cpu_draws(wl_cpu, gen))
+        opt.step()
+        n_prefit += 1
+        if time.perf_counter() - t_pre > 150.0:          # bounded: the whole reference arm must end within a few minutes
+            break
     times, n_s = [], 0
     for it in range(args.warmup + args.steps):
-        draws = _cpu_draws(wl_cpu, gen)
+        draws = F.cpu_draws(wl_cpu, gen)
         t0 = time.perf_counter()
-        _, n_inside = cpu_mapping_iteration(wl_cpu, field, draws)
+        F.oracle_mapping_iteration(wl_cpu, field, draws)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt); n_s += wl_cpu.n_rays * wl_cpu.S
@@ -162,28 +146,11 @@ def run_reference(args, rank, world):
     val = n_s / total
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / max(len(times), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
+            "data": "synthetic", "config": {"workload": WORKLOAD, "l2": "n/a (CPU)", "prefit_iterations": n_prefit},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{args.steps} full mapping iterations ({wl_cpu.n_rays} rays x {wl_cpu.S} samples each)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
-
-
-def _to_cpu(wl):
-    import copy
-    w = copy.copy(wl)
-    for k in ("bound", "c2ws", "cam_poses", "depths", "colors", "dirs_cam"):
-        setattr(w, k, getattr(wl, k).detach().cpu())
-    w.cur_frame = tuple(t.cpu() for t in wl.cur_frame)
-    return w
-
-
-def _cpu_draws(wl, gen):
-    R, S = wl.n_rays, wl.S
-    idx_main = torch.randint(wl.P, (wl.K * wl.n_main,), generator=gen)
-    idx_recent = torch.randint(wl.P, (10 * wl.n_recent,), generator=gen) if wl.n_recent else None
-    return (idx_main, idx_recent, torch.rand((R, S), generator=gen), torch.rand((R, wl.cfg.n_stratified), generator=gen),
-            torch.rand((R, wl.cfg.n_importance), generator=gen))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -247,7 +214,6 @@ def run_ours(args, rank, world, local_rank):
         opt.step()
         if it % 10 == 0 or it == args.prefit - 1:
             losses.append(float(step.loss))
-    step.fs.repack()
 
     # ---- CUDA graph of one step (RNG draws + every kernel) ----
     use_graph = not args.no_graph          # NCCL collectives are captured too when world > 1
@@ -465,15 +431,15 @@ def run_ours(args, rank, world, local_rank):
         extra.update(ri)
 
     if rank == 0:
-        cpu_base = None
+        cpu_base, parity = None, None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_base = cpu_baseline_leg(wl, tabs, dec, beta)
+            cpu_base, parity = cpu_baseline_leg(wl, step, tabs, dec, beta, cam_poses, dev)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {"workload": WORKLOAD if args.config == "replica_room0" else f"{args.config} mapping iteration: {wl.K}-frame window, {R} rays x {S} samples, joint_opt, fp32", "l2": "flushed between timed steps (256 MiB write)",
-                                                "cuda_graph": graph is not None, "rays": R, "samples_per_ray": S, "frames": wl.K},
+                                                "cuda_graph": graph is not None, "rays": R, "samples_per_ray": S, "frames": wl.K, "prefit_iterations": args.prefit},
                 "clocks": clocks, "roofline": roofline, "kernels": kern, "kernel_ms_all": kms,
-                "cpu_baseline": cpu_base,
+                "cpu_baseline": cpu_base, "parity_full_size": parity,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches_per_step * args.steps,
                 "value_l2_warm": samples / (warm_ms * 1e-3), "prefit_loss": losses[:1] + losses[-1:], **extra}
@@ -641,23 +607,29 @@ def bench_render_img(P, cfg, meta, tabs, dec, beta, dev, rank, world, dist=None,
             "render_img_gather_ms": gather_ms}
 
 
-def cpu_baseline_leg(wl, tabs, dec, beta):
-    """The oracle port timed on this box's host cores on a bounded sample: 3 full mapping iterations."""
+def cpu_baseline_leg(wl, step, tabs, dec, beta, cam_poses, dev):
+    """The oracle port of the reference path on this box's host cores, on the SAME workload, parameters and RNG draws as
+    one step of the GPU arm: first the full-size parity check (one iteration of both, compared: "parity_full_size"),
+    then a bounded timing sample of 3 more oracle iterations."""
+    F = _fullsize()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    wl_cpu = _to_cpu(wl)
-    field = _oracle_field(wl_cpu, [t.detach().cpu().clone() for t in tabs], [d.detach().cpu().clone() for d in dec], beta.detach().cpu().clone())
     gen = torch.Generator().manual_seed(1)
+    parity = F.compare_mapping(step, wl, tabs, dec, beta, F.cpu_draws(wl, gen), cam_poses, dev)
+    parity["violations"] = F.mapping_ok(parity)
+    parity["bars"] = "indices/samples bit-exact; depth/colour/loss <= 1e-4 rel; gradients <= 1e-3 rel (tables per level, norm-wise)"
+    wl_cpu = F.to_cpu(wl)
+    field = F.oracle_field(wl_cpu, tabs, dec, beta)
     times = []
     for it in range(4):
-        draws = _cpu_draws(wl_cpu, gen)
+        draws = F.cpu_draws(wl_cpu, gen)
         t0 = time.perf_counter()
-        cpu_mapping_iteration(wl_cpu, field, draws)
+        F.oracle_mapping_iteration(wl_cpu, field, draws)
         if it > 0:
             times.append(time.perf_counter() - t0)
     val = wl_cpu.n_rays * wl_cpu.S * len(times) / sum(times)
     return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"3 full mapping iterations ({wl_cpu.n_rays} rays x {wl_cpu.S} samples) after 1 warm-up, oracle port, torch CPU fp32"}
+            "sample": f"3 full mapping iterations ({wl_cpu.n_rays} rays x {wl_cpu.S} samples) after 1 warm-up, oracle port, torch CPU fp32"}, parity
 
 
 def main():

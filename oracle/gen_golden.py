@@ -22,7 +22,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 REF = "/root/reference"
-OUT = os.path.join(REPO, "tests", "golden")
+OUT = os.environ.get("USL_GOLDEN_OUT", os.path.join(REPO, "tests", "golden"))    # override: tests/test_golden_reproduce.py
 
 CASES = {
     # name: (yaml, decoder variant implied by yaml, H, W, intrinsics scale, n_keyframes, joint_opt)
@@ -65,7 +65,12 @@ class Recorder:
         rec = self
         self._orig = dict(rand=torch.rand, randint=torch.randint, randperm=torch.randperm,
                           backward=torch.Tensor.backward, step=torch.optim.Adam.step,
-                          gsa=M.get_samples_all, gs=T.get_samples)
+                          gsa=M.get_samples_all, gs=T.get_samples, searchsorted=torch.searchsorted)
+        self.searches = []    # outputs of torch.searchsorted (sample_pdf, common.py:70): the "sample indices" of the no-depth branch
+
+        def searchsorted(*a, **k):
+            t = rec._orig["searchsorted"](*a, **k); rec.searches.append(t.clone()); return t
+        torch.searchsorted = searchsorted
 
         def rand(*a, **k):
             t = rec._orig["rand"](*a, **k); rec.draws.append(("rand", t.clone())); return t
@@ -107,6 +112,7 @@ class Recorder:
         import src.Mapper as M
         import src.Tracker as T
         torch.rand, torch.randint, torch.randperm = self._orig["rand"], self._orig["randint"], self._orig["randperm"]
+        torch.searchsorted = self._orig["searchsorted"]
         torch.Tensor.backward = self._orig["backward"]
         torch.optim.Adam.step = self._orig["step"]
         M.get_samples_all = self._orig["gsa"]
@@ -157,9 +163,9 @@ def _build_world(cfg, seed_salt):
 
 
 def _frames(cfg, case, n, seed):
-    """Tiny synthetic frames (stored in the fixture, so generation need not be reproducible)."""
-    import importlib
-    syn = importlib.import_module("uni-slam_b200.synthetic")
+    """Tiny synthetic frames from the oracle's own frozen scene (oracle/scene.py): nothing in the product package
+    can change what this generator writes."""
+    from oracle import scene as syn
     cam = syn.CameraCfg(case["H"], case["W"], cfg["cam"]["fx"], cfg["cam"]["fy"], cfg["cam"]["cx"], cfg["cam"]["cy"])
     room = syn.AnalyticRoom(cfg["mapping"]["bound"])
     poses = syn.trajectory(room, 200)
@@ -175,6 +181,12 @@ def _frames(cfg, case, n, seed):
         t = torch.where(hole, torch.zeros_like(t), t)
         out.append((col.float().contiguous(), t.float().contiguous(), c2w.clone()))
     return out, dirs
+
+
+def _save(name, out):
+    """Deterministic container bytes are not needed (the reproduce test compares arrays), but keep key order stable."""
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **{k: out[k] for k in sorted(out)})
 
 
 def _np(t):
@@ -283,6 +295,7 @@ def gen_mapping(name, case):
     out["t_rand"] = _np(tail[0]); assert tail[0].shape[0] == n_valid
     if n0 > 0:
         out["t_rand_uni"] = _np(tail[1]); out["u_pdf"] = _np(tail[2])
+        out["pdf_inds"] = _np(rec.searches[-1]); assert rec.searches[-1].shape == (n0, cfg["rendering"]["n_importance"])
     out["render_rays_o"] = _np(r["rays_o"]); out["render_rays_d"] = _np(r["rays_d"]); out["render_gt_depth"] = _np(r["gt_depth"])
     for nm, o in zip(("term", "pixel_unc", "depth", "rgb", "sdf", "z_vals", "depth_unc"), r["out"]):
         out["ret_" + nm] = _np(o)
@@ -304,7 +317,7 @@ def gen_mapping(name, case):
     if m.joint_opt:
         out["cam_poses"] = _np(pvals[3][0]); out["grad_cam_poses"] = _np(grads[3][0])
     os.makedirs(OUT, exist_ok=True)
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    _save(name, out)
     print(name, "rays", r["gt_depth"].numel(), "holes", n0, "loss", float(rec.losses[-1]), "calls", len(calls))
 
 
@@ -373,7 +386,7 @@ def gen_tracking(name, case):
     out["loss"] = np.array(loss); out["pixel_unc"] = _np(punc)
     out["grad_T"] = _np(rec.steps[-1][0][0]); out["grad_R"] = _np(rec.steps[-1][1][0])
     os.makedirs(OUT, exist_ok=True)
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    _save(name, out)
     print(name, "rays", r["gt_depth"].numel(), "loss", loss, "gradT", out["grad_T"], "gradR", out["grad_R"])
 
 
@@ -404,7 +417,7 @@ def gen_mesh_query(name, case):
         out["axis_" + nm] = np.asarray(a)                        # float64 np.linspace, as the reference keeps them
     out["points"] = _np(pts); out["sdf"] = _np(ret[:, 3]); out["rgb"] = _np(ret[:, :3])
     os.makedirs(OUT, exist_ok=True)
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    _save(name, out)
     print(name, "points", pts.shape[0], "dims", [len(a) for a in grid["xyz"]], "outside", int((ret[:, 3] == -1).sum()))
 
 
@@ -441,7 +454,7 @@ def gen_render_img(name, case):
         out["ret_" + nm] = _np(o)
         out["dtype_" + nm] = np.array(str(o.dtype))
     os.makedirs(OUT, exist_ok=True)
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    _save(name, out)
     print(name, "pixels", H * W, "holes", int((dep == 0).sum()), "draws", len(rands), "mean depth", float(ret[0].mean()))
 
 

@@ -199,6 +199,8 @@ class Field:
     w: Dict[str, torch.Tensor]         # decoder weights (see init_decoder_weights)
     beta: torch.Tensor                 # Parameter[1] init 10 (decoders.py:86-89)
     bound: torch.Tensor                # (3,2)
+    tape: Optional[list] = None        # when a list: every differentiable encode appends (grid, clamped points, features) with
+                                       # features.retain_grad(), so a test can re-accumulate the table gradient in fp64
 
     def parameters(self):
         return [self.sdf_table, self.rgb_table, self.beta] + list(self.w.values())
@@ -245,6 +247,8 @@ def raw_sdf(field: Field, p_nor):
     """Decoders.get_raw_sdf (decoders.py:107-130) incl. the clamp of sample_hash_grid_feature (:101)."""
     p = torch.clamp(p_nor, min=0, max=1)
     h = grid_ref.encode(field.sdf_spec, field.sdf_table, p)
+    if field.tape is not None and h.requires_grad:
+        h.retain_grad(); field.tape.append(("sdf", p.detach(), h))
     w = field.w
     if field.variant == "B":
         return mlp_B(h, w["sdf_decoder.params"], 1, torch.tanh).squeeze()
@@ -257,6 +261,8 @@ def raw_rgb(field: Field, p_nor):
     """Decoders.get_raw_rgb (decoders.py:132-155)."""
     p = torch.clamp(p_nor, min=0, max=1)
     h = grid_ref.encode(field.rgb_spec, field.rgb_table, p)
+    if field.tape is not None and h.requires_grad:
+        h.retain_grad(); field.tape.append(("rgb", p.detach(), h))
     w = field.w
     if field.variant == "B":
         return mlp_B(h, w["color_decoder.params"], 3, torch.sigmoid)
@@ -325,10 +331,13 @@ def zvals_no_depth(field: Field, rays_o, rays_d, n_stratified, n_importance, t_r
 
 
 def render_batch_ray(field: Field, rays_d, rays_o, gt_depth, n_stratified, n_importance, truncation,
-                     t_rand=None, t_rand_uni=None, u_pdf=None):
+                     t_rand=None, t_rand_uni=None, u_pdf=None, parts: Optional[dict] = None, nodepth_field: Optional[Field] = None):
     """Renderer.render_batch_ray (Renderer.py:59-152) with RNG draws passed in:
     t_rand (R_valid,S): perturbation of depth-guided rays; t_rand_uni (R0,n_strat), u_pdf (R0,n_imp):
-    draws of the no-depth branch, in the order the reference consumes them."""
+    draws of the no-depth branch, in the order the reference consumes them.
+    parts (optional) receives 'pdf_inds' (R0,n_imp): the torch.searchsorted indices of sample_pdf (common.py:70).
+    nodepth_field (optional): field used for the no_grad z-sampling of depth-less rays -- an fp64 gradient check passes
+    the fp32 field here so that both runs integrate along identical sample positions."""
     n_rays = rays_o.shape[0]
     S = n_stratified + n_importance
     z_vals = torch.empty([n_rays, S], device=rays_o.device, dtype=torch.float32)
@@ -336,9 +345,11 @@ def render_batch_ray(field: Field, rays_d, rays_o, gt_depth, n_stratified, n_imp
     gt_mask = (gt_depth > 0).squeeze(-1)
     z_vals[gt_mask] = zvals_with_depth(gt_depth[gt_mask], n_stratified, n_importance, truncation, t_rand)
     if not gt_mask.all():
-        z0, _ = zvals_no_depth(field, rays_o[~gt_mask], rays_d[~gt_mask], n_stratified, n_importance,
-                               t_rand_uni, u_pdf)
-        z_vals[~gt_mask] = z0
+        z0, inds = zvals_no_depth(nodepth_field if nodepth_field is not None else field, rays_o[~gt_mask], rays_d[~gt_mask],
+                                  n_stratified, n_importance, t_rand_uni, u_pdf)
+        z_vals[~gt_mask] = z0.to(z_vals.dtype)
+        if parts is not None:
+            parts["pdf_inds"] = inds
     pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
     bound = field.bound
     pts = (pts - bound[:, 0]) / (bound[:, 1] - bound[:, 0])
@@ -461,7 +472,7 @@ def tracking_loss(ret, gt_depth, gt_color, truncation, lw: LossWeights = TRACK_W
 # whole iterations (sample -> prefilter -> render -> loss), RNG passed in
 # ----------------------------------------------------------------------------------------------
 def mapping_iteration(field: Field, batches, truncation, n_stratified, n_importance, draw_rand,
-                      lw: LossWeights = MAP_WEIGHTS, parts=None, mask_mode="original"):
+                      lw: LossWeights = MAP_WEIGHTS, parts=None, mask_mode="original", nodepth_field: Optional[Field] = None):
     """Mapper.optimize_mapping body, Mapper.py:379-430. batches = [(c2ws, depths, colors, rays_d_cam,
     indices), ...]: the main get_samples_all call (:379) and, when >20 keyframes, the 200 px x last-10
     frames call (:385-393), concatenated in that order. draw_rand(shape) supplies the torch.rand
@@ -477,7 +488,7 @@ def mapping_iteration(field: Field, batches, truncation, n_stratified, n_importa
     t_uni = draw_rand((n0, n_stratified)) if n0 > 0 else None
     u_pdf = draw_rand((n0, n_importance)) if n0 > 0 else None
     ret = render_batch_ray(field, rays_d, rays_o, gt_depth, n_stratified, n_importance, truncation,
-                           t_rand, t_uni, u_pdf)
+                           t_rand, t_uni, u_pdf, parts, nodepth_field)
     if parts is not None:
         parts.update(inside=inside, ret=ret, gt_depth=gt_depth, gt_color=gt_color, rays_o=rays_o, rays_d=rays_d)
     return mapping_loss(ret, gt_depth, gt_color, truncation, lw, parts, mask_mode)

@@ -61,6 +61,7 @@ def run_mapping_case(name, device="cuda:0"):
     step = P.MappingStep(meta, tabs[0], tabs[1], dec, beta, n_stratified=ns, n_importance=ni, truncation=tr,
                          max_rays=R, max_frames=K, mask_mode=str(g["mask_mode"]) if "mask_mode" in g else "original")
     cam_poses = T(g["cam_poses"]).to(device).contiguous() if joint else None
+    step.record_pdf_inds(True)
     loss = step.run(batches, t_rand, t_uni, u_pdf, cam_poses=cam_poses,
                     c2w_fixed=T(g["call0_c2ws"][0]).to(device) if joint else None, has_holes=has_holes)
     torch.cuda.synchronize()
@@ -75,6 +76,8 @@ def run_mapping_case(name, device="cuda:0"):
     has_depth = T(g["render_gt_depth"]) > 0
     res["z_depth_mismatch"] = float((zc[has_depth] != zg[has_depth]).sum())          # depth-guided rays: bit-exact
     res["z_hole_maxabs"] = float((zc[~has_depth] - zg[~has_depth]).abs().max()) if (~has_depth).any() else 0.0
+    # "sample indices bit-exact": torch.searchsorted of sample_pdf (common.py:70) as the unmodified reference produced them
+    res["pdf_inds_mismatch"] = float((step.pdf_inds[:R][ins].cpu()[~has_depth] != T(g["pdf_inds"])).sum()) if "pdf_inds" in g else 0.0
     for nm, t in (("term", step.term), ("pixel_unc", step.punc), ("depth", step.depth), ("rgb", step.rgb)):
         res[nm + "_rel"] = max_rel(t[:R][ins].cpu(), g["ret_" + nm], 1e-3)
     res["sdf_rel"] = max_rel(step.raw[:R][ins][..., 3].cpu(), g["ret_sdf"], 1e-2)

@@ -149,6 +149,30 @@ def test_network_matches_torch(variant):
             assert (out.detach().cpu().double() - ref.detach()).abs().max() < 1e-5      # O(1) activations: absolute fp32 noise
             assert rel_err(net.params.grad.cpu(), p.grad) < 1e-4
             assert rel_err(hp.grad.cpu(), hr.grad) < 1e-4
+    else:
+        # variant A (tcnn_network: False): the nn.Linear stacks of decoders.py:72-84,125-128,150-153 through the same
+        # stand-alone decoder seam (usl_mlp_fwd / usl_mlp_bwd), against torch.nn.functional in fp64
+        import torch.nn.functional as Fn
+        from importlib import import_module
+        modules = import_module("uni-slam_b200.modules")
+        for n_out, act_id, tact in ((1, P._lib.ACT_TANH, torch.tanh), (3, P._lib.ACT_SIGMOID, torch.sigmoid)):
+            lin = lambda o, i: [((torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5), ((torch.rand(o, generator=g) * 2 - 1) / i ** 0.5)]
+            ws = lin(16, 32) + lin(16, 16) + lin(n_out, 16)
+            wd = [w.to(DEV).requires_grad_(True) for w in ws]
+            hp = h.to(DEV).requires_grad_(True)
+            out = modules._MlpFn.apply(P.ops.DecoderLayout("A", n_out, act_id), hp, *wd)
+            dout = torch.randn(n, n_out, generator=g)
+            out.backward(dout.to(DEV))
+            wr = [w.double().requires_grad_(True) for w in ws]
+            hr = h.double().requires_grad_(True)
+            a = torch.relu(Fn.linear(hr, wr[0], wr[1]))
+            a = torch.relu(Fn.linear(a, wr[2], wr[3]))
+            ref = tact(Fn.linear(a, wr[4], wr[5]))
+            ref.backward(dout.double())
+            assert (out.detach().cpu().double() - ref.detach()).abs().max() < 1e-5
+            for got, want in zip(wd, wr):
+                assert rel_err(got.grad.cpu(), want.grad) < 1e-4
+            assert rel_err(hp.grad.cpu(), hr.grad) < 1e-4
 
 
 @pytest.mark.parametrize("name", ["map_replica_k1", "map_replica_k7", "map_scannet_k23", "map_replica_nomask", "map_replica_kfstore"])
@@ -158,6 +182,7 @@ def test_mapping_step_matches_reference(name):
     assert r["rays_o_mismatch"] == 0 and r["rays_d_mismatch"] == 0 and r["valid_mismatch"] == 0
     assert r["z_depth_mismatch"] == 0                                  # sample positions bit-exact
     assert r["z_hole_maxabs"] < 1e-4
+    assert r["pdf_inds_mismatch"] == 0                                 # searchsorted indices of sample_pdf bit-exact
     for k in ("term_rel", "pixel_unc_rel", "depth_rel", "rgb_rel", "loss_rel"):
         assert r[k] < 1e-4, (k, r[k])
     for k in ("dec_grad_rel", "beta_grad_rel", "table_grad_rel", "pose_grad_rel"):
@@ -232,6 +257,14 @@ def test_dropin_renderer_matches_reference(name, monkeypatch):
     for pre, e in (("grad_sdf_table", encs[0]), ("grad_rgb_table", encs[1])):
         assert rel_err(e.params.grad.cpu()[T(g[pre + "_idx"])], g[pre + "_val"]) < 1e-3
     assert rays_o.grad is not None and torch.isfinite(rays_o.grad).all() and torch.isfinite(rays_d.grad).all()
+    # ray gradients numerically: the oracle's autograd through the same rays / draws (this is what feeds the pose gradient)
+    field = golden_field(g, 0)
+    ro = T(g["render_rays_o"]).clone().requires_grad_(True); rd = T(g["render_rays_d"]).clone().requires_grad_(True)
+    qd = [T(g["t_rand"])] + ([T(g["t_rand_uni"]), T(g["u_pdf"])] if "t_rand_uni" in g else [])
+    ret_ref = path_ref.render_batch_ray(field, rd, ro, T(g["render_gt_depth"]), int(g["n_stratified"]), int(g["n_importance"]),
+                                        float(g["truncation"]), *qd)
+    path_ref.mapping_loss(ret_ref, T(g["render_gt_depth"]), gt_color[inside], float(g["truncation"])).backward()
+    assert rel_err(rays_o.grad.cpu(), ro.grad) < 1e-3 and rel_err(rays_d.grad.cpu(), rd.grad) < 1e-3
 
 
 def _dropin_modules(P, g, seed_salt):

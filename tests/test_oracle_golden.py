@@ -43,6 +43,8 @@ def test_mapping_iteration_matches_reference(name):
     assert torch.equal(parts["gt_depth"], T(g["render_gt_depth"]))
     ret = parts["ret"]
     assert torch.equal(ret[5], T(g["ret_z_vals"]))                               # z_vals bit-exact (incl. sample_pdf path)
+    if "pdf_inds" in g:                                                          # searchsorted indices of sample_pdf (common.py:70)
+        assert torch.equal(parts["pdf_inds"], T(g["pdf_inds"]))
     for nm, t in zip(("term", "pixel_unc", "depth", "rgb", "sdf"), ret[:5]):
         assert max_rel(t.detach(), g["ret_" + nm], 1e-4) < 1e-5, nm
     assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-6

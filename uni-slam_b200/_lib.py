@@ -168,6 +168,20 @@ def ptr(t):
     return t.data_ptr()
 
 
+def cptr(t, dtype, numel=None, name="tensor"):
+    """Checked device pointer for CALLER-supplied tensors: the kernels reinterpret raw memory, so a wrong dtype, a CPU
+    tensor, a strided view or a short buffer must be refused here (None -> NULL)."""
+    if t is None:
+        return None
+    if not (t.is_cuda and t.is_contiguous()):
+        raise ValueError(f"{name}: need a contiguous CUDA tensor")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: dtype {t.dtype}, expected {dtype}")
+    if numel is not None and t.numel() < numel:
+        raise ValueError(f"{name}: {t.numel()} elements, need at least {numel}")
+    return t.data_ptr()
+
+
 def f32c(t):
     """fp32, contiguous (the tcnn torch binding does the same cast)."""
     if t.dtype != torch.float32:

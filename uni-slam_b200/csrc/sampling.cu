@@ -233,12 +233,12 @@ __global__ void ray_setup_kernel(const __grid_constant__ usl_ray_setup_t A) {
             bool v = (A.mode == 2) || bbox_exit(o, rd, A.bound) >= gt;
             if (A.require_depth) v = v && (gt > 0.f);
             A.valid[r] = v ? 1 : 0;
-            live = (v && gt > 0.f) ? 1 : 0;
+            live = v ? ((gt > 0.f) ? 1 : 2) : 0;           // 2: valid ray without sensor depth (usl_zsample_nodepth fills its z row)
         }
         s_gt[rl] = gt; s_live[rl] = live;
     }
     __syncthreads();
-    const bool live = s_live[rl] != 0;
+    const bool live = s_live[rl] == 1;
     const float gt = s_gt[rl];
     const float g12 = __fmul_rn(1.2f, gt);
     const float s0 = __fsub_rn(gt, A.zs.c_surf_lo);
@@ -258,7 +258,12 @@ __global__ void ray_setup_kernel(const __grid_constant__ usl_ray_setup_t A) {
         sz[rl * S + rank] = v;
     }
     __syncthreads();
-    if (!live) return;
+    if (!live) {
+        // a depth-less valid ray must not keep a z row from an earlier iteration: poison it, so a caller that skips
+        // usl_zsample_nodepth sees NaN instead of silently stale samples
+        if (s_live[rl] == 2) A.z[r * S + k] = __int_as_float(0x7fc00000);
+        return;
+    }
     const float *zr = sz + rl * S;
     float out = zr[k];
     if (A.t_rand) {

@@ -20,7 +20,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from ._lib import call, ptr, stream
+from ._lib import call, cptr, ptr, stream
 
 
 def _mask_mode(mask_mode: str, original: int) -> int:
@@ -88,6 +88,22 @@ class _FieldState:
     def repack(self):
         self.field = self.meta.pack(self.sdf_table, self.rgb_table, self.dec)
 
+    def refresh(self, sdf_table=None, rgb_table=None, dec=None, beta=None):
+        """Re-pack the descriptor at the top of every run(): a few ctypes stores, and an integrator that rebinds a table,
+        a decoder tensor or beta (Tracker.update_params_from_mapping, Tracker.py:257-267; load_state_dict) is picked up
+        instead of leaving the kernels on stale memory."""
+        if sdf_table is not None:
+            self.sdf_table = sdf_table
+        if rgb_table is not None:
+            self.rgb_table = rgb_table
+        if dec is not None:
+            self.dec = list(dec)
+        if beta is not None:
+            self.beta = beta
+        for t, nm in ((self.sdf_table, "sdf table"), (self.rgb_table, "colour table"), (self.beta, "beta")):
+            cptr(t, torch.float32, None, nm)
+        self.field = self.meta.pack(self.sdf_table, self.rgb_table, self.dec)
+
 
 class MappingStep(_Profiled):
     """One mapping iteration (sample -> prefilter -> z-sample -> render -> loss -> backward)."""
@@ -118,6 +134,7 @@ class MappingStep(_Profiled):
         self.d_raw = torch.empty((R, S, 4), **f32)
         self.d_rays_o = torch.empty((R, 3), **f32); self.d_rays_d = torch.empty((R, 3), **f32)
         self.d_c2w = self.fs.d_c2w; self.d_pose = self.fs.d_pose
+        self.pdf_inds = None      # set record_pdf_inds(True) to keep sample_pdf's searchsorted indices (parity inspection)
         self.n_rays = 0
         self.acc_hook = None      # multi-GPU: called with self.acc between loss_fwd and loss_bwd (all-reduce of sums/counts)
         self.rgb_grads_hook = None  # multi-GPU: called with the colour-table gradient as soon as its half of field_bwd is queued
@@ -131,6 +148,10 @@ class MappingStep(_Profiled):
             self._side = torch.cuda.Stream()
         return self._side
 
+    def record_pdf_inds(self, on: bool = True):
+        """Keep the torch.searchsorted indices of the no-depth branch (common.py:70) in self.pdf_inds (R, n_importance) int64."""
+        self.pdf_inds = torch.full((self.max_rays, self.zs.n_importance), -1, device=self.z.device, dtype=torch.int64) if on else None
+
     # gradients, in the order Mapper.create_optimizer groups the parameters (Mapper.py:111-139)
     @property
     def grads(self):
@@ -143,8 +164,14 @@ class MappingStep(_Profiled):
         device as cat(c2w_fixed[None], pose_to_matrix(cam_poses)) and pose gradients land in self.d_pose."""
         st = stream()
         fs, S = self.fs, self.S
+        fs.refresh()
         joint = cam_poses is not None
         K = (cam_poses.shape[0] + 1) if joint else 0
+        max_frames = self.d_pose.shape[0]
+        if joint and K > max_frames:
+            raise ValueError(f"MappingStep: window of {K} frames, gradient buffers sized for max_frames={max_frames}")
+        if joint and (c2w_fixed is None or c2w_fixed.numel() < 12):
+            raise ValueError("MappingStep: joint_opt needs c2w_fixed (4,4), the first keyframe's fixed pose (Mapper.py:360,374)")
         fork = self.side_branches and not self.profile
         cur = torch.cuda.current_stream()
         side = self._side_stream() if fork else None
@@ -160,14 +187,36 @@ class MappingStep(_Profiled):
         rs = L.RaySetup()
         rs.mode, rs.n_batches = 0, len(batches)
         R = 0
-        for b_, (c2ws, depths, colors, dirs_cam, indices, n, frame_base) in zip(rs.batch, batches):
+        if not 1 <= len(batches) <= 2:
+            raise ValueError("MappingStep: 1 or 2 keyframe batches (Mapper.py:379-393)")
+        f32, i64 = torch.float32, torch.int64
+        for bi, (b_, (c2ws, depths, colors, dirs_cam, indices, n, frame_base)) in enumerate(zip(rs.batch, batches)):
             Kb, P = depths.shape
-            b_.c2ws = None if joint else ptr(c2ws)
-            b_.depths, b_.colors, b_.dirs_cam, b_.indices = ptr(depths), ptr(colors), ptr(dirs_cam), ptr(indices)
+            if joint and (frame_base < 0 or frame_base + Kb > K):
+                raise ValueError(f"MappingStep: batch {bi} covers frames [{frame_base}, {frame_base + Kb}) of a {K}-frame window")
+            if not joint and frame_base + Kb > max_frames:
+                raise ValueError(f"MappingStep: batch {bi} frame ids reach {frame_base + Kb}, buffers sized for max_frames={max_frames}")
+            if indices.numel() != Kb * n:
+                raise ValueError(f"MappingStep: batch {bi} has {indices.numel()} indices, expected K*n = {Kb * n}")
+            b_.c2ws = None if joint else cptr(c2ws, f32, Kb * 16, "c2ws")
+            b_.depths, b_.colors = cptr(depths, f32, Kb * P, "depths"), cptr(colors, f32, Kb * P * 3, "colors")
+            b_.dirs_cam, b_.indices = cptr(dirs_cam, f32, Kb * P * 3, "dirs_cam"), cptr(indices, i64, Kb * n, "indices")
             b_.P, b_.K, b_.n, b_.frame_base = P, Kb, n, frame_base
             R += Kb * n
         if R > self.max_rays:
             raise RuntimeError(f"MappingStep: {R} rays requested, buffers sized for max_rays={self.max_rays}")
+        if self.perturb:
+            cptr(t_rand, f32, R * S, "t_rand (R,S)")
+        if has_holes:
+            if u_pdf is None or (self.perturb and t_rand_uni is None):
+                raise ValueError("MappingStep: rays without sensor depth need the draws of the no-depth branch "
+                                 "(t_rand_uni (R,n_stratified), u_pdf (R,n_importance); Renderer.py:103-130); "
+                                 "pass has_holes=False only if every sampled pixel has depth > 0")
+            cptr(u_pdf, f32, R * self.zs.n_importance, "u_pdf (R,n_importance)")
+            if self.perturb:
+                cptr(t_rand_uni, f32, R * self.zs.n_stratified, "t_rand_uni (R,n_stratified)")
+        if joint:
+            cptr(cam_poses, f32, (K - 1) * 7, "cam_poses (K-1,7)"); cptr(c2w_fixed, f32, 12, "c2w_fixed")
         self.n_rays = R
         v = lambda t: ptr(t[:R]) if t is not None else None
         rs.cam_poses = ptr(cam_poses) if joint else None
@@ -180,7 +229,8 @@ class MappingStep(_Profiled):
         self._call("usl_ray_setup", byref(rs), st)
         if has_holes:                                      # a-6
             self._call("usl_zsample_nodepth", byref(self.zs.args), byref(fs.field), ptr(fs.beta), v(self.rays_o), v(self.rays_d), v(self.gt_depth),
-                       v(self.valid), ptr(t_rand_uni) if self.perturb else None, ptr(u_pdf), None, R, v(self.z), None, st)
+                       v(self.valid), ptr(t_rand_uni) if self.perturb else None, ptr(u_pdf), None, R, v(self.z),
+                       ptr(self.pdf_inds) if self.pdf_inds is not None else None, st)
         # ---- a-7, a-1, a-2: field query; a-8: compositing ----
         pts = L.Points()
         pts.x = None; pts.rays_o, pts.rays_d, pts.z, pts.valid = v(self.rays_o), v(self.rays_d), v(self.z), v(self.valid)
@@ -269,8 +319,14 @@ class TrackingStep(_Profiled):
         candidate pose (before the optimiser moves cam_pose)."""
         st = stream()
         fs, S, R = self.fs, self.S, self.R
+        fs.refresh()
         H, W, fx, fy, cx, cy = self.cam
         H0, H1, W0, W1 = self.win
+        f32 = torch.float32
+        cptr(cam_pose, f32, 7, "cam_pose (1,7)"); cptr(depth_img, f32, H * W, "depth_img (H,W)"); cptr(color_img, f32, H * W * 3, "color_img (H,W,3)")
+        cptr(indices, torch.int64, R, "indices (n_rays,)")
+        if self.perturb:
+            cptr(t_rand, f32, R * S, "t_rand (R,S)")
         self._small.zero_()
         rs = L.RaySetup()                                   # pose -> matrix, a-3, a-4, a-5 in one launch
         rs.mode, rs.n_batches = 1, 0
@@ -342,9 +398,17 @@ class RenderImageStep(_Profiled):
         depth, color (n,3), term, pixel_unc, depth_unc (the reference converts all but colour to float64 on return)."""
         st = stream()
         fs, S = self.fs, self.S
+        fs.refresh()
         H, W, fx, fy, cx, cy = self.cam
         pixel_end = H * W if pixel_end is None else pixel_end
         n_total = pixel_end - pixel_begin
+        if self.perturb:
+            cptr(t_rand, torch.float32, n_total * S, "t_rand (n,S)")
+        if has_holes:
+            if u_pdf is None or (self.perturb and t_rand_uni is None):
+                raise ValueError("RenderImageStep: pixels without sensor depth need t_rand_uni / u_pdf (Renderer.py:103-130); "
+                                 "pass has_holes=False only for hole-free depth images")
+            cptr(u_pdf, torch.float32, n_total * self.zs.n_importance, "u_pdf (n,n_importance)")
         out = out if out is not None else self.alloc_outputs(n_total)
         c2w = L.f32c(c2w); depth_img = L.f32c(depth_img)
         for c0 in range(0, n_total, self.chunk):
@@ -381,6 +445,7 @@ class DenseSdfQuery:
     (src/utils/Mesher.py:134-195,219-227); points are generated in-kernel from the per-axis coordinates."""
 
     def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec, axes: Sequence[torch.Tensor]):
+        self.meta = meta
         self.field = meta.pack(sdf_table, rgb_table, list(dec))
         self._keep = (sdf_table, rgb_table, list(dec))
         self.ax, self.ay, self.az = [a.contiguous().float() for a in axes]
@@ -391,6 +456,7 @@ class DenseSdfQuery:
 
     def run(self, y_begin: int, y_end: int, out: Optional[torch.Tensor] = None):
         n = self.slab_points(y_begin, y_end)
+        self.field = self.meta.pack(self._keep[0], self._keep[1], self._keep[2])    # pick up rebound tensors
         if out is None:
             out = torch.empty((n,), device=self.ax.device, dtype=torch.float32)
         call("usl_sdf_query_grid", byref(self.field), ptr(self.ax), ptr(self.ay), ptr(self.az), self.nx, self.ny, self.nz,
