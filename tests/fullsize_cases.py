@@ -122,6 +122,7 @@ def make_mapping(config_name, device, scale_hw=1.0, seed=1):
 def compare_mapping(step, wl, tabs, dec, beta, draws_cpu, cam_poses, device, fp64_tables=True):
     """Run ONE MappingStep iteration on `draws_cpu` (uploaded) and the oracle on the same draws; return error metrics."""
     wl_cpu = to_cpu(wl)
+    wl_cpu.cam_poses = cam_poses.detach().cpu().clone()          # the poses THIS iteration runs on (bench: after its pre-fit)
     R, S = wl.n_rays, wl.S
     dd = [d.to(device) if d is not None else None for d in draws_cpu]
     step.record_pdf_inds(True)
@@ -257,8 +258,8 @@ def run_tracking_fullsize(config_name, device="cuda:0", scale_hw=1.0):
     for nm, t, k in (("term", trk.term, 0), ("pixel_unc", trk.punc, 1), ("depth", trk.depth, 2), ("rgb", trk.rgb, 3)):
         res[nm + "_rel"] = max_rel(t[insd].cpu(), ret[k].detach(), 1e-3)
     res["median_mismatch"] = int(float(trk.median) != float(parts["median"]))
-    res["loss_gpu"], res["loss_ref"] = float(loss), float(loss_ref)
-    res["loss_rel"] = abs(float(loss) - float(loss_ref)) / abs(float(loss_ref))
+    res["loss_gpu"], res["loss_ref"] = float(loss), float(loss_ref.detach())
+    res["loss_rel"] = abs(float(loss) - float(loss_ref.detach())) / abs(float(loss_ref.detach()))
     res["grad_T_rel"] = rel_err(trk.d_pose[:, 4:].cpu(), cam_pose.grad[:, 4:])
     res["grad_R_rel"] = rel_err(trk.d_pose[:, :4].cpu(), cam_pose.grad[:, :4])
     return res

@@ -194,8 +194,6 @@ class MappingStep(_Profiled):
             Kb, P = depths.shape
             if joint and (frame_base < 0 or frame_base + Kb > K):
                 raise ValueError(f"MappingStep: batch {bi} covers frames [{frame_base}, {frame_base + Kb}) of a {K}-frame window")
-            if not joint and frame_base + Kb > max_frames:
-                raise ValueError(f"MappingStep: batch {bi} frame ids reach {frame_base + Kb}, buffers sized for max_frames={max_frames}")
             if indices.numel() != Kb * n:
                 raise ValueError(f"MappingStep: batch {bi} has {indices.numel()} indices, expected K*n = {Kb * n}")
             b_.c2ws = None if joint else cptr(c2ws, f32, Kb * 16, "c2ws")
