@@ -211,12 +211,17 @@ typedef struct usl_points {
                            * Outputs are written in ray-major order either way. */
     int64_t n;            /* number of points (= R*S when built from rays) */
 } usl_points_t;
-/* raw[n,4] = (r,g,b,sdf). feat (nullable): activation stash for the backward pass, 2*n*48 floats:
- * interpolated features [2][L][n][2] followed by the hidden pre-activations [2][16][n]. jac (nullable): [12,n] component-major
+/* raw[n,4] = (r,g,b,sdf). feat (nullable): activation stash for the backward pass, usl_field_stash_floats(n) = n*(2*48+3)
+ * floats: interpolated features [2][L][n][2], the hidden pre-activations [2][16][n], then the clamped coordinates [3][n]
+ * (x0 = -1 marks a filtered point: usl_field_bwd needs neither the rays nor z again).  Every row is contiguous over the
+ * points, so the backward fetches a tile of it with a handful of bulk copies.  jac (nullable): [12,n] component-major
  * d raw / d x (component o*3+d, rows o = r,g,b,sdf; clamp-gated). */
+USL_API int usl_field_stash_floats(int64_t n_points, int64_t *n_floats);
 USL_API int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac,
                   usl_stream_t stream);
-/* d_raw[n,4] -> table gradients (scatter), decoder gradients (gm[2], may be NULL to skip).
+/* d_raw[n,4] -> table gradients (scatter), decoder gradients (gm[2], may be NULL to skip).  Of `p` only n is read (the
+ * points themselves come from the stash).  Persistent kernel: stash / d_raw / raw tiles arrive by cp.async.bulk when
+ * n % 4 == 0 and raw, feat, d_raw are 16-byte aligned, by ordinary loads otherwise (same results).
  * scratch (nullable): zero-filled workspace of usl_field_bwd_scratch_floats() floats holding private copies of the
  * small coarse levels (L2 atomics serialise on small tables); it is folded into the gradient tables before return
  * and must be zero-filled again by the caller before the next call. grid_mask: 1 = sdf grid only, 2 = colour grid

@@ -97,6 +97,7 @@ _SIGS = {
     "usl_field_fwd": [POINTER(Field), POINTER(Points), _P, _P, _P, _P],
     "usl_field_bwd": [POINTER(Field), POINTER(Points), _P, _P, _P, _P, _P, POINTER(Mlp), _P, c_int, _P],
     "usl_field_bwd_scratch_floats": [POINTER(Field), POINTER(c_int64)],
+    "usl_field_stash_floats": [c_int64, POINTER(c_int64)],
     "usl_field_sdf": [POINTER(Field), POINTER(Points), _P, _P],
     "usl_composite_fwd": [_P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P],
     "usl_composite_bwd": [_P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, POINTER(Bound), _P, _P, _P, _P, _P],
@@ -149,7 +150,7 @@ LAUNCHES = 0   # number of kernel-launching C-ABI calls made so far (bench.py re
 def call(name, *args):
     global LAUNCHES
     lib = load()
-    if name not in ("usl_grid_build", "usl_field_bwd_scratch_floats"):
+    if name not in ("usl_grid_build", "usl_field_bwd_scratch_floats", "usl_field_stash_floats"):
         LAUNCHES += 1
     rc = getattr(lib, name)(*args)
     if rc != 0:

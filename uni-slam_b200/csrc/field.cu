@@ -62,7 +62,18 @@ __global__ void __launch_bounds__(256, (WITH_JAC ? USL_FWD_MINB : 4)) field_fwd_
     __syncthreads();
     float xc[3] = {0.f, 0.f, 0.f}, gate[3] = {0.f, 0.f, 0.f};
     int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // thread's point; i below = its slot in the ray-major outputs
-    const bool active = (ti < A.p.n) && load_point(A.p, A.f, ti, xc, gate, &ti);
+    const bool in_range = ti < A.p.n;
+    const bool active = in_range && load_point(A.p, A.f, ti, xc, gate, &ti);
+    if (SAVE_FEAT && in_range) {
+        // clamped coordinates for the backward pass, component-major [3][n]; x0 = -1 marks a filtered point (the only part
+        // of the stash written for those), so the backward never has to re-read rays / z / valid
+        float *xs = A.feat + (int64_t)2 * (USL_IN + USL_HID) * A.p.n + ti;
+        if (gi == 0) {
+            __stcs(xs, active ? xc[0] : -1.0f);
+            __stcs(xs + A.p.n, xc[1]);
+            __stcs(xs + 2 * A.p.n, xc[2]);
+        }
+    }
     if (!__any_sync(0xffffffffu, active)) return;           // warps made only of filtered rays cost nothing
     const int64_t i = ti;
     const usl_grid_t &g = A.f.grid[gi];
@@ -157,97 +168,54 @@ __global__ void __launch_bounds__(256) sdf_query_grid_kernel(const __grid_consta
     }
 }
 
-// ---- backward ---------------------------------------------------------------------------------
-#define BWD_THREADS 128
-#define BWD_WARPS (BWD_THREADS / 32)
-#define TILE_STRIDE 52   // floats per point row: 16B-aligned rows, conflict-free 128-bit stores
-
-struct FieldBwdArgs {
-    usl_field_t f;
-    usl_points_t p;
-    const float *raw;     // [n,4] saved outputs
-    const float *feat;    // [2][L][n][2]
-    const float *d_raw;   // [n,4]
-    float *grad_table[2];
-    usl_mlp_t gm[2];
+// ---- stand-alone decoder backward (tinycudann.Network / nn.Linear stacks: usl_mlp_bwd) -------------------
+// feat is h[n,32] (row-major), raw / d_raw are [n,n_out]; gradients wrt the weights (block-reduced, one atomic per
+// element per CTA) and wrt the input features dh[n,32].  The fused path has its own kernel (field_bwd.cu).
+#define MB_THREADS 128
+#define MB_WARPS (MB_THREADS / 32)
+#define MB_STRIDE 52   // floats per point row: 16B-aligned rows, conflict-free 128-bit stores
+struct MlpBwdArgs {
+    usl_mlp_t m, gm;
     int has_gm;
-    int gi_base;                  // first grid handled by this launch (gridDim.y grids from here): lets the caller run
-                                  // the colour and sdf halves as separate launches and overlap a collective with the second
-    float *scratch;               // replicated copies of the small coarse levels (see plan_replicas), or NULL
-    uint32_t rep_count[2][USL_MAX_LEVELS];   // replicas per level (power of two, 1 = scatter straight into the table)
-    uint32_t rep_offset[2][USL_MAX_LEVELS];  // first entry of the level's replica block inside scratch
-    int dbg;              // development switches (USL_DEBUG_BWD): 1 = skip scatter, 2 = skip weight-gradient tiles
-    int stagger_mod, stagger_ns, stagger_first;   // de-phasing of the first round of CTAs (see usl_field_bwd; USL_STAGGER=mod,ns,first overrides)
-    float *dh;            // stand-alone decoder mode: [n,32] gradient wrt the input features (nullable)
+    const float *h, *out, *dout;
+    int64_t n;
+    float *dh;
 };
 
-// STANDALONE: tinycudann.Network seam -- feat is h[n,32] (row-major), raw/d_raw are [n,n_out], no scatter.
-template <int NH, bool STANDALONE>
-#ifndef USL_BWD_MINB
-#define USL_BWD_MINB 5
-#endif
-__global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field_bwd_kernel(const __grid_constant__ FieldBwdArgs A) {
+template <int NH>
+__global__ void __launch_bounds__(MB_THREADS) mlp_bwd_kernel(const __grid_constant__ MlpBwdArgs A) {
     __shared__ MlpSmem sm;
-    __shared__ __align__(16) float tiles[BWD_WARPS][32][TILE_STRIDE];
-    const int gi = A.gi_base + blockIdx.y;
-    const usl_mlp_t &m = A.f.mlp[gi];
+    __shared__ __align__(16) float tiles[MB_WARPS][32][MB_STRIDE];
+    const usl_mlp_t &m = A.m;
     stage_mlp(m, sm);
     __syncthreads();
-    if (!STANDALONE && A.stagger_mod > 1 && (int)blockIdx.x < A.stagger_first) {
-        const unsigned d = ((blockIdx.x + blockIdx.y) % A.stagger_mod) * (unsigned)A.stagger_ns;
-        if (d) __nanosleep(d);
-    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float(*tile)[TILE_STRIDE] = tiles[warp];
-    const usl_grid_t &g = A.f.grid[gi];
-    const int L = g.n_levels;
-    const int64_t n = A.p.n;
+    float(*tile)[MB_STRIDE] = tiles[warp];
+    const int64_t n = A.n;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-
-    float xc[3] = {0.f, 0.f, 0.f}, gate[3];
-    bool active = (i < n);
-    if (!STANDALONE) active = active && load_point(A.p, A.f, i, xc, gate);
-
-    // ---- hidden pre-activations: stashed by the forward pass (fused) or recomputed from h (stand-alone) ----
+    const bool active = i < n;
+    const float2 *fin = reinterpret_cast<const float2 *>(A.h) + (active ? i : 0) * (USL_IN / 2);
     float h1[USL_HID];
-    const float2 *fin = STANDALONE ? reinterpret_cast<const float2 *>(A.feat) + (active ? i : 0) * (USL_IN / 2)
-                                   : reinterpret_cast<const float2 *>(A.feat) + ((int64_t)gi * L) * n + (active ? i : 0);
-    const int64_t fstride = STANDALONE ? 1 : n;
-    if (STANDALONE) {
 #pragma unroll
-        for (int j = 0; j < USL_HID; ++j) h1[j] = sm.b1[j];
+    for (int j = 0; j < USL_HID; ++j) h1[j] = sm.b1[j];
 #pragma unroll
-        for (int l = 0; l < USL_IN / 2; ++l) {
-            float2 v = make_float2(0.f, 0.f);
-            if (active) v = __ldg(fin + (int64_t)l * fstride);
-            const float4 *wa = reinterpret_cast<const float4 *>(sm.w1t[2 * l]);
-            const float4 *wb = reinterpret_cast<const float4 *>(sm.w1t[2 * l + 1]);
+    for (int l = 0; l < USL_IN / 2; ++l) {
+        float2 v = make_float2(0.f, 0.f);
+        if (active) v = __ldg(fin + l);
+        const float4 *wa = reinterpret_cast<const float4 *>(sm.w1t[2 * l]);
+        const float4 *wb = reinterpret_cast<const float4 *>(sm.w1t[2 * l + 1]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 a = wa[q], b = wb[q];
-                h1[q * 4 + 0] = fmaf(b.x, v.y, fmaf(a.x, v.x, h1[q * 4 + 0]));
-                h1[q * 4 + 1] = fmaf(b.y, v.y, fmaf(a.y, v.x, h1[q * 4 + 1]));
-                h1[q * 4 + 2] = fmaf(b.z, v.y, fmaf(a.z, v.x, h1[q * 4 + 2]));
-                h1[q * 4 + 3] = fmaf(b.w, v.y, fmaf(a.w, v.x, h1[q * 4 + 3]));
-            }
+        for (int q = 0; q < 4; ++q) {
+            const float4 a = wa[q], b = wb[q];
+            h1[q * 4 + 0] = fmaf(b.x, v.y, fmaf(a.x, v.x, h1[q * 4 + 0]));
+            h1[q * 4 + 1] = fmaf(b.y, v.y, fmaf(a.y, v.x, h1[q * 4 + 1]));
+            h1[q * 4 + 2] = fmaf(b.z, v.y, fmaf(a.z, v.x, h1[q * 4 + 2]));
+            h1[q * 4 + 3] = fmaf(b.w, v.y, fmaf(a.w, v.x, h1[q * 4 + 3]));
         }
-    } else {
-        const float *hin = A.feat + (int64_t)2 * USL_IN * n + ((int64_t)gi * USL_HID) * n + (active ? i : 0);
-#pragma unroll
-        for (int j = 0; j < USL_HID; ++j) h1[j] = active ? __ldcs(hin + (int64_t)j * n) : 0.f;
     }
-    // output-side gradient
     float du[4] = {0.f, 0.f, 0.f, 0.f};
-    if (active) {
-        if (STANDALONE) {
-            for (int o = 0; o < m.n_out; ++o) du[o] = A.d_raw[i * m.n_out + o] * act_bwd(m.out_act, A.raw[i * m.n_out + o]);
-        } else if (gi == 0) {
-            du[0] = A.d_raw[i * 4 + 3] * act_bwd(m.out_act, A.raw[i * 4 + 3]);
-        } else {
-#pragma unroll
-            for (int o = 0; o < 3; ++o) du[o] = A.d_raw[i * 4 + o] * act_bwd(m.out_act, A.raw[i * 4 + o]);
-        }
-    }
+    if (active)
+        for (int o = 0; o < m.n_out; ++o) du[o] = A.dout[i * m.n_out + o] * act_bwd(m.out_act, A.out[i * m.n_out + o]);
     float dh1[USL_HID];
     float a2[USL_HID], dh2[USL_HID];
     if (NH == 2) {
@@ -278,23 +246,21 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field
             dh1[j] = (h1[j] > 0.f) ? d : 0.f;
         }
     }
-
-    // ---- decoder weight gradients: warp-private tile, each lane owns a patch of every matrix ----
+    // weight gradients: warp-private tile, each lane owns a patch of every matrix
     float acc1[16], acc2[8], acco[2], accb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int q = 0; q < 16; ++q) acc1[q] = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc2[q] = 0.f;
     acco[0] = acco[1] = 0.f;
-    if (A.has_gm && !(A.dbg & 2)) {
+    if (A.has_gm) {
         float4 *row = reinterpret_cast<float4 *>(tile[lane]);
-        // phase 1: [0:16] dh1, [16:48] f
 #pragma unroll
         for (int q = 0; q < 4; ++q) row[q] = make_float4(dh1[4 * q], dh1[4 * q + 1], dh1[4 * q + 2], dh1[4 * q + 3]);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {     // features go global -> shared without living in registers
+        for (int q = 0; q < 8; ++q) {
             float2 u0 = make_float2(0.f, 0.f), u1 = u0;
-            if (active) { u0 = __ldcs(fin + (int64_t)(2 * q) * fstride); u1 = __ldcs(fin + (int64_t)(2 * q + 1) * fstride); }   // read-once stream
+            if (active) { u0 = __ldg(fin + 2 * q); u1 = __ldg(fin + 2 * q + 1); }
             row[4 + q] = make_float4(u0.x, u0.y, u1.x, u1.y);
         }
         __syncwarp();
@@ -353,40 +319,10 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field
         }
         __syncwarp();
     }
-
-    // ---- hash-table gradient scatter: d f_l = W1[:, 2l:2l+2]^T dh1, then 8 vector atomics ----
-    // (issuing the scatter BEFORE the weight-gradient tiles was measured slower: 329 vs 316 us)
-    // the table scatter is warp-collective (lane pairing): the condition must be warp-uniform, inactive lanes are predicated
-    if (!(A.dbg & 1) && (STANDALONE ? (active && A.dh != nullptr) : (A.grad_table[gi] != nullptr))) {
-        float2 *gt = STANDALONE ? nullptr : reinterpret_cast<float2 *>(A.grad_table[gi]);
-        // warps walk the levels in rotated order so the atomics in flight at any instant spread over all levels'
-        // sectors instead of hammering the few sectors of one coarse level (L2 same-sector RMW turnaround)
-        const uint32_t wid = blockIdx.x * BWD_WARPS + warp;
-        const int rot = (int)((wid * 5u) % (unsigned)L);
-        // lane pair (2k, 2k+1) = 2 points x 2 x-sides: first the even lane's point (A), then the odd lane's (B); every lane
-        // serves x-side (lane & 1) of both.  Only coordinates (once) and the two level gradients (per level) are exchanged.
-        // (stand-alone decoder mode never reaches the scatter and its branch is per lane: no warp collectives there)
-        const uint32_t side = lane & 1;
-        float xA[3] = {0.f, 0.f, 0.f}, xB[3] = {0.f, 0.f, 0.f};
-        bool actA = false, actB = false;
-        if (!STANDALONE) {
+    // gradient wrt the input features: d f_l = W1[:, 2l:2l+2]^T dh1
+    if (active && A.dh != nullptr) {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const float px = __shfl_xor_sync(0xffffffffu, xc[d], 1);
-                xA[d] = side ? px : xc[d];
-                xB[d] = side ? xc[d] : px;
-            }
-            const bool pact = __shfl_xor_sync(0xffffffffu, active ? 1 : 0, 1) != 0;
-            actA = side ? pact : active; actB = side ? active : pact;
-        }
-#ifndef USL_BWD_UNROLL
-#define USL_BWD_UNROLL 2
-#endif
-        constexpr int kScatterUnroll = USL_BWD_UNROLL;   // two levels' address chains in flight per thread
-#pragma unroll kScatterUnroll
-        for (int it = 0; it < L; ++it) {
-            int l = it + rot;
-            if (l >= L) l -= L;
+        for (int l = 0; l < USL_IN / 2; ++l) {
             float dfx = 0.f, dfy = 0.f;
             const float4 *wa = reinterpret_cast<const float4 *>(sm.w1t[2 * l]);
             const float4 *wb = reinterpret_cast<const float4 *>(sm.w1t[2 * l + 1]);
@@ -398,27 +334,13 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field
                 dfy = fmaf(b.x, dh1[4 * q], dfy); dfy = fmaf(b.y, dh1[4 * q + 1], dfy);
                 dfy = fmaf(b.z, dh1[4 * q + 2], dfy); dfy = fmaf(b.w, dh1[4 * q + 3], dfy);
             }
-            if (STANDALONE) {
-                reinterpret_cast<float2 *>(A.dh)[i * (USL_IN / 2) + l] = make_float2(dfx, dfy);
-                continue;
-            }
-            const usl_level_t &lv = g.levels[l];
-            const uint32_t R = A.scratch ? A.rep_count[gi][l] : 1u;
-            float2 *tab = (R > 1u) ? reinterpret_cast<float2 *>(A.scratch) + A.rep_offset[gi][l] + (size_t)(wid & (R - 1u)) * lv.size
-                                   : gt + lv.offset;
-            {
-                const float pfx = __shfl_xor_sync(0xffffffffu, dfx, 1), pfy = __shfl_xor_sync(0xffffffffu, dfy, 1);
-                scatter_level_side(tab, lv, xA[0], xA[1], xA[2], side, side ? pfx : dfx, side ? pfy : dfy, actA);
-                scatter_level_side(tab, lv, xB[0], xB[1], xB[2], side, side ? dfx : pfx, side ? dfy : pfy, actB);
-            }
+            reinterpret_cast<float2 *>(A.dh)[i * (USL_IN / 2) + l] = make_float2(dfx, dfy);
         }
     }
-
-    // ---- block reduction of the decoder gradients, one atomic per element per CTA ----
     if (A.has_gm) {
         __syncthreads();
-        float *red = &tiles[0][0][0];               // reuse: [BWD_WARPS][32][32] floats needed (<= tile storage)
-        float *mine = red + (warp * 32 + lane) * 32;
+        float *red = &tiles[0][0][0];               // reuse: [MB_WARPS][32][33] floats needed (<= tile storage)
+        float *mine = red + (warp * 32 + lane) * 33;
 #pragma unroll
         for (int q = 0; q < 16; ++q) mine[q] = acc1[q];
 #pragma unroll
@@ -426,12 +348,12 @@ __global__ void __launch_bounds__(BWD_THREADS, NH == 1 ? USL_BWD_MINB : 3) field
         mine[24] = acco[0]; mine[25] = acco[1];
         mine[26] = accb[0]; mine[27] = accb[1]; mine[28] = accb[2];
         __syncthreads();
-        const usl_mlp_t &gm = A.gm[gi];
+        const usl_mlp_t &gm = A.gm;
         for (int e = threadIdx.x; e < 32 * 29; e += blockDim.x) {
             const int ln = e / 29, q = e % 29;
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < BWD_WARPS; ++w) s += red[(w * 32 + ln) * 32 + q];
+            for (int w = 0; w < MB_WARPS; ++w) s += red[(w * 32 + ln) * 33 + q];
             if (q < 16) {                                   // dW1[j][k0+q]
                 const int j = ln >> 1, k = (ln & 1) * 16 + q;
                 if (gm.w1) atomicAdd(gm.w1 + j * USL_IN + k, s);
@@ -493,52 +415,6 @@ __global__ void __launch_bounds__(256) mlp_fwd_kernel(usl_mlp_t m, const float *
     for (int o = 0; o < m.n_out; ++o) out[i * m.n_out + o] = act_fwd(m.out_act, u[o]);
 }
 
-// ---- replicated coarse levels ---------------------------------------------------------------------
-// L2 atomic throughput collapses on small tables (tools/microbench_footprint.py: 79 G ops/s on 32 KB, 121 G on
-// 175 KB, 220 G from 4 MB up) because operations on one 32-byte sector serialise.  The coarse dense levels are
-// exactly such tables and every sample hits them, so the scatter writes them into R private copies (picked by warp
-// id, ~1 MB per level in total) and a tiny second kernel folds the copies into the gradient table.
-static void plan_replicas(const usl_field_t *f, uint32_t cnt[2][USL_MAX_LEVELS], uint32_t off[2][USL_MAX_LEVELS], int64_t *total_entries) {
-    int64_t o = 0;
-    static const uint64_t max_bytes = getenv("USL_REP_MAXBYTES") ? strtoull(getenv("USL_REP_MAXBYTES"), nullptr, 10) : 512u * 1024u;
-    static const uint64_t target = getenv("USL_REP_TARGET") ? strtoull(getenv("USL_REP_TARGET"), nullptr, 10) : 1024u * 1024u;
-    for (int gi = 0; gi < 2; ++gi)
-        for (int l = 0; l < USL_MAX_LEVELS; ++l) {
-            cnt[gi][l] = 1; off[gi][l] = 0;
-            if (l >= f->grid[gi].n_levels) continue;
-            const uint64_t bytes = (uint64_t)f->grid[gi].levels[l].size * 8u;
-            if (bytes >= max_bytes) continue;
-            uint32_t r = 1;
-            while (r < 32u && (uint64_t)r * bytes < target) r *= 2;
-            cnt[gi][l] = r; off[gi][l] = (uint32_t)o;
-            o += (int64_t)r * f->grid[gi].levels[l].size;
-        }
-    *total_entries = o;
-}
-
-__global__ void __launch_bounds__(256) fold_replicas_kernel(const __grid_constant__ FieldBwdArgs A) {
-    const int gi = A.gi_base + blockIdx.y;
-    float2 *gt = reinterpret_cast<float2 *>(A.grad_table[gi]);
-    if (!gt) return;
-    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    const usl_grid_t &g = A.f.grid[gi];
-    for (int l = 0; l < g.n_levels; ++l) {
-        const uint32_t R = A.rep_count[gi][l], sz = g.levels[l].size;
-        if (R <= 1u) continue;
-        if (e < sz) {
-            const float2 *src = reinterpret_cast<const float2 *>(A.scratch) + A.rep_offset[gi][l] + e;
-            float sx = 0.f, sy = 0.f;
-            for (uint32_t r = 0; r < R; ++r) { const float2 v = src[(size_t)r * sz]; sx += v.x; sy += v.y; }
-            float2 *dst = gt + g.levels[l].offset + e;
-            float2 cur = *dst;
-            cur.x += sx; cur.y += sy;
-            *dst = cur;
-            return;
-        }
-        e -= sz;
-    }
-}
-
 static int check_field(const usl_field_t *f, const usl_points_t *p) {
     if (!f || !p) { set_error("null field/points"); return 1; }
     for (int gi = 0; gi < 2; ++gi) {
@@ -572,9 +448,11 @@ int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float
     // USL_TCGEN05=1: tangent contraction of the Jacobian path on the tcgen05 tensor cores (field_tc.cu). Parity-tested
     // and profiled, but not the default: the kernel is bound by L1 sector lookups of the gather,
     // so moving 57 % of the FMA-pipe work to the tensor pipe does not shorten it (196 us vs 182 us measured).
-    const char *tc_env = getenv("USL_TCGEN05");
     if (p->sample_major && !p->x && (p->n % p->S)) { set_error("usl_field_fwd: sample_major needs n == R * S"); return 1; }
-    if (jac && tc_env && tc_env[0] == '1' && !p->sample_major) return usl_field_fwd_tc_launch(f, p, raw, feat, jac, s);
+#ifdef USL_DEV
+    { const char *tc_env = getenv("USL_TCGEN05");      // development builds only: select the tensor-core variant by environment
+      if (jac && tc_env && tc_env[0] == '1' && !p->sample_major) return usl_field_fwd_tc_launch(f, p, raw, feat, jac, s); }
+#endif
     if (jac && feat) field_fwd_kernel<true, true><<<grid, 256, 0, s>>>(A);
     else if (jac) field_fwd_kernel<true, false><<<grid, 256, 0, s>>>(A);
     else if (feat) field_fwd_kernel<false, true><<<grid, 256, 0, s>>>(A);
@@ -592,82 +470,19 @@ int usl_field_sdf(const usl_field_t *f, const usl_points_t *p, float *sdf, usl_s
     return check_launch("usl_field_sdf");
 }
 
-int usl_field_bwd_scratch_floats(const usl_field_t *f, int64_t *n_floats) {
-    if (!f || !n_floats) { set_error("usl_field_bwd_scratch_floats: null argument"); return 1; }
-    uint32_t cnt[2][USL_MAX_LEVELS], off[2][USL_MAX_LEVELS];
-    int64_t entries = 0;
-    plan_replicas(f, cnt, off, &entries);
-    *n_floats = entries * 2;
-    return 0;
-}
-
-int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw, const float *feat,
-                  const float *d_raw, float *grad_table_sdf, float *grad_table_rgb, const usl_mlp_t *gm,
-                  float *scratch, int grid_mask, usl_stream_t stream) {
-    if (check_field(f, p)) return 1;
-    if (p->n <= 0) return 0;
-    if (!feat || !raw || !d_raw) { set_error("usl_field_bwd: raw, feat and d_raw are required"); return 1; }
-    if (p->sample_major) { set_error("usl_field_bwd: sample_major point order is only supported by usl_field_fwd"); return 1; }
-    if (f->mlp[0].n_hidden != f->mlp[1].n_hidden) { set_error("usl_field_bwd: decoders must share n_hidden"); return 1; }
-    FieldBwdArgs A;
-    A.f = *f; A.p = *p; A.raw = raw; A.feat = feat; A.d_raw = d_raw;
-    A.grad_table[0] = grad_table_sdf; A.grad_table[1] = grad_table_rgb;
-    A.has_gm = gm ? 1 : 0;
-    A.dh = nullptr;
-    { const char *e = getenv("USL_DEBUG_BWD"); A.dbg = e ? atoi(e) : 0; }
-    // Every CTA runs a compute phase (stash loads, decoder backward) and then a scatter phase (atomics).  The CTAs of the
-    // first round start together, so the whole GPU alternates between the two phases and the L2 atomic units idle during
-    // the first; delaying the first-round CTAs by 0..3 x 8 us interleaves the phases (measured: 275 -> 268 us).
-    static int n_sm = 0;
-    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-    A.stagger_mod = 4; A.stagger_ns = 8000; A.stagger_first = 0;    // stagger_first is set below, once the grid is known
-    bool stagger_env = false;
-    { const char *e = getenv("USL_STAGGER"); if (e) { stagger_env = true; sscanf(e, "%d,%d,%d", &A.stagger_mod, &A.stagger_ns, &A.stagger_first); } }
-    if (gm) { A.gm[0] = gm[0]; A.gm[1] = gm[1]; }
-    if (grid_mask < 1 || grid_mask > 3) { set_error("usl_field_bwd: grid_mask must be 1 (sdf), 2 (colour) or 3 (both)"); return 1; }
-    A.gi_base = (grid_mask == 2) ? 1 : 0;
-    const unsigned ny = (grid_mask == 3) ? 2u : 1u;
-    dim3 grid((unsigned)((p->n + BWD_THREADS - 1) / BWD_THREADS), ny);
-    if (!stagger_env) {
-        const int resident = n_sm * ((f->mlp[0].n_hidden == 1) ? USL_BWD_MINB : 3);
-        A.stagger_first = ((int64_t)grid.x * ny > 2 * (int64_t)resident) ? resident / (int)ny : 0;   // only worth it over several rounds
-    }
-    cudaStream_t s = (cudaStream_t)stream;
-    int64_t rep_entries = 0;
-    plan_replicas(f, A.rep_count, A.rep_offset, &rep_entries);
-    A.scratch = (rep_entries > 0) ? scratch : nullptr;
-    if (f->mlp[0].n_hidden == 2) field_bwd_kernel<2, false><<<grid, BWD_THREADS, 0, s>>>(A);
-    else field_bwd_kernel<1, false><<<grid, BWD_THREADS, 0, s>>>(A);
-    if (check_launch("usl_field_bwd")) return 1;
-    if (A.scratch) {
-        uint32_t per_grid = 0;
-        for (int gi = A.gi_base; gi < A.gi_base + (int)ny; ++gi) {
-            uint32_t t = 0;
-            for (int l = 0; l < f->grid[gi].n_levels; ++l) if (A.rep_count[gi][l] > 1) t += f->grid[gi].levels[l].size;
-            if (t > per_grid) per_grid = t;
-        }
-        if (per_grid) fold_replicas_kernel<<<dim3((per_grid + 255) / 256, ny), 256, 0, s>>>(A);
-        return check_launch("usl_field_bwd (fold)");
-    }
-    return 0;
-}
-
 int usl_mlp_bwd(const usl_mlp_t *m, const usl_mlp_t *gm, const float *h, const float *out, const float *dout,
                 int64_t n, float *dh, usl_stream_t stream) {
     if (!m || m->n_hidden < 1 || m->n_hidden > 2 || m->n_out < 1 || m->n_out > 3) { set_error("usl_mlp_bwd: unsupported decoder shape"); return 1; }
     if (n <= 0) return 0;
-    FieldBwdArgs A;
+    MlpBwdArgs A;
     memset(&A, 0, sizeof(A));
-    A.f.mlp[0] = *m;
-    A.f.grid[0].n_levels = USL_IN / USL_FEATS;
-    A.p.n = n;
-    A.raw = out; A.feat = h; A.d_raw = dout; A.dh = dh; A.scratch = nullptr; A.gi_base = 0;
-    A.has_gm = gm ? 1 : 0;
-    if (gm) A.gm[0] = *gm;
-    dim3 grid((unsigned)((n + BWD_THREADS - 1) / BWD_THREADS), 1);
+    A.m = *m; A.has_gm = gm ? 1 : 0;
+    if (gm) A.gm = *gm;
+    A.h = h; A.out = out; A.dout = dout; A.n = n; A.dh = dh;
+    const unsigned grid = (unsigned)((n + MB_THREADS - 1) / MB_THREADS);
     cudaStream_t s = (cudaStream_t)stream;
-    if (m->n_hidden == 2) field_bwd_kernel<2, true><<<grid, BWD_THREADS, 0, s>>>(A);
-    else field_bwd_kernel<1, true><<<grid, BWD_THREADS, 0, s>>>(A);
+    if (m->n_hidden == 2) mlp_bwd_kernel<2><<<grid, MB_THREADS, 0, s>>>(A);
+    else mlp_bwd_kernel<1><<<grid, MB_THREADS, 0, s>>>(A);
     return check_launch("usl_mlp_bwd");
 }
 
@@ -686,7 +501,10 @@ int usl_sdf_query_grid(const usl_field_t *f, const float *ax, const float *ay, c
     QueryArgs A;
     A.f = *f; A.ax = ax; A.ay = ay; A.az = az; A.nx = nx; A.ny = ny; A.nz = nz; A.y_begin = y_begin; A.y_end = y_end; A.out = out;
     int64_t blocks = (int64_t)(y_end - y_begin) * ((nx + QT_X - 1) / QT_X) * ((nz + QT_Z - 1) / QT_Z);   // one tile per CTA and pass
-    const int64_t cap = 148 * 64;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t cap = (int64_t)(n_sm > 0 ? n_sm : 1) * 64;     // persistent tile loop: a few waves of resident CTAs per SM
     if (blocks > cap) blocks = cap;
     sdf_query_grid_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A);
     return check_launch("usl_sdf_query_grid");

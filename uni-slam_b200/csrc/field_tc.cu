@@ -8,6 +8,7 @@
 // operand tile and one thread issues 3 tcgen05.mma; tcgen05.ld (32x32b) returns row t to thread t at the end.
 // The VALUE path (h = W1 f + b1) stays in fp32 on the CUDA cores: outputs keep the 1e-4 parity bar, while the
 // tangents only feed gradients (1e-3 bar) where TF32 operands (round-to-nearest, ~2.4e-4 per operand) are ample.
+#include "usl_async.cuh"
 #include "usl_field.cuh"
 
 namespace usl {
@@ -26,8 +27,6 @@ struct TcSmem {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE: core matrices of 8 rows x 16 bytes;
 // LBO = byte distance between the two core matrices along K, SBO = between 8-row groups along M/N.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -41,20 +40,6 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    }
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
@@ -158,6 +143,12 @@ __global__ void __launch_bounds__(TC_CTA_THREADS, USL_TC_MINB) field_fwd_tc_kern
     const usl_grid_t &g = A.f.grid[gi];
     const float2 *table = reinterpret_cast<const float2 *>(A.f.table[gi]);
     float2 *fo = SAVE_FEAT ? reinterpret_cast<float2 *>(A.feat) + ((int64_t)gi * g.n_levels) * n + i : nullptr;
+    if (SAVE_FEAT && i < n && gi == 0) {                   // clamped coordinates for the backward pass (x0 = -1: filtered point)
+        float *xs = A.feat + (int64_t)2 * (USL_IN + USL_HID) * n + i;
+        __stcs(xs, active ? xc[0] : -1.0f);
+        __stcs(xs + n, xc[1]);
+        __stcs(xs + 2 * n, xc[2]);
+    }
 
     float h[USL_HID];
 #pragma unroll

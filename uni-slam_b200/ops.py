@@ -16,6 +16,14 @@ from ._lib import call, f32c, ptr, stream
 N_LEVELS, N_FEATS, C_DIM, HIDDEN = 16, 2, 32, 16
 
 
+def stash_floats(n_points: int) -> int:
+    """Size of the activation stash usl_field_fwd writes for usl_field_bwd (features, hidden pre-activations, clamped coordinates)."""
+    from ctypes import c_int64
+    out = c_int64(0)
+    call("usl_field_stash_floats", int(n_points), byref(out))
+    return int(out.value)
+
+
 # ------------------------------------------------------------------------------------------------
 # B1: tinycudann.Encoding
 # ------------------------------------------------------------------------------------------------
@@ -172,7 +180,7 @@ class _FieldPointsFn(torch.autograd.Function):
         need_p = any(ctx.needs_input_grad[2:])
         need_x = ctx.needs_input_grad[1]
         raw = torch.empty((n, 4), device=x.device, dtype=torch.float32)
-        feat = torch.empty((2 * (C_DIM + HIDDEN) * n,), device=x.device, dtype=torch.float32) if need_p else None
+        feat = torch.empty((stash_floats(n),), device=x.device, dtype=torch.float32) if need_p else None
         jac = torch.empty((12, n), device=x.device, dtype=torch.float32) if need_x else None
         f = meta.pack(sdf_table, rgb_table, dec)
         pts = _points_from_x(x)
@@ -227,7 +235,7 @@ class _RenderFn(torch.autograd.Function):
         need_rays = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         need_p = any(ctx.needs_input_grad[5:])
         raw = torch.empty((R, S, 4), device=dev, dtype=torch.float32)
-        feat = torch.empty((2 * (C_DIM + HIDDEN) * R * S,), device=dev, dtype=torch.float32) if need_p else None
+        feat = torch.empty((stash_floats(R * S),), device=dev, dtype=torch.float32) if need_p else None
         jac = torch.empty((12, R * S), device=dev, dtype=torch.float32) if need_rays else None
         f = meta.pack(sdf_table, rgb_table, dec)
         pts = _points_from_rays(rays_o, rays_d, z_vals)

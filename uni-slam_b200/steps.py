@@ -126,7 +126,7 @@ class MappingStep(_Profiled):
         self.dirs = torch.empty((R, 3), **f32); self.frame_id = torch.empty((R,), device=dev, dtype=torch.int32)
         self.valid = torch.empty((R,), device=dev, dtype=torch.uint8); self.mask = torch.empty((R,), device=dev, dtype=torch.uint8)
         self.z = torch.zeros((R, S), **f32)
-        self.raw = torch.empty((R, S, 4), **f32); self.feat = torch.empty((2 * (ops.C_DIM + ops.HIDDEN) * R * S,), **f32)   # stash: features + hidden pre-activations
+        self.raw = torch.empty((R, S, 4), **f32); self.feat = torch.empty((ops.stash_floats(R * S),), **f32)   # stash: features + hidden pre-activations + clamped coordinates
         self.jac = torch.empty((12 * R * S,), **f32)        # component-major [12][n] of THIS call's n = R*S
         self.term = torch.empty((R,), **f32); self.punc = torch.empty((R,), **f32); self.depth = torch.empty((R,), **f32)
         self.rgb = torch.empty((R, 3), **f32); self.dunc = torch.empty((R,), **f32)
