@@ -223,8 +223,9 @@ USL_API int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *ra
  * points themselves come from the stash).  Persistent kernel: stash / d_raw / raw tiles arrive by cp.async.bulk when
  * n % 4 == 0 and raw, feat, d_raw are 16-byte aligned, by ordinary loads otherwise (same results).
  * scratch (nullable): zero-filled workspace of usl_field_bwd_scratch_floats() floats holding private copies of the
- * small coarse levels (L2 atomics serialise on small tables); it is folded into the gradient tables before return
- * and must be zero-filled again by the caller before the next call. grid_mask: 1 = sdf grid only, 2 = colour grid
+ * small coarse levels (L2 atomics serialise on small tables) and the work-queue counters of the persistent kernel; it
+ * is folded into the gradient tables before return and must be zero-filled again by the caller before the next call
+ * (NULL: no replicas, static tile assignment). grid_mask: 1 = sdf grid only, 2 = colour grid
  * only, 3 = both (one launch); the halves are independent, so a caller can all-reduce one while the other runs. */
 USL_API int usl_field_bwd_scratch_floats(const usl_field_t *f, int64_t *n_floats);
 USL_API int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw, const float *feat,

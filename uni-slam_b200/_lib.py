@@ -12,7 +12,8 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_float, c_int
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libunislam_b200.so")
+# USL_LIB_PATH: development only -- load a side-by-side build variant (csrc/build.sh with USL_LIB_NAME) for A/B measurements
+LIB_PATH = os.environ.get("USL_LIB_PATH") or os.path.join(_HERE, "lib", "libunislam_b200.so")
 
 MAX_LEVELS = 16
 ACT_NONE, ACT_TANH, ACT_SIGMOID = 0, 1, 2

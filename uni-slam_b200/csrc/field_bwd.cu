@@ -5,9 +5,12 @@
 // Shape of the kernel (sm_100a):
 //   * persistent CTAs (resident CTAs per SM x SM count, half of them per grid), each looping over tiles of 128 points;
 //   * the activation stash of tile i+1 (features, hidden pre-activations, clamped coordinates) and d_raw / raw arrive by
-//     cp.async.bulk (TMA unit, SASS UBLKCP) into a double-buffered shared-memory stage, completion on an mbarrier, while
-//     tile i runs its decoder backward and issues its fire-and-forget atomics: the global-memory latency of the stash,
-//     which stalled the previous one-shot kernel for a third of its time, is off the critical path and off the LSU pipe;
+//     cp.async.bulk (TMA unit, SASS UBLKCP) into a shared-memory stage, completion on an mbarrier, while tile i issues
+//     its fire-and-forget atomics: a tile is consumed into registers by the decoder backward at the START of its
+//     iteration, so ONE stage suffices -- it is refilled as soon as the compute phase ends and has the whole (longer)
+//     scatter phase to land.  The global-memory latency of the stash, which stalled the previous one-shot kernel for a
+//     third of its time, is off the critical path and off the LSU pipe, and the small footprint (44 KB) keeps 5 CTAs
+//     per SM resident;
 //   * scatter by lane quads: lanes 4k..4k+3 serve the four points 4k..4k+3 together; lane bit 0 = x side, bit 1 = y side,
 //     each lane owns the two z corners of its (x,y) side for all four points.  The x-neighbour corners therefore sit in
 //     adjacent lanes of one RED instruction (adjacent entries of one 32-byte sector: merged by the L2), and consecutive
@@ -16,6 +19,7 @@
 //   * small coarse levels go to replicated private copies (L2 same-sector atomics serialise), folded afterwards.
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "usl_async.cuh"
@@ -23,11 +27,19 @@
 
 namespace usl {
 
-#define B2_THREADS 128
+#ifndef B2_THREADS
+#define B2_THREADS 128           // = points per tile (thread = point)
+#endif
 #define B2_WARPS (B2_THREADS / 32)
-#define B2_TILE 128
+#define B2_TILE B2_THREADS
 #define B2_FROW (B2_TILE + 2)    // float2 per feature row: +16 bytes so that neighbouring levels start 4 banks apart
 #define B2_HROW (B2_TILE + 4)    // floats per hidden row: likewise
+#ifndef B2_MINB
+#define B2_MINB 4                // resident CTAs per SM the register allocation aims for (one hidden layer)
+#endif
+#ifndef B2_MINB2
+#define B2_MINB2 3               // ... with two hidden layers (more live registers, 26 KB of exchange tiles)
+#endif
 
 struct FieldBwd2Args {
     usl_field_t f;
@@ -42,6 +54,8 @@ struct FieldBwd2Args {
     float *scratch;
     uint32_t rep_count[2][USL_MAX_LEVELS];
     uint32_t rep_offset[2][USL_MAX_LEVELS];
+    unsigned int *counter;  // device work-queue counter (zero at launch; lives in the caller-zeroed scratch), or NULL: static stride
+    int dbg;              // development builds (-DUSL_DEV) only: ablation switches, see usl_field_bwd
     int bulk_ok;          // 1: every tile row is 16-byte aligned and sized -> cp.async.bulk; 0: plain cooperative loads
 };
 
@@ -55,22 +69,25 @@ struct alignas(128) B2Stage {
 };
 
 struct B2Smem {
-    B2Stage st[2];
+    B2Stage st;
     MlpSmem mlp;
-    alignas(8) uint64_t full[2];
-    alignas(16) float tile[1];         // [B2_WARPS][32][TROW] follows (TROW = 20 floats for one hidden layer, 52 for two)
+    float2 w1p[USL_IN / 2][USL_HID];   // first decoder layer as (feature 0, feature 1) weight pairs per level: [level][unit]
+    alignas(8) uint64_t full;
+    int64_t next[2];                   // next work item of this CTA (written by thread 0, read after the CTA barrier; slot = iteration parity)
+    alignas(16) float tile[1];         // [B2_WARPS][32][TROW] follows: per-point rows of decoder-gradient operands; TROW = 22 / 54
+                                       // floats (one / two hidden layers): 64-bit accesses of 16 consecutive rows hit 32 distinct banks
 };
-template <int NH> struct B2Row { static constexpr int value = (NH == 2) ? 52 : 20; };
+template <int NH> struct B2Row { static constexpr int value = (NH == 2) ? 54 : 22; };
 template <int NH> constexpr size_t b2_smem_bytes() { return offsetof(B2Smem, tile) + sizeof(float) * B2_WARPS * 32 * B2Row<NH>::value; }
 
 __device__ __forceinline__ uint32_t stage_bytes(int cnt) { return (uint32_t)cnt * (16u * 8u + 16u * 4u + 16u + 16u + 12u); }
 
-// Issue the loads of tile `t` of grid `gi` into stage `s` (one thread).
-__device__ __forceinline__ void issue_tile(const FieldBwd2Args &A, B2Smem &S, int s, int gi, int64_t t, uint64_t pol) {
+// Issue the loads of tile `t` of grid `gi` into the stage (one thread).
+__device__ __forceinline__ void issue_tile(const FieldBwd2Args &A, B2Smem &S, int gi, int64_t t, uint64_t pol) {
     const int64_t n = A.n, i0 = t * B2_TILE;
     const int cnt = (int)min((int64_t)B2_TILE, n - i0);
-    B2Stage &st = S.st[s];
-    uint64_t *bar = &S.full[s];
+    B2Stage &st = S.st;
+    uint64_t *bar = &S.full;
     mbar_arrive_expect_tx(bar, stage_bytes(cnt));
     const float2 *feat = reinterpret_cast<const float2 *>(A.feat) + ((int64_t)gi * (USL_IN / 2)) * n + i0;
 #pragma unroll 1
@@ -87,9 +104,9 @@ __device__ __forceinline__ void issue_tile(const FieldBwd2Args &A, B2Smem &S, in
 
 // Fallback when the rows are not 16-byte aligned / sized (n % 4 != 0 or odd base pointers): every thread fetches its own
 // column with ordinary loads.  Same stage layout, so everything downstream is shared.
-__device__ __forceinline__ void load_tile_sync(const FieldBwd2Args &A, B2Smem &S, int s, int gi, int64_t t) {
+__device__ __forceinline__ void load_tile_sync(const FieldBwd2Args &A, B2Smem &S, int gi, int64_t t) {
     const int64_t n = A.n, i = t * B2_TILE + threadIdx.x;
-    B2Stage &st = S.st[s];
+    B2Stage &st = S.st;
     const int p = threadIdx.x;
     if (i < n) {
         const float2 *feat = reinterpret_cast<const float2 *>(A.feat) + ((int64_t)gi * (USL_IN / 2)) * n + i;
@@ -106,88 +123,168 @@ __device__ __forceinline__ void load_tile_sync(const FieldBwd2Args &A, B2Smem &S
     }
 }
 
-// The two z corners on (x side sx, y side sy) of the cell of point (x0,x1,x2) at level lv: entry indices and weights.
-// Index and weight arithmetic is corner_indices<true> / corner_weights restricted to one (x,y) side: bit-identical.
-struct SideCorners {
-    uint32_t g0, g1, g2;      // cell (for the same-cell test)
+// ---- packed FP32 (Blackwell FFMA2: two IEEE fp32 FMAs per instruction, each rounded like fmaf) ----
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ void ffma2(f32x2_t &acc, f32x2_t a, f32x2_t b) {       // acc = a * b + acc (element-wise)
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+// Per-level constants hoisted out of the point loop.  Branch-free over dense / hashed levels: both index forms are two
+// multiplies and combines (add or xor) followed by a wrap (conditional subtract or mask), so the kind only selects.
+struct LevelConst {
+    float scale;
+    uint32_t size, mask, my, mz;   // multipliers of g1 / g2: (res, res^2) dense, (PRIME_Y, PRIME_Z) hashed
+    bool hashed;
+};
+__device__ __forceinline__ LevelConst level_const(const usl_level_t &lv) {
+    LevelConst c;
+    c.scale = lv.scale; c.size = lv.size; c.mask = lv.size - 1u; c.hashed = lv.hashed != 0;
+    c.my = c.hashed ? USL_PRIME_Y : lv.res;
+    c.mz = c.hashed ? USL_PRIME_Z : lv.res * lv.res;
+    return c;
+}
+// The two z corners on (x side sx, y side sy) of the cell of point (x0,x1,x2): entry indices, weights, packed cell id.
+// Index and weight arithmetic is corner_indices<true> / corner_weights restricted to one (x,y) side: bit-identical values.
+struct SideCorners2 {
+    uint32_t cell;
     uint32_t i0, i1;          // entries of corner z = g2 and z = g2 + 1
     float w0, w1;
 };
-__device__ __forceinline__ SideCorners side_corners(const usl_level_t &lv, float x0, float x1, float x2, uint32_t sx, uint32_t sy) {
-    SideCorners c;
+__device__ __forceinline__ SideCorners2 side_corners2(const LevelConst &lc, float x0, float x1, float x2, uint32_t sx, uint32_t sy) {
+    SideCorners2 c;
+    uint32_t g0, g1, g2;
     float f0, f1, f2;
-    pos_fract(lv.scale, x0, c.g0, f0);
-    pos_fract(lv.scale, x1, c.g1, f1);
-    pos_fract(lv.scale, x2, c.g2, f2);
-    if (lv.hashed) {
-        const uint32_t mask = lv.size - 1u;
-        const uint32_t h = (c.g0 + sx) ^ ((c.g1 + sy) * USL_PRIME_Y);
-        const uint32_t hz = c.g2 * USL_PRIME_Z;
-        c.i0 = (h ^ hz) & mask;
-        c.i1 = (h ^ (hz + USL_PRIME_Z)) & mask;
-    } else {
-        const uint32_t res = lv.res, res2 = lv.res * lv.res;
-        uint32_t b = (c.g0 + sx) + (c.g1 + sy) * res + c.g2 * res2;
-        uint32_t b1 = b + res2;
-        if (b >= lv.size) b -= lv.size;               // clamped coordinates: one conditional subtract is the exact modulo
-        if (b1 >= lv.size) b1 -= lv.size;
-        c.i0 = b; c.i1 = b1;
-    }
-    float w = sx ? f0 : 1.0f - f0;                    // tcnn's multiplication order: ((f0) * f1) * f2
+    pos_fract(lc.scale, x0, g0, f0);
+    pos_fract(lc.scale, x1, g1, f1);
+    pos_fract(lc.scale, x2, g2, f2);
+    c.cell = g0 | (g1 << 10) | (g2 << 20);
+    const uint32_t a = g0 + sx, b = (g1 + sy) * lc.my, z0 = g2 * lc.mz, z1 = z0 + lc.mz;
+    const uint32_t ab_x = a ^ b, ab_s = a + b;
+    uint32_t d0 = ab_s + z0, d1 = ab_s + z1;
+    d0 = (d0 >= lc.size) ? d0 - lc.size : d0;
+    d1 = (d1 >= lc.size) ? d1 - lc.size : d1;
+    c.i0 = lc.hashed ? ((ab_x ^ z0) & lc.mask) : d0;
+    c.i1 = lc.hashed ? ((ab_x ^ z1) & lc.mask) : d1;
+    float w = sx ? f0 : 1.0f - f0;                      // tcnn's multiplication order: ((f0) * f1) * f2
     w *= sy ? f1 : 1.0f - f1;
     c.w0 = w * (1.0f - f2);
     c.w1 = w * f2;
     return c;
 }
 
+// Sum the per-lane decoder-gradient accumulators over the CTA's warps and add them to the gradient tensors: one atomic
+// per element per call.  Runs when a CTA leaves a grid (at most twice per CTA); the warp tiles serve as scratch.
 template <int NH>
-__global__ void __launch_bounds__(B2_THREADS, 3) field_bwd2_kernel(const __grid_constant__ FieldBwd2Args A) {
+__device__ __forceinline__ void flush_decoder_grads(const usl_mlp_t &gm, const usl_mlp_t &m, float *scr, float acc[29]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int c0 = 0; c0 < 29; c0 += 8) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (c0 + q < 29) scr[(warp * 32 + lane) * 9 + q] = acc[c0 + q];
+        __syncthreads();
+        for (int e = tid; e < 32 * 8; e += B2_THREADS) {
+            const int ln = e >> 3, q = c0 + (e & 7);
+            if (q >= 29) continue;
+            float sacc = 0.f;
+#pragma unroll
+            for (int w = 0; w < B2_WARPS; ++w) sacc += scr[(w * 32 + ln) * 9 + (e & 7)];
+            if (q < 16) {                                   // dW1[j][k]: lane ln = (j, level parity), q = 2*(level >> 1) + feature
+                const int j = ln >> 1, kk = 4 * (q >> 1) + 2 * (ln & 1) + (q & 1);
+                if (gm.w1) atomicAdd(gm.w1 + j * USL_IN + kk, sacc);
+            } else if (q < 24) {                            // dW2[r2][2*(q-16) + parity]
+                if (NH == 2 && gm.w2) atomicAdd(gm.w2 + (ln >> 1) * USL_HID + 2 * (q - 16) + (ln & 1), sacc);
+            } else if (q < 26) {                            // dWo[2*(ln>>4) + (q-24)][ln & 15]
+                const int o = (ln >> 4) * 2 + (q - 24), ii = ln & 15;
+                if (o < m.n_out && gm.wo) atomicAdd(gm.wo + o * USL_HID + ii, sacc);
+            } else if (q == 26) {
+                if (ln < 16 && gm.b1) atomicAdd(gm.b1 + ln, sacc);
+            } else if (q == 27) {
+                if (NH == 2 && ln < 16 && gm.b2) atomicAdd(gm.b2 + ln, sacc);
+            } else {
+                if (ln < m.n_out && gm.bo) atomicAdd(gm.bo + ln, sacc);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int NH>
+__global__ void __launch_bounds__(B2_THREADS, (NH == 2) ? B2_MINB2 : B2_MINB) field_bwd2_kernel(const __grid_constant__ FieldBwd2Args A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     B2Smem &S = *reinterpret_cast<B2Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gi = A.gi_base + (A.n_grids == 2 ? (int)(blockIdx.x & 1u) : 0);
-    const int cta = (A.n_grids == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int n_cta = (A.n_grids == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const usl_mlp_t &m = A.f.mlp[gi];
-    const usl_grid_t &g = A.f.grid[gi];
-    const int L = g.n_levels;
     const int64_t n = A.n;
     const int64_t n_tiles = (n + B2_TILE - 1) / B2_TILE;
-
-    stage_mlp(m, S.mlp);
-    if (tid == 0) { mbar_init(&S.full[0], 1); mbar_init(&S.full[1], 1); mbar_fence_init(); }
-    __syncthreads();
+    const int64_t n_items = n_tiles * A.n_grids;            // work items, grid-major: item w = (grid w / n_tiles, tile w % n_tiles)
     const MlpSmem &sm = S.mlp;
     const uint64_t pol = l2_policy_evict_first();
-    if (A.bulk_ok && tid == 0 && cta < n_tiles) issue_tile(A, S, 0, gi, cta, pol);
+    if (tid == 0) { mbar_init(&S.full, 1); mbar_fence_init(); }
+    __syncthreads();
 
-    float acc1[16], acc2[8], acco[2], accb[3] = {0.f, 0.f, 0.f};      // decoder weight gradients, kept across tiles
+    // decoder weight gradients kept in registers across tiles: a1[q] = dW1 patch (packed pairs), rest[0:8] dW2 patch,
+    // rest[8:10] dWo patch, rest[10:13] bias sums
+    f32x2_t a1[8];
+    float rest[13];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) acc1[q] = 0.f;
+    for (int q = 0; q < 8; ++q) a1[q] = 0ull;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc2[q] = 0.f;
-    acco[0] = acco[1] = 0.f;
+    for (int q = 0; q < 13; ++q) rest[q] = 0.f;
 
     constexpr int TROW = B2Row<NH>::value;
     float(*tile)[TROW] = reinterpret_cast<float(*)[TROW]>(S.tile + (size_t)warp * 32 * TROW);
-    float2 *gt = reinterpret_cast<float2 *>(A.grad_table[gi]);
-    const uint32_t wid = (uint32_t)cta * B2_WARPS + warp;
-    const uint32_t sx = lane & 1u, sy = (lane >> 1) & 1u;
-    const int qbase = lane & ~3;
+    const uint32_t wid = (uint32_t)blockIdx.x * B2_WARPS + warp;
 
+    auto flush = [&](int gi_) {
+        float acc[29];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const float2 v = unpack2(a1[q]); acc[2 * q] = v.x; acc[2 * q + 1] = v.y; a1[q] = 0ull; }
+#pragma unroll
+        for (int q = 0; q < 13; ++q) { acc[16 + q] = rest[q]; rest[q] = 0.f; }
+        flush_decoder_grads<NH>(A.gm[gi_], A.f.mlp[gi_], S.tile, acc);
+    };
+
+    int64_t w = blockIdx.x;                                 // first item: static; later ones from the device-side queue
+    if (A.bulk_ok && tid == 0 && w < n_items) issue_tile(A, S, A.gi_base + (int)(w / n_tiles), w % n_tiles, pol);
+    int cur = -1;                                           // grid whose decoder is staged / whose gradients the accumulators hold
     int k = 0;
 #pragma unroll 1
-    for (int64_t t = cta; t < n_tiles; t += n_cta, ++k) {
-        const int s = k & 1;
-        if (A.bulk_ok) {
-            // stage s^1 was last read in iteration k-1, before its __syncthreads: free to refill
-            if (tid == 0 && t + n_cta < n_tiles) issue_tile(A, S, s ^ 1, gi, t + n_cta, pol);
-            mbar_wait(&S.full[s], (uint32_t)(k >> 1) & 1u);
-        } else {
-            load_tile_sync(A, S, s, gi, t);
+    for (; w < n_items; ++k) {
+        const int gi = A.gi_base + (int)(w / n_tiles);
+        const int64_t t = w % n_tiles;
+        if (gi != cur) {                                    // at most one switch per CTA (items are grid-major)
+            if (cur >= 0 && A.has_gm) flush(cur);
+            __syncthreads();
+            stage_mlp(A.f.mlp[gi], S.mlp);
+            for (int e = tid; e < (USL_IN / 2) * USL_HID; e += B2_THREADS) {        // W1 as (feature 0, feature 1) pairs per level
+                const int l = e / USL_HID, j = e % USL_HID;
+                S.w1p[l][j] = make_float2(A.f.mlp[gi].w1[j * USL_IN + 2 * l], A.f.mlp[gi].w1[j * USL_IN + 2 * l + 1]);
+            }
+            cur = gi;
             __syncthreads();
         }
-        const B2Stage &st = S.st[s];
+        // next item: one atomic on the work counter (dynamic load balance: items differ in cost and CTAs share SMs)
+        if (tid == 0) S.next[k & 1] = A.counter ? (int64_t)atomicAdd(A.counter, 1u) + gridDim.x : w + gridDim.x;
+        const usl_mlp_t &m = A.f.mlp[gi];
+        const usl_grid_t &g = A.f.grid[gi];
+        const int L = g.n_levels;
+        if (A.bulk_ok) mbar_wait(&S.full, (uint32_t)k & 1u);
+        else {
+            load_tile_sync(A, S, gi, t);
+            __syncthreads();
+        }
+        const B2Stage &st = S.st;
         const int cnt = (int)min((int64_t)B2_TILE, n - t * B2_TILE);
         const int p = tid;
         float xc[3];
@@ -243,38 +340,40 @@ __global__ void __launch_bounds__(B2_THREADS, 3) field_bwd2_kernel(const __grid_
         // ---- decoder weight gradients: each lane owns a patch of every matrix, summed over the warp's 32 points ----
         // tile row (per point): [0:16] dh1, [16:20] du, [20:36] dh2, [36:52] a2 (the last two only when NH == 2);
         // features and first-layer activations are read straight from the stage.
+#ifdef USL_DEV
+        if (A.has_gm && !(A.dbg & 4)) {
+#else
         if (A.has_gm) {
-            float4 *row = reinterpret_cast<float4 *>(tile[lane]);
+#endif
+            float2 *row = reinterpret_cast<float2 *>(tile[lane]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) row[q] = make_float4(dh1[4 * q], dh1[4 * q + 1], dh1[4 * q + 2], dh1[4 * q + 3]);
-            row[4] = make_float4(du[0], du[1], du[2], du[3]);
+            for (int q = 0; q < 8; ++q) row[q] = make_float2(dh1[2 * q], dh1[2 * q + 1]);
+            row[8] = make_float2(du[0], du[1]); row[9] = make_float2(du[2], du[3]);
             if (NH == 2) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    row[5 + q] = make_float4(dh2[4 * q], dh2[4 * q + 1], dh2[4 * q + 2], dh2[4 * q + 3]);
-                    row[9 + q] = make_float4(a2[4 * q], a2[4 * q + 1], a2[4 * q + 2], a2[4 * q + 3]);
+                for (int q = 0; q < 8; ++q) {
+                    row[10 + q] = make_float2(dh2[2 * q], dh2[2 * q + 1]);
+                    row[18 + q] = make_float2(a2[2 * q], a2[2 * q + 1]);
                 }
             }
             __syncwarp();
             const int pw = warp * 32;                      // first point of this warp inside the tile
             const uint32_t amask = __ballot_sync(0xffffffffu, active);   // inactive points have no stash: never touch their rows
-            {   // dW1[j][k] and db1: lane = (j, parity of the level); acc1[2q+f] <-> input k = 2*(2q + (lane&1)) + f
+            {   // dW1[j][k] and db1: lane = (j, parity of the level); a1[q] <-> inputs k = 2*(2q + (lane&1)) + {0,1}
                 const int j = lane >> 1, lp = lane & 1;
 #pragma unroll 2
                 for (int pp = 0; pp < 32; ++pp) {
                     if (!((amask >> pp) & 1u)) continue;
                     const float d = tile[pp][j];
+                    const f32x2_t dd = pack2(d, d);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float2 v = st.F[2 * q + lp][pw + pp];
-                        acc1[2 * q] = fmaf(d, v.x, acc1[2 * q]);
-                        acc1[2 * q + 1] = fmaf(d, v.y, acc1[2 * q + 1]);
-                    }
-                    if (lane < 16) accb[0] += tile[pp][lane];
+                    for (int q = 0; q < 8; ++q)
+                        ffma2(a1[q], dd, *reinterpret_cast<const f32x2_t *>(&st.F[2 * q + lp][pw + pp]));
+                    if (lane < 16) rest[10] += tile[pp][lane];
                 }
             }
-            {   // dW2 (NH == 2): lane = (r2, parity of j), acc2[q] <-> dW2[r2][2q + (lane&1)];
-                // dWo: lane = (i = lane & 15, output pair lane >> 4), acco[e] <-> dWo[2*(lane>>4)+e][i];  db2, dbo
+            {   // dW2 (NH == 2): lane = (r2, parity of j), rest[q] <-> dW2[r2][2q + (lane&1)];
+                // dWo: lane = (i = lane & 15, output pair lane >> 4), rest[8+e] <-> dWo[2*(lane>>4)+e][i];  db2, dbo
                 const int r2 = lane >> 1, lp = lane & 1;
                 const int ii = lane & 15, o0 = (lane >> 4) * 2;
 #pragma unroll 2
@@ -284,23 +383,42 @@ __global__ void __launch_bounds__(B2_THREADS, 3) field_bwd2_kernel(const __grid_
                     if (NH == 2) {
                         const float d = tile[pp][20 + r2];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) acc2[q] = fmaf(d, fmaxf(st.H1[2 * q + lp][pw + pp], 0.f), acc2[q]);
-                        if (lane < 16) accb[1] += tile[pp][20 + lane];
+                        for (int q = 0; q < 8; ++q) rest[q] = fmaf(d, fmaxf(st.H1[2 * q + lp][pw + pp], 0.f), rest[q]);
+                        if (lane < 16) rest[11] += tile[pp][20 + lane];
                         al = tile[pp][36 + ii];
                     } else {
                         al = fmaxf(st.H1[ii][pw + pp], 0.f);
                     }
                     const float2 duo = *reinterpret_cast<const float2 *>(&tile[pp][16 + o0]);
-                    acco[0] = fmaf(duo.x, al, acco[0]);
-                    acco[1] = fmaf(duo.y, al, acco[1]);
-                    if (lane < 4) accb[2] += tile[pp][16 + lane];
+                    rest[8] = fmaf(duo.x, al, rest[8]);
+                    rest[9] = fmaf(duo.y, al, rest[9]);
+                    if (lane < 4) rest[12] += tile[pp][16 + lane];
                 }
             }
         }
-        __syncthreads();          // every warp is done with stage s: the producer may refill it two iterations from now
 
-        // ---- hash-table gradient scatter by lane quads ----
+        __syncthreads();          // every warp has consumed the stage into registers: refill it while this tile scatters
+        const int64_t w_next = S.next[k & 1];
+        if (A.bulk_ok && tid == 0 && w_next < n_items) issue_tile(A, S, A.gi_base + (int)(w_next / n_tiles), w_next % n_tiles, pol);
+
+        // ---- hash-table gradient scatter by lane QUADS: lanes 4k..4k+3 serve the four points 4k..4k+3 together; lane bit 0
+        //      = x side, bit 1 = y side, each lane owns the two z corners of its (x,y) side for all four points.  The two x
+        //      neighbours of a corner therefore sit in adjacent lanes of one RED instruction (adjacent entries, one 32-byte
+        //      sector in 75 % of the cases: merged by the memory system into one atomic sector operation), and consecutive
+        //      samples of a ray that fall into the SAME cell (coarse levels: 30-70 % of neighbouring samples) are summed in
+        //      registers and flushed as one atomic where the run ends: 39.0 M -> 31.6 M atomic sector operations.
+        //      The loop is bound by the rate at which the LSU drains the REDs (~30 cycles per warp instruction), so the index
+        //      arithmetic and the level-gradient contraction d f_l = W1[:, 2l:2l+2]^T dh1 stay INSIDE it, where they are hidden;
+        //      variants that moved work out of the loop (level gradients precomputed into shared memory; lane pairs with half
+        //      the index arithmetic for the fine levels) measured slower (231-242 us vs 220 us).
+        float2 *gt = reinterpret_cast<float2 *>(A.grad_table[gi]);
+#ifdef USL_DEV
+        if (gt != nullptr && !(A.dbg & 2)) {
+#else
         if (gt != nullptr) {
+#endif
+            const int qbase = lane & ~3;
+            const uint32_t sx = lane & 1u, sy = (lane >> 1) & 1u;
             float qx[4][3];
             bool qact[4];
 #pragma unroll
@@ -309,94 +427,54 @@ __global__ void __launch_bounds__(B2_THREADS, 3) field_bwd2_kernel(const __grid_
                 for (int d = 0; d < 3; ++d) qx[q][d] = __shfl_sync(0xffffffffu, xc[d], qbase + q);
                 qact[q] = __shfl_sync(0xffffffffu, active ? 1 : 0, qbase + q) != 0;
             }
+            f32x2_t dhp[USL_HID];
+#pragma unroll
+            for (int j = 0; j < USL_HID; ++j) dhp[j] = pack2(dh1[j], dh1[j]);
             const int rot = (int)((wid * 5u + (uint32_t)k * 3u) % (unsigned)L);    // de-correlate the levels in flight across warps
 #pragma unroll 1
             for (int it = 0; it < L; ++it) {
                 int l = it + rot;
                 if (l >= L) l -= L;
-                float dfx = 0.f, dfy = 0.f;
-                const float4 *wa = reinterpret_cast<const float4 *>(sm.w1t[2 * l]);
-                const float4 *wb = reinterpret_cast<const float4 *>(sm.w1t[2 * l + 1]);
+                f32x2_t dfp = 0ull;                                                   // (d f_l.x, d f_l.y) of this lane's own point
+                const f32x2_t *wp = reinterpret_cast<const f32x2_t *>(S.w1p[l]);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 a = wa[q], b = wb[q];
-                    dfx = fmaf(a.x, dh1[4 * q], dfx); dfx = fmaf(a.y, dh1[4 * q + 1], dfx);
-                    dfx = fmaf(a.z, dh1[4 * q + 2], dfx); dfx = fmaf(a.w, dh1[4 * q + 3], dfx);
-                    dfy = fmaf(b.x, dh1[4 * q], dfy); dfy = fmaf(b.y, dh1[4 * q + 1], dfy);
-                    dfy = fmaf(b.z, dh1[4 * q + 2], dfy); dfy = fmaf(b.w, dh1[4 * q + 3], dfy);
-                }
+                for (int j = 0; j < USL_HID; ++j) ffma2(dfp, wp[j], dhp[j]);
+                const float2 df = unpack2(dfp);
                 const usl_level_t &lv = g.levels[l];
+                const LevelConst lc = level_const(lv);
                 const uint32_t R = A.scratch ? A.rep_count[gi][l] : 1u;
                 float2 *tab = (R > 1u) ? reinterpret_cast<float2 *>(A.scratch) + A.rep_offset[gi][l] + (size_t)(wid & (R - 1u)) * lv.size
                                        : gt + lv.offset;
-                // walk the quad's four points; a run of points in the same cell is summed and flushed once
-                uint32_t pi0 = 0, pi1 = 0, pg0 = 0, pg1 = 0, pg2 = 0;
-                float2 v0 = make_float2(0.f, 0.f), v1 = v0;
-                bool pending = false;
+                SideCorners2 c[4];
+                float2 u0[4], u1[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float fx = __shfl_sync(0xffffffffu, dfx, qbase + q), fy = __shfl_sync(0xffffffffu, dfy, qbase + q);
-                    const SideCorners c = side_corners(lv, qx[q][0], qx[q][1], qx[q][2], sx, sy);
-                    const bool same = pending && qact[q] && (c.g0 == pg0) && (c.g1 == pg1) && (c.g2 == pg2);
-                    if (pending && !same) {
-                        atomicAdd(tab + pi0, v0);
-                        atomicAdd(tab + pi1, v1);
-                        pending = false;
-                    }
-                    if (qact[q]) {
-                        if (same) {
-                            v0.x = fmaf(c.w0, fx, v0.x); v0.y = fmaf(c.w0, fy, v0.y);
-                            v1.x = fmaf(c.w1, fx, v1.x); v1.y = fmaf(c.w1, fy, v1.y);
-                        } else {
-                            v0 = make_float2(c.w0 * fx, c.w0 * fy); v1 = make_float2(c.w1 * fx, c.w1 * fy);
-                            pi0 = c.i0; pi1 = c.i1; pg0 = c.g0; pg1 = c.g1; pg2 = c.g2;
-                            pending = true;
-                        }
-                    }
+                    const float fx = __shfl_sync(0xffffffffu, df.x, qbase + q), fy = __shfl_sync(0xffffffffu, df.y, qbase + q);
+                    c[q] = side_corners2(lc, qx[q][0], qx[q][1], qx[q][2], sx, sy);
+                    u0[q] = make_float2(c[q].w0 * fx, c[q].w0 * fy);
+                    u1[q] = make_float2(c[q].w1 * fx, c[q].w1 * fy);
                 }
-                if (pending) {
-                    atomicAdd(tab + pi0, v0);
-                    atomicAdd(tab + pi1, v1);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q > 0) {
+                        const bool join = qact[q] && qact[q - 1] && (c[q].cell == c[q - 1].cell);     // continues the run of q-1
+                        u0[q].x += join ? u0[q - 1].x : 0.f; u0[q].y += join ? u0[q - 1].y : 0.f;
+                        u1[q].x += join ? u1[q - 1].x : 0.f; u1[q].y += join ? u1[q - 1].y : 0.f;
+                    }
+                    const bool ends = qact[q] && (q == 3 || !(qact[q + 1 < 4 ? q + 1 : 3] && (c[q + 1 < 4 ? q + 1 : 3].cell == c[q].cell)));
+#ifdef USL_DEV
+                    if (A.dbg & 1) continue;
+#endif
+                    if (ends) {
+                        atomicAdd(tab + c[q].i0, u0[q]);
+                        atomicAdd(tab + c[q].i1, u1[q]);
+                    }
                 }
             }
         }
+        w = w_next;
     }
-
-    // ---- block reduction of the decoder gradients, one atomic per element per CTA (once, after the last tile) ----
-    if (A.has_gm) {
-        __syncthreads();
-        float *red = reinterpret_cast<float *>(&S.st[0]);          // stages are idle now: [B2_WARPS][32][33] floats
-        float *mine = red + (warp * 32 + lane) * 33;                // stride 33: conflict-free
-#pragma unroll
-        for (int q = 0; q < 16; ++q) mine[q] = acc1[q];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) mine[16 + q] = acc2[q];
-        mine[24] = acco[0]; mine[25] = acco[1];
-        mine[26] = accb[0]; mine[27] = accb[1]; mine[28] = accb[2];
-        __syncthreads();
-        const usl_mlp_t &gm = A.gm[gi];
-        for (int e = tid; e < 32 * 29; e += B2_THREADS) {
-            const int ln = e / 29, q = e % 29;
-            float sacc = 0.f;
-#pragma unroll
-            for (int w = 0; w < B2_WARPS; ++w) sacc += red[(w * 32 + ln) * 33 + q];
-            if (q < 16) {                                   // dW1[j][k]: lane ln = (j, level parity), q = 2*(level >> 1) + feature
-                const int j = ln >> 1, kk = 4 * (q >> 1) + 2 * (ln & 1) + (q & 1);
-                if (gm.w1) atomicAdd(gm.w1 + j * USL_IN + kk, sacc);
-            } else if (q < 24) {                            // dW2[r2][2*(q-16) + parity]
-                if (NH == 2 && gm.w2) atomicAdd(gm.w2 + (ln >> 1) * USL_HID + 2 * (q - 16) + (ln & 1), sacc);
-            } else if (q < 26) {                            // dWo[2*(ln>>4) + (q-24)][ln & 15]
-                const int o = (ln >> 4) * 2 + (q - 24), ii = ln & 15;
-                if (o < m.n_out && gm.wo) atomicAdd(gm.wo + o * USL_HID + ii, sacc);
-            } else if (q == 26) {
-                if (ln < 16 && gm.b1) atomicAdd(gm.b1 + ln, sacc);
-            } else if (q == 27) {
-                if (NH == 2 && ln < 16 && gm.b2) atomicAdd(gm.b2 + ln, sacc);
-            } else {
-                if (ln < m.n_out && gm.bo) atomicAdd(gm.bo + ln, sacc);
-            }
-        }
-    }
+    if (cur >= 0 && A.has_gm) flush(cur);
 }
 
 // ---- replicated coarse levels ---------------------------------------------------------------------
@@ -461,7 +539,7 @@ int usl_field_bwd_scratch_floats(const usl_field_t *f, int64_t *n_floats) {
     uint32_t cnt[2][USL_MAX_LEVELS], off[2][USL_MAX_LEVELS];
     int64_t entries = 0;
     plan_replicas(f, cnt, off, &entries);
-    *n_floats = entries * 2;
+    *n_floats = entries * 2 + 32;        // + work-queue counters (one per grid_mask value), zero-filled with the rest
     return 0;
 }
 
@@ -492,6 +570,12 @@ int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw,
     int64_t rep_entries = 0;
     plan_replicas(f, A.rep_count, A.rep_offset, &rep_entries);
     A.scratch = (rep_entries > 0) ? scratch : nullptr;
+    A.dbg = 0;
+#ifdef USL_DEV
+    { const char *e = getenv("USL_DBG_BWD"); if (e) A.dbg = atoi(e); }   // ablations: 1 no atomics, 2 no scatter phase, 4 no weight-gradient phase
+    if (A.dbg & 8) A.scratch = nullptr;                                  // ablation: no replicated coarse levels
+#endif
+    A.counter = scratch ? reinterpret_cast<unsigned int *>(scratch + rep_entries * 2) + grid_mask : nullptr;
     cudaStream_t s = (cudaStream_t)stream;
 
     int dev = 0, n_sm = 0, per_sm = 0;
@@ -504,11 +588,10 @@ int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw,
         cudaGetLastError(); set_error("usl_field_bwd: cannot reserve %zu bytes of shared memory", smem); return 1;
     }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, B2_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const int64_t n_tiles = (p->n + B2_TILE - 1) / B2_TILE;
-    int64_t ctas_per_grid = ((int64_t)n_sm * per_sm) / A.n_grids;
-    if (ctas_per_grid < 1) ctas_per_grid = 1;
-    if (ctas_per_grid > n_tiles) ctas_per_grid = n_tiles;
-    const unsigned nblk = (unsigned)(ctas_per_grid * A.n_grids);
+    const int64_t n_items = ((p->n + B2_TILE - 1) / B2_TILE) * A.n_grids;
+    int64_t nb = (int64_t)n_sm * per_sm;                      // persistent: every resident slot of the device, once
+    if (nb > n_items) nb = n_items;
+    const unsigned nblk = (unsigned)nb;
     if (nh2) field_bwd2_kernel<2><<<nblk, B2_THREADS, smem, s>>>(A);
     else field_bwd2_kernel<1><<<nblk, B2_THREADS, smem, s>>>(A);
     if (check_launch("usl_field_bwd")) return 1;
