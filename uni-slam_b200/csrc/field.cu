@@ -52,10 +52,16 @@ __device__ __forceinline__ bool load_point(const usl_points_t &p, const usl_fiel
 }
 
 template <bool WITH_JAC, bool SAVE_FEAT>
+#ifndef USL_FWD_THREADS
+#define USL_FWD_THREADS 256
+#endif
 #ifndef USL_FWD_MINB
 #define USL_FWD_MINB 2
 #endif
-__global__ void __launch_bounds__(256, (WITH_JAC ? USL_FWD_MINB : 4)) field_fwd_kernel(const __grid_constant__ FieldArgs A) {
+#ifndef USL_FWD_UNR
+#define USL_FWD_UNR 1            // levels whose gathers are in flight together (with the Jacobian)
+#endif
+__global__ void __launch_bounds__(USL_FWD_THREADS, (WITH_JAC ? USL_FWD_MINB : (1024 / USL_FWD_THREADS))) field_fwd_kernel(const __grid_constant__ FieldArgs A) {
     __shared__ MlpSmem sm;
     const int gi = blockIdx.y;
     stage_mlp(A.f.mlp[gi], sm);
@@ -83,8 +89,11 @@ __global__ void __launch_bounds__(256, (WITH_JAC ? USL_FWD_MINB : 4)) field_fwd_
     float *ho = (SAVE_FEAT && active) ? A.feat + (int64_t)2 * USL_IN * A.p.n + ((int64_t)gi * USL_HID) * A.p.n + i : nullptr;
     // PAIRED gather (template arg 4) measured 165.6 vs 163.5 us un-paired: the forward is latency / occupancy bound, not
     // bound by sector requests -- left off.  (The same lane pairing is what speeds up the atomics in field_bwd.)
-    decode_point<WITH_JAC, SAVE_FEAT, 1, false>(g, reinterpret_cast<const float2 *>(A.f.table[gi]), A.f.mlp[gi], sm, xc, fo,
-                                                A.p.n, out, tout, ho);
+#ifndef USL_FWD_LANEPAIR
+#define USL_FWD_LANEPAIR 1
+#endif
+    decode_point<WITH_JAC, SAVE_FEAT, USL_FWD_UNR, false, (USL_FWD_LANEPAIR != 0)>(g, reinterpret_cast<const float2 *>(A.f.table[gi]), A.f.mlp[gi],
+                                                                        sm, xc, fo, A.p.n, out, tout, ho);
     if (!active) return;
     if (gi == 0) {
         A.raw[i * 4 + 3] = out[0];
@@ -443,7 +452,7 @@ int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float
     if (p->n <= 0) return 0;
     FieldArgs A;
     A.f = *f; A.p = *p; A.raw = raw; A.feat = feat; A.jac = jac; A.sdf = nullptr;
-    dim3 grid((unsigned)((p->n + 255) / 256), 2);
+    dim3 grid((unsigned)((p->n + USL_FWD_THREADS - 1) / USL_FWD_THREADS), 2);
     cudaStream_t s = (cudaStream_t)stream;
     // USL_TCGEN05=1: tangent contraction of the Jacobian path on the tcgen05 tensor cores (field_tc.cu). Parity-tested
     // and profiled, but not the default: the kernel is bound by L1 sector lookups of the gather,
@@ -453,10 +462,10 @@ int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float
     { const char *tc_env = getenv("USL_TCGEN05");      // development builds only: select the tensor-core variant by environment
       if (jac && tc_env && tc_env[0] == '1' && !p->sample_major) return usl_field_fwd_tc_launch(f, p, raw, feat, jac, s); }
 #endif
-    if (jac && feat) field_fwd_kernel<true, true><<<grid, 256, 0, s>>>(A);
-    else if (jac) field_fwd_kernel<true, false><<<grid, 256, 0, s>>>(A);
-    else if (feat) field_fwd_kernel<false, true><<<grid, 256, 0, s>>>(A);
-    else field_fwd_kernel<false, false><<<grid, 256, 0, s>>>(A);
+    if (jac && feat) field_fwd_kernel<true, true><<<grid, USL_FWD_THREADS, 0, s>>>(A);
+    else if (jac) field_fwd_kernel<true, false><<<grid, USL_FWD_THREADS, 0, s>>>(A);
+    else if (feat) field_fwd_kernel<false, true><<<grid, USL_FWD_THREADS, 0, s>>>(A);
+    else field_fwd_kernel<false, false><<<grid, USL_FWD_THREADS, 0, s>>>(A);
     return check_launch("usl_field_fwd");
 }
 

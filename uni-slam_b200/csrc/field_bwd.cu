@@ -123,22 +123,6 @@ __device__ __forceinline__ void load_tile_sync(const FieldBwd2Args &A, B2Smem &S
     }
 }
 
-// ---- packed FP32 (Blackwell FFMA2: two IEEE fp32 FMAs per instruction, each rounded like fmaf) ----
-typedef unsigned long long f32x2_t;
-__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
-    f32x2_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float2 unpack2(f32x2_t v) {
-    float2 r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-    return r;
-}
-__device__ __forceinline__ void ffma2(f32x2_t &acc, f32x2_t a, f32x2_t b) {       // acc = a * b + acc (element-wise)
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
-}
-
 // Per-level constants hoisted out of the point loop.  Branch-free over dense / hashed levels: both index forms are two
 // multiplies and combines (add or xor) followed by a wrap (conditional subtract or mask), so the kind only selects.
 struct LevelConst {

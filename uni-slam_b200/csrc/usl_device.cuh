@@ -215,7 +215,7 @@ __device__ __forceinline__ void level_interp(const usl_level_t &lv, const float2
 
 // ---- decoder weights staged in shared memory --------------------------------------------------
 // Layout (floats): w1t[32][16] (transposed: [k][j]), b1[16], w2[16][16], b2[16], wo[4][16], bo[4]
-struct MlpSmem {
+struct alignas(16) MlpSmem {
     float w1t[USL_IN][USL_HID];
     float b1[USL_HID];
     float w2[USL_HID][USL_HID];
@@ -283,6 +283,22 @@ __device__ __forceinline__ void pose_to_c2w(const float *__restrict__ pose, floa
 #undef USL_MUL
 #undef USL_ADD
 #undef USL_SUB
+}
+
+// ---- packed FP32 (Blackwell FFMA2: two IEEE fp32 FMAs per instruction, each rounded like fmaf) ----
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ void ffma2(f32x2_t &acc, f32x2_t a, f32x2_t b) {       // acc = a * b + acc (element-wise)
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
