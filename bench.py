@@ -40,6 +40,18 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _load_profile_json(kind):
+    """Newest profiles/rNN_<kind>.json (written from ncu / tools/microbench.py runs of an earlier gpurun call)."""
+    import glob
+    cands = sorted(glob.glob(os.path.join(REPO, "profiles", f"r[0-9][0-9]_{kind}.json")))
+    for p in reversed(cands):
+        try:
+            return json.load(open(p))
+        except Exception:
+            continue
+    return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -168,11 +180,15 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(dev))
     cfg = syn.CONFIGS[args.config]
-    wl = wlmod.build_mapping_workload(cfg, dev, seed=1 + rank)        # weak scaling: every rank its own ray batch
+    # Every rank holds the same keyframe window (replicated scene data, as the replicated tables); what differs per rank is
+    # the ray batch: its own random draws (weak scaling: N batches per step) or its contiguous slice of ONE batch (strong).
+    wl = wlmod.build_mapping_workload(cfg, dev, seed=1)
     meta, tabs, dec, beta = wlmod.init_field_tensors(cfg, wl.bound, wl.per_level_scale, dev, seed=0)
     R, S = wl.n_rays, wl.S
+    par = importlib.import_module("uni-slam_b200.parallel")
+    pg = par.PeerGroup(dev) if (world > 1 and args.collective == "peer") else None
     step = P.MappingStep(meta, tabs[0], tabs[1], dec, beta, n_stratified=cfg.n_stratified, n_importance=cfg.n_importance,
-                         truncation=cfg.truncation, max_rays=R, max_frames=wl.K)
+                         truncation=cfg.truncation, max_rays=R, max_frames=wl.K, grad_alloc=pg.alloc if pg else None)
     cam_poses = wl.cam_poses.clone()
     params = [tabs[0], tabs[1], beta] + dec + [cam_poses]
     grads = [step.fs.g_sdf_table, step.fs.g_rgb_table, step.fs.g_beta] + step.fs.g_dec + [step.d_pose[:wl.K - 1]]
@@ -189,19 +205,22 @@ def run_ours(args, rank, world, local_rank):
 
     reduce_grads = None
     if world > 1:
-        par = importlib.import_module("uni-slam_b200.parallel")
-        reduce_grads = par.attach_mapping_collectives(step, overlap=args.overlap)
+        reduce_grads = par.attach_peer_collectives(step, pg) if pg else par.attach_mapping_collectives(step, overlap=args.overlap)
+    my_rays = par.slab_range(R, rank, world)                           # strong scaling: this rank's contiguous slice of the batch
+    mode = {"strong": False}                                           # flipped for the strong-scaling leg
 
     def one_step():
         idx_main, idx_recent, t_rand, t_uni, u_pdf = bufs
         # host-code side of the iteration: the RNG draws (torch.randint / torch.rand, common.py:155, Renderer.py:55) --
         # one index fill and one uniform fill over the two flat buffers that hold the five slot-indexed tensors
-        flat_idx.random_(0, wl.P, generator=gen)
-        flat_u.uniform_(generator=gen)
+        g_ = mode.get("gen", gen)
+        flat_idx.random_(0, wl.P, generator=g_)
+        flat_u.uniform_(generator=g_)
+        rr = my_rays if mode["strong"] else None
         if args.no_joint:
-            step.run(wl.batches(idx_main, idx_recent), t_rand, t_uni, u_pdf)
+            step.run(wl.batches(idx_main, idx_recent), t_rand, t_uni, u_pdf, ray_range=rr)
         else:
-            step.run(wl.batches(idx_main, idx_recent), t_rand, t_uni, u_pdf, cam_poses=cam_poses.detach(), c2w_fixed=wl.c2ws[0])
+            step.run(wl.batches(idx_main, idx_recent), t_rand, t_uni, u_pdf, cam_poses=cam_poses.detach(), c2w_fixed=wl.c2ws[0], ray_range=rr)
         if world > 1:                                                   # a-12/8e: gradient all-reduce over NVLink
             reduce_grads()
 
@@ -283,6 +302,11 @@ def run_ours(args, rank, world, local_rank):
     samples = R * S * args.steps * world
     value = samples / (total_ms * 1e-3)
 
+    mg = {}
+    if world > 1:
+        mg = multi_gpu_legs(args, P, par, pg, step, wl, one_step, mode, flat_idx, flat_u, bufs, cam_poses, tabs, dec, beta, cfg, dev,
+                            rank, world, dist, R, S, flush, reduce_grads, my_rays)
+
     # ---- per-kernel durations (eager, CUDA events on the launching stream) for the roofline ----
     step.profile = True
     step.events = {}
@@ -299,26 +323,38 @@ def run_ours(args, rank, world, local_rank):
         "usl_field_bwd": {"ms": kms.get("usl_field_bwd"), "alg_bytes": gather_bytes + n_pts * 16},
     }
     peak, peak_src = _peaks()
-    # ceilings measured on this pool's B200 by tools/microbench.py (profiles/r01_microbench.json): L2-resident random
-    # 8-byte gathers ~280 G loads/s, 8-byte vector atomics ~223 G ops/s
-    l2_ceiling = {"usl_field_fwd": 280.0e9, "usl_field_bwd": 223.0e9}
-    lane_ops = n_pts * 2 * 16 * 8
+    # Secondary rooflines.  The tables are L2-resident, so besides the HBM fraction every kernel reports (i) its L2 traffic
+    # (ncu lts sectors x 32 B per launch, profiles/rNN_traffic.json) over its own duration against the MEASURED L2 read
+    # bandwidth, and (ii) the request rate of the unit that actually binds it -- L1TEX sector lookups for the gather,
+    # atomic sector operations for the scatter -- against the ceilings tools/microbench.py measured on this pool's B200
+    # (profiles/rNN_microbench.json).  Nothing here is hard-coded; a missing file leaves the fractions null.
+    ceil = _load_profile_json("microbench").get("ceilings", {})
+    traffic = _load_profile_json("traffic")
     for name, k in kern.items():
-        k["gbs"] = k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] else None
+        sec = k["ms"] * 1e-3 if k["ms"] else None
+        k["gbs"] = k["alg_bytes"] / sec / 1e9 if sec else None
         k["frac"] = k["gbs"] / peak if k["gbs"] else None
-        k["lane_ops_per_s"] = lane_ops / (k["ms"] * 1e-3) if k["ms"] else None
-        k["frac_of_measured_l2_random_access_ceiling"] = k["lane_ops_per_s"] / l2_ceiling[name] if k["ms"] else None
-    traffic = {}
-    tp = os.path.join(REPO, "profiles", "r01_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp))
-    for name, k in kern.items():
-        k["dram_traffic_bytes_ncu"] = traffic.get(name)
+        t = traffic.get(name) if args.config == "replica_room0" else None     # the ncu capture is of the replica workload
+        k["dram_traffic_bytes_ncu"] = t.get("dram_bytes") if t else None
+        if t and sec:
+            l2_bytes = 32.0 * (t["lts_sectors_read"] + t["lts_sectors_write"] + t["lts_sectors_red"])
+            k["l2"] = {"bytes_ncu": l2_bytes, "achieved_gbs": l2_bytes / sec / 1e9, "peak_gbs": ceil.get("l2_read_gbs"),
+                       "frac_l2": (l2_bytes / sec / 1e9 / ceil["l2_read_gbs"]) if ceil.get("l2_read_gbs") else None}
+            if name == "usl_field_fwd":
+                k["binding_unit"] = {"unit": "L1TEX sector lookups", "count_ncu": t["l1_sector_lookups_ld"], "rate_per_s": t["l1_sector_lookups_ld"] / sec,
+                                     "ceiling_per_s": ceil.get("l1_sector_lookups_per_s"),
+                                     "frac": (t["l1_sector_lookups_ld"] / sec / ceil["l1_sector_lookups_per_s"]) if ceil.get("l1_sector_lookups_per_s") else None}
+            else:
+                k["binding_unit"] = {"unit": "atomic sector operations (red.global.add.v2.f32)", "count_ncu": t["lts_sectors_red"], "rate_per_s": t["lts_sectors_red"] / sec,
+                                     "ceiling_per_s": ceil.get("atomic_sectors_per_s"),
+                                     "frac": (t["lts_sectors_red"] / sec / ceil["atomic_sectors_per_s"]) if ceil.get("atomic_sectors_per_s") else None}
     dom = max(kern, key=lambda k: kern[k]["ms"] or 0)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
                 "traffic": kern[dom]["dram_traffic_bytes_ncu"], "peak_source": peak_src,
-                "frac_of_measured_l2_random_access_ceiling": kern[dom]["frac_of_measured_l2_random_access_ceiling"],
-                "note": "tables (49 MB) are L2-resident: the binding resource is L2 sector throughput, not HBM; see DESIGN.md section 5"}
+                "l2": kern[dom].get("l2"), "binding_unit": kern[dom].get("binding_unit"),
+                "note": "achieved = algorithmic bytes (1024 B gathered or scattered per point per grid) / kernel time; the tables "
+                        "(49 MB) are L2-resident, so DRAM traffic is a fraction of that and the binding resource is the atomic "
+                        "sector rate (scatter) / the L1TEX lookup + latency (gather); see DESIGN.md section 5"}
 
     if args.quick:
         if rank == 0:
@@ -442,15 +478,182 @@ def run_ours(args, rank, world, local_rank):
                 "cpu_baseline": cpu_base, "parity_full_size": parity,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches_per_step * args.steps,
-                "value_l2_warm": samples / (warm_ms * 1e-3), "prefit_loss": losses[:1] + losses[-1:], **extra}
+                "value_l2_warm": samples / (warm_ms * 1e-3), "prefit_loss": losses[:1] + losses[-1:], **mg, **extra}
+        if world > 1:
+            line["config"]["collective"] = mg.get("collective", {}).get("collective")
         print(json.dumps(line), flush=True)
     if world > 1:
-        # leave without tearing NCCL down: destroy_process_group() can block when captured graphs still hold
-        # communicator work (seen on this stack); every rank has synchronised and rank 0 has printed its line
-        dist.barrier()
-        torch.cuda.synchronize()
+        # clean teardown: drop every captured graph (they hold communicator / peer-memory work), synchronise, then destroy the
+        # process group.  A watchdog ends the process if the teardown blocks (seen once on this stack with NCCL work captured
+        # in live graphs); by then every rank has synchronised and rank 0 has printed its line.
         sys.stdout.flush(); sys.stderr.flush()
-        os._exit(0)
+        graph = None; e2e_graphs = None; run_step = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        wd = threading.Timer(20.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
+        dist.destroy_process_group()
+        wd.cancel()
+
+
+def multi_gpu_legs(args, P, par, pg, step, wl, one_step, mode, flat_idx, flat_u, bufs, cam_poses, tabs, dec, beta, cfg, dev, rank, world,
+                   dist, R, S, flush, reduce_grads, my_rays):
+    """N > 1 only (pytest -m gpu runs on one GPU, so the multi-GPU correctness checks live here):
+      allreduce_check   the all-reduced gradients of the SPLIT batch (every rank its contiguous slice, loss sums exchanged,
+                        gradients all-reduced) against the single-GPU gradients of the WHOLE batch computed on the same rank;
+                        and the peer all-reduce against NCCL's on the same input
+      collective        stand-alone time of the gradient exchange (hand-written peer kernel vs NCCL), bus GB/s
+      strong scaling    the same global batch of R rays split across the ranks, timed like the headline
+      sharded Adam      usl_allreduce_adam_step: reduction + Adam on 1/N of the parameters + parameter broadcast in one pass"""
+    out = {}
+    L = P._lib
+    run_args = dict(cam_poses=cam_poses.detach(), c2w_fixed=wl.c2ws[0]) if not args.no_joint else {}
+
+    def sync():
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+
+    # ---- (A) split batch + exchange + all-reduce  ==  whole batch on one GPU ----
+    g0 = torch.Generator(device=dev).manual_seed(4242)                 # the same draws on every rank
+    flat_idx.random_(0, wl.P, generator=g0); flat_u.uniform_(generator=g0)
+    hook, step.acc_hook = step.acc_hook, None
+    step.run(wl.batches(bufs[0], bufs[1]), bufs[2], bufs[3], bufs[4], **run_args)          # whole batch, local sums only
+    sync()
+    g_full = step.fs.g_grads.double().clone(); loss_full = float(step.loss)
+    step.acc_hook = hook
+    step.run(wl.batches(bufs[0], bufs[1]), bufs[2], bufs[3], bufs[4], ray_range=my_rays, **run_args)
+    reduce_grads()
+    sync()
+    g_split = step.fs.g_grads.double()
+    chk = {"split_vs_whole_batch_grad_rel": float((g_split - g_full).norm() / g_full.norm()),
+           "split_vs_whole_batch_loss_rel": abs(float(step.loss) - loss_full) / abs(loss_full)}
+    step.run(wl.batches(bufs[0], bufs[1]), bufs[2], bufs[3], bufs[4], **run_args)          # the same whole batch on every rank
+    reduce_grads()
+    sync()
+    chk["replicated_batch_grad_rel"] = float((step.fs.g_grads.double() - g_full).norm() / g_full.norm())
+    # peer all-reduce vs NCCL on identical inputs
+    n = step.fs.n_grad_padded
+    base = torch.rand(n, device=dev, generator=torch.Generator(device=dev).manual_seed(99)) - 0.5
+    ref = (base * (rank + 1)).clone()
+    dist.all_reduce(ref)
+    if pg is not None:
+        step.fs.g_all[:n].copy_(base * (rank + 1))
+        sync()
+        pg.allreduce(step.fs.g_all, n)
+        sync()
+        chk["peer_vs_nccl_max_abs"] = float((step.fs.g_all[:n] - ref).abs().max())
+        chk["peer_vs_expected_max_rel"] = float(((step.fs.g_all[:n] - base * (world * (world + 1) / 2)).abs() / base.abs().clamp_min(1e-3)).max())
+    t = torch.tensor([chk[k] for k in sorted(chk)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                           # worst rank
+    chk = {k: float(v) for k, v in zip(sorted(chk), t)}
+    chk["ok"] = bool(chk["split_vs_whole_batch_grad_rel"] < 1e-3 and chk["replicated_batch_grad_rel"] < 1e-3 and chk.get("peer_vs_expected_max_rel", 0.0) < 1e-5)
+    out["allreduce_check"] = chk
+
+    # ---- (B) the gradient exchange alone ----
+    def timeit(fn, iters=20):
+        for _ in range(3):
+            fn()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0])
+    nbytes = n * 4
+    bus = lambda ms: 2 * (world - 1) / world * nbytes / (ms * 1e-3) / 1e9
+    coll = {"bytes": nbytes, "collective": "usl_allreduce_sum (two-shot over peer memory)" if pg is not None else "ncclAllReduce"}
+    ms = timeit(lambda: dist.all_reduce(step.fs.g_all[:n]))
+    coll["nccl_us"] = ms * 1e3; coll["nccl_bus_gbs"] = bus(ms)
+    if pg is not None:
+        ms = timeit(lambda: pg.allreduce(step.fs.g_all, n))
+        coll["peer_us"] = ms * 1e3; coll["peer_bus_gbs"] = bus(ms)
+        ms = timeit(lambda: pg.exchange_sums(step.acc))
+        coll["exchange_sums_us"] = ms * 1e3
+    ms = timeit(lambda: dist.all_reduce(step.acc))
+    coll["nccl_small_allreduce_us"] = ms * 1e3
+    coll["nvlink5_peak_gbs_per_direction"] = 900.0
+    out["collective"] = coll
+
+    # ---- (C) strong scaling: ONE batch of R rays, split contiguously across the ranks ----
+    mode["strong"] = True
+    mode["gen"] = torch.Generator(device=dev).manual_seed(777)         # identical draws on every rank: one global batch
+    run = one_step
+    graph = None
+    if not args.no_graph:
+        try:
+            s_ = torch.cuda.Stream(); s_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_):
+                for _ in range(2):
+                    one_step()
+            torch.cuda.current_stream().wait_stream(s_); sync()
+            graph = torch.cuda.CUDAGraph()
+            graph.register_generator_state(mode["gen"])
+            with torch.cuda.graph(graph):
+                one_step()
+            run = graph.replay
+        except Exception as e:                                         # noqa: BLE001
+            print(f"[bench] strong-scaling graph capture failed ({type(e).__name__}: {e}); eager", file=sys.stderr)
+            graph = None; torch.cuda.synchronize()
+    for _ in range(3):
+        run()
+    sync()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record()
+        evs.append((e0, e1))
+    sync()
+    tt = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt[0]) / args.steps
+    out["strong_scaling"] = {"rays_total": R, "rays_per_rank": my_rays[1] - my_rays[0], "ms_per_step": ms, "value": R * S / (ms * 1e-3), "unit": UNIT,
+                             "cuda_graph": graph is not None,
+                             "note": "the reference's fixed global batch (Mapper.py:379-393) split contiguously across the ranks; the step "
+                                     "is bound by the exchange of the 51.6 MB dense gradient, which does not shrink with the batch"}
+    mode["strong"] = False
+    mode.pop("gen")
+    if graph is not None:
+        del graph
+
+    # ---- (D) fused reduction + sharded Adam + parameter broadcast ----
+    if pg is not None:
+        fs = step.fs
+        pflat = pg.alloc(n)
+        # parameters in the gradient buffer's layout: [sdf table | colour table | decoders | beta | poses | pad]
+        srcs = [tabs[0], tabs[1]] + list(dec) + [beta, cam_poses]
+        o = 0
+        offs = []
+        for t_, g_ in zip(srcs, [fs.g_sdf_table, fs.g_rgb_table] + fs.g_dec + [fs.g_beta, fs.d_pose]):
+            pflat[o:o + t_.numel()].copy_(t_.detach().reshape(-1))
+            offs.append((o, o + t_.numel()))
+            o += g_.numel()
+        n_tab = tabs[0].numel() + tabs[1].numel()
+        ranges = [(0, n_tab, cfg.hash_lr), (n_tab, n, 1e-3)]
+        fsa = par.FusedShardedAdam(pg, pflat, fs.g_all, n, ranges)
+        gsum = None
+        # one checked step: first Adam step from zero state has the closed form p - lr * g / (|g| + eps)
+        fs.g_all[:n].copy_(base * (rank + 1))
+        p_before = pflat.clone()
+        sync()
+        fsa.step()
+        sync()
+        gsum = base * (world * (world + 1) / 2)
+        lr_vec = torch.full((n,), 1e-3, device=dev); lr_vec[:n_tab] = cfg.hash_lr
+        want = p_before - lr_vec * gsum / (gsum.abs() + 1e-8)
+        err = float(((pflat - want).abs() / want.abs().clamp_min(1e-3)).max())
+        te = torch.tensor([err], device=dev, dtype=torch.float64); dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ms = timeit(fsa.step, iters=10)
+        fopt_ms = None
+        out["sharded_adam"] = {"op": "usl_allreduce_adam_step", "us": ms * 1e3, "first_step_max_rel_err_vs_closed_form": float(te[0]),
+                               "params": n, "state_floats_per_rank": fsa.exp_avg.numel() * 2,
+                               "note": "gradient reduction + Adam on this rank's 1/N slice + broadcast of the new parameters, one pass"}
+    return out
 
 
 def bench_tracking(P, wl, meta, tabs, dec, beta, cfg, dev, args):
@@ -646,6 +849,8 @@ def main():
                     help="workload: BASELINE configs[1] (default, the metric's config) or configs[2] (ScanNet-shaped; extra)")
     ap.add_argument("--overlap", action="store_true", help="N>1: all-reduce the colour-table gradient on a side stream while the sdf half of "
                     "field_bwd runs (measured SLOWER at N=2: 0.80 vs 0.75 ms/step -- NCCL's reduction and the atomics contend for L2)")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N>1: gradient / loss-sum exchange by the hand-written peer-memory kernels (csrc/collective.cu, default) or by NCCL")
     ap.add_argument("--quick", action="store_true", help="mapping step only (used under ncu): skip e2e / tracking / dense query / Adam / cpu baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -194,6 +194,9 @@ typedef struct usl_ray_setup {
     uint8_t *valid;
     float *z;                           /* [n_rays,S]; rows of depth-less rays are left for usl_zsample_nodepth */
     int64_t pixel_begin;                /* mode 2: row-major index (j*W + i) of the first pixel; gt_color / dirs_out nullable */
+    int64_t ray_offset;                 /* mode 0: first GLOBAL ray slot of this call (multi-GPU: the batch is split contiguously
+                                         * across ranks after sampling); indices / t_rand are indexed by global slot,
+                                         * outputs by local slot 0..n_rays-1 */
 } usl_ray_setup_t;
 USL_API int usl_ray_setup(const usl_ray_setup_t *a, usl_stream_t stream);
 
@@ -320,8 +323,46 @@ typedef struct usl_adam_group {
 USL_API int usl_adam_step(const usl_adam_group_t *groups, int n_groups, int64_t step, const int64_t *step_dev,
                           int zero_grad, usl_stream_t stream);
 
+/* ---- 8e: multi-GPU exchange steps of the sharded mapping iteration, over peer memory (NVLink / NVSwitch) -----------
+ * The reference is single-GPU; these entry points are what its proposed `allreduce_grads` seam becomes.
+ * The host layer maps every rank's buffers into every rank's address space (CUDA IPC / symmetric memory: one allocation
+ * call per buffer at start-up) and passes the mapped pointers; nothing here calls NCCL. */
+#define USL_MAX_PEERS 8
+#define USL_PEER_CTRL_BYTES 2048          /* per-rank control block (flags, exchange slots, epochs): peer-mapped, zeroed once */
+typedef struct usl_peers {
+    int32_t rank, world;
+    void *buf[USL_MAX_PEERS];             /* buf[p]: rank p's flat gradient buffer as mapped HERE (buf[rank] = the local one) */
+    void *ctrl[USL_MAX_PEERS];            /* ctrl[p]: rank p's control block as mapped here */
+} usl_peers_t;
+USL_API int usl_peer_ctrl_bytes(void);
+/* acc[USL_LOSS_SLOTS] (device, local) <- sum over ranks of acc: the loss sums / counts of usl_loss_fwd become global, so
+ * every mean of the loss divides by the GLOBAL element count (one tiny kernel: push to all peers, flag, wait, sum) */
+USL_API int usl_exchange_sums(const usl_peers_t *P, float *acc, usl_stream_t stream);
+USL_API int usl_peer_barrier(const usl_peers_t *P, usl_stream_t stream);
+/* buf[p][offset : offset+n] <- sum over ranks, on every rank (two-shot over peer memory: rank r reduces slice r and
+ * pushes it to all; barrier before and after).  offset and n in floats, multiples of 4. */
+USL_API int usl_allreduce_sum(const usl_peers_t *P, int64_t offset_floats, int64_t n_floats, usl_stream_t stream);
+/* The same pass with the optimiser fused in (f1): the owner of a slice sums the gradients, applies torch.optim.Adam's update
+ * (no weight decay / amsgrad) to its slice of the parameters and pushes the NEW PARAMETERS to every rank's param[p]
+ * (same flat layout as the gradient buffers).  exp_avg / exp_avg_sq: this rank's state for its own slice only
+ * (usl_allreduce_adam_slice_floats() floats each, zero-initialised).  ranges: learning rate per [begin,end) of the flat
+ * layout (floats outside every range are left untouched).  step / step_dev as in usl_adam_step. */
+#define USL_ADAM_MAX_RANGES 8
+typedef struct usl_adam_range {
+    int64_t begin, end;
+    float lr, _pad;
+} usl_adam_range_t;
+USL_API int usl_allreduce_adam_slice_floats(int world, int64_t n_floats, int64_t *slice_floats);
+USL_API int usl_allreduce_adam_step(const usl_peers_t *P, float *const *param, int64_t offset_floats, int64_t n_floats,
+                                    float *exp_avg, float *exp_avg_sq, const usl_adam_range_t *ranges, int n_ranges,
+                                    float beta1, float beta2, float eps, int64_t step, const int64_t *step_dev,
+                                    usl_stream_t stream);
+
 /* ---- measurement utilities (no reference counterpart): ceilings for the roofline discussion ---- */
 /* n_threads threads each issue per_thread random 8-byte loads from / vector atomics into table[entries*2] */
+/* `repeats` coalesced read passes over buf[n_floats] (ld.global.cg, 16 bytes per lane): L2 read bandwidth when the buffer
+ * fits L2, HBM read bandwidth when it does not */
+USL_API int usl_bench_stream_read(const float *buf, int64_t n_floats, int repeats, float *out, usl_stream_t stream);
 USL_API int usl_bench_gather(const float *table, uint32_t entries, int64_t n_threads, int per_thread, float *out,
                              usl_stream_t stream);
 USL_API int usl_bench_scatter(float *table, uint32_t entries, int64_t n_threads, int per_thread, int mode,

@@ -540,3 +540,44 @@ def test_median_select_and_keep_best():
         L.call("usl_track_keep_best", L.ptr(lt), L.ptr(poses[i]), L.ptr(best_loss), L.ptr(best_pose), L.stream())
         assert torch.equal(best_pose, poses[i]) == keep
     assert float(best_loss) == 1.0
+
+
+def test_peer_collectives_single_rank_and_sharded_adam():
+    """csrc/collective.cu on one GPU (world = 1: the peer is this rank itself): the loss-sum exchange and the all-reduce are
+    identities, and usl_allreduce_adam_step reproduces torch.optim.Adam (two learning-rate ranges, several steps, device-side
+    step counter).  The N > 1 behaviour is checked inside bench.py --gpus N ("allreduce_check")."""
+    import importlib
+    P = pkg()
+    par = importlib.import_module("uni-slam_b200.parallel")
+    pg = par.PeerGroup.single(DEV)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    acc = torch.rand(16, device=DEV, generator=g)
+    want = acc.clone()
+    for _ in range(3):                                   # epochs advance; double-buffered slots
+        pg.exchange_sums(acc)
+    torch.cuda.synchronize()
+    assert torch.equal(acc, want)
+    n = 4096 * 5 + 64
+    grads = pg.alloc(n); params = pg.alloc(n)
+    grads.copy_(torch.randn(n, device=DEV, generator=g))
+    before = grads.clone()
+    pg.allreduce(grads, n)
+    pg.barrier()
+    torch.cuda.synchronize()
+    assert torch.equal(grads, before)
+    params.copy_(torch.randn(n, device=DEV, generator=g))
+    split = 4096 * 3
+    ref = [params[:split].clone().requires_grad_(True), params[split:n - 64].clone().requires_grad_(True)]
+    opt = torch.optim.Adam([{"params": [ref[0]], "lr": 0.05}, {"params": [ref[1]], "lr": 1e-3}])
+    fsa = par.FusedShardedAdam(pg, params, grads, n, [(0, split, 0.05), (split, n - 64, 1e-3)])
+    tail = params[n - 64:].clone()
+    for it in range(4):
+        gr = torch.randn(n, device=DEV, generator=g) * (0.1 + it)
+        grads.copy_(gr)
+        ref[0].grad = gr[:split].clone(); ref[1].grad = gr[split:n - 64].clone()
+        opt.step()
+        fsa.step()
+    torch.cuda.synchronize()
+    assert rel_err(params[:split].cpu(), ref[0].detach().cpu()) < 1e-6
+    assert rel_err(params[split:n - 64].cpu(), ref[1].detach().cpu()) < 1e-6
+    assert torch.equal(params[n - 64:], tail)            # floats outside every learning-rate range are left untouched

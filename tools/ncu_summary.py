@@ -55,5 +55,37 @@ def raw(path):
         print("  top stalls (warps per issue):", ", ".join(f"{k}={v:.2f}" for k, v in sorted(st, key=lambda x: -x[1])[:6]))
 
 
+def traffic(path):
+    """JSON for bench.py (profiles/rNN_traffic.json): per kernel and launch, the DRAM bytes and the L1TEX / L2 sector counts
+    that its L2 / L1TEX / atomic fractions are computed from."""
+    import json
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]
+    ci = {h: i for i, h in enumerate(hdr)}
+    names = {"field_fwd_kernel<1, 1>": "usl_field_fwd", "field_fwd_kernel<(bool)1, (bool)1>": "usl_field_fwd", "field_bwd2_kernel": "usl_field_bwd",
+             "sdf_query_grid_kernel": "usl_sdf_query_grid", "field_fwd_kernel<0, 0>": "usl_field_fwd_render",
+             "field_fwd_kernel<(bool)0, (bool)0>": "usl_field_fwd_render", "field_fwd_kernel<1, 0>": "usl_field_fwd_tracking",
+             "field_fwd_kernel<(bool)1, (bool)0>": "usl_field_fwd_tracking"}
+    get = lambda r, k: float(r[ci[k]].replace(",", "")) if k in ci and r[ci[k]] not in ("", "n/a") else 0.0
+    out = {"_source": f"ncu --set full capture, {path} (per launch)"}
+    for r in rows[2:]:
+        kn = r[ci["Kernel Name"]]
+        key = next((v for k, v in names.items() if k in kn), None)
+        if key is None or key in out:
+            continue
+        unit = rows[1][ci["dram__bytes_read.sum"]] if "dram__bytes_read.sum" in ci else "byte"
+        mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        out[key] = {
+            "duration_us_under_ncu": get(r, "gpu__time_duration.sum"),
+            "dram_bytes": (get(r, "dram__bytes_read.sum") + get(r, "dram__bytes_write.sum")) * mul,
+            "lts_sectors_read": get(r, "lts__t_sectors_srcunit_tex_op_read.sum"), "lts_sectors_write": get(r, "lts__t_sectors_srcunit_tex_op_write.sum"),
+            "lts_sectors_red": get(r, "lts__t_sectors_srcunit_tex_op_red.sum"),
+            "l1_sector_lookups_ld": get(r, "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"),
+            "l1_sectors_red": get(r, "l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum"),
+            "warp_instructions": get(r, "smsp__inst_executed.sum"), "registers": get(r, "launch__registers_per_thread"),
+        }
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "raw": raw, "traffic": traffic}[sys.argv[1]](sys.argv[2])

@@ -65,7 +65,7 @@ class RaySetup(Structure):
                 ("bound", Bound), ("require_depth", c_int32), ("_pad2", c_int32),
                 ("zs", ZSampleArgs), ("t_rand", c_void_p), ("n_rays", c_int64),
                 ("rays_o", c_void_p), ("rays_d", c_void_p), ("gt_depth", c_void_p), ("gt_color", c_void_p), ("dirs_out", c_void_p),
-                ("frame_id", c_void_p), ("valid", c_void_p), ("z", c_void_p), ("pixel_begin", c_int64)]
+                ("frame_id", c_void_p), ("valid", c_void_p), ("z", c_void_p), ("pixel_begin", c_int64), ("ray_offset", c_int64)]
 
 
 class LossArgs(Structure):
@@ -76,6 +76,14 @@ class LossArgs(Structure):
 class AdamGroup(Structure):
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("n", c_int64),
                 ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float)]
+
+
+class Peers(Structure):
+    _fields_ = [("rank", c_int32), ("world", c_int32), ("buf", c_void_p * 8), ("ctrl", c_void_p * 8)]
+
+
+class AdamRange(Structure):
+    _fields_ = [("begin", c_int64), ("end", c_int64), ("lr", c_float), ("_pad", c_float)]
 
 
 ADAM_MAX_GROUPS = 24
@@ -115,10 +123,17 @@ _SIGS = {
     "usl_composite_loss_bwd": [POINTER(LossArgs), _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, POINTER(Bound),
                                _P, _P, _P, _P, _P, _P],
     "usl_adam_step": [POINTER(AdamGroup), c_int, c_int64, _P, c_int, _P],
+    "usl_exchange_sums": [POINTER(Peers), _P, _P],
+    "usl_peer_barrier": [POINTER(Peers), _P],
+    "usl_allreduce_sum": [POINTER(Peers), c_int64, c_int64, _P],
+    "usl_allreduce_adam_slice_floats": [c_int, c_int64, POINTER(c_int64)],
+    "usl_allreduce_adam_step": [POINTER(Peers), POINTER(c_void_p), c_int64, c_int64, _P, _P, POINTER(AdamRange), c_int, c_float, c_float, c_float,
+                                c_int64, _P, _P],
+    "usl_bench_stream_read": [_P, c_int64, c_int, _P, _P],
     "usl_bench_gather": [_P, c_uint32, c_int64, c_int, _P, _P],
     "usl_bench_scatter": [_P, c_uint32, c_int64, c_int, c_int, _P],
 }
-EXPORTS = ["usl_last_error", "usl_version"] + list(_SIGS)
+EXPORTS = ["usl_last_error", "usl_version", "usl_peer_ctrl_bytes"] + list(_SIGS)
 
 _lib = None
 
@@ -137,6 +152,8 @@ def load():
     lib.usl_last_error.argtypes = []
     lib.usl_version.restype = c_int
     lib.usl_version.argtypes = []
+    lib.usl_peer_ctrl_bytes.restype = c_int
+    lib.usl_peer_ctrl_bytes.argtypes = []
     for name, sig in _SIGS.items():
         fn = getattr(lib, name)
         fn.restype = c_int
@@ -151,7 +168,7 @@ LAUNCHES = 0   # number of kernel-launching C-ABI calls made so far (bench.py re
 def call(name, *args):
     global LAUNCHES
     lib = load()
-    if name not in ("usl_grid_build", "usl_field_bwd_scratch_floats", "usl_field_stash_floats"):
+    if name not in ("usl_grid_build", "usl_field_bwd_scratch_floats", "usl_field_stash_floats", "usl_allreduce_adam_slice_floats"):
         LAUNCHES += 1
     rc = getattr(lib, name)(*args)
     if rc != 0:

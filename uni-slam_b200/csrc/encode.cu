@@ -110,6 +110,21 @@ __global__ void __launch_bounds__(256) bench_gather_kernel(const float2 *__restr
     if (ax == 123.456f) out[i] = ax + ay;            // keep the loads alive
 }
 
+// Coalesced 16-byte reads of a buffer, `repeats` passes: with a buffer that fits L2 this measures the L2 -> SM read
+// bandwidth (the first pass warms it), with a larger one the HBM read bandwidth.
+__global__ void __launch_bounds__(256) bench_stream_read_kernel(const float4 *__restrict__ buf, int64_t n4, int repeats,
+                                                                float *__restrict__ out) {
+    float acc = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < repeats; ++r) {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 3 * stride < n4; i += 4 * stride) {
+            const float4 a = __ldcg(buf + i), b = __ldcg(buf + i + stride), c = __ldcg(buf + i + 2 * stride), d = __ldcg(buf + i + 3 * stride);
+            acc += (a.x + a.y + a.z + a.w) + (b.x + b.y + b.z + b.w) + (c.x + c.y + c.z + c.w) + (d.x + d.y + d.z + d.w);
+        }
+    }
+    if (acc == 123.456f) out[0] = acc;                   // keep the loads alive
+}
+
 // mode 0: every lane its own random entry; 1: lane pairs share a 16 B slot; 3: lane quads share a 32 B sector;
 // 4: a warp covers 32 consecutive entries; 2: one float4 atomic per lane at a random 16 B slot
 __global__ void __launch_bounds__(256) bench_scatter_kernel(float2 *__restrict__ table, uint32_t entries, int64_t n,
@@ -204,6 +219,15 @@ int usl_grid_encode_bwd_input(const usl_grid_t *g, const float *params, const fl
     encode_bwd_input_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         *g, (const float2 *)params, x, (const float2 *)dy, n, dx);
     return check_launch("usl_grid_encode_bwd_input");
+}
+
+int usl_bench_stream_read(const float *buf, int64_t n_floats, int repeats, float *out, usl_stream_t stream) {
+    if (!buf || n_floats < 4 || repeats < 1) { set_error("usl_bench_stream_read: bad arguments"); return 1; }
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    bench_stream_read_kernel<<<(unsigned)(n_sm * 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(buf), n_floats / 4, repeats, out);
+    return check_launch("usl_bench_stream_read");
 }
 
 int usl_bench_gather(const float *table, uint32_t entries, int64_t n_threads, int per_thread, float *out,

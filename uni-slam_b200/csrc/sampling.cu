@@ -179,7 +179,7 @@ __global__ void ray_setup_kernel(const __grid_constant__ usl_ray_setup_t A) {
             int frame = 0;
             if (A.mode == 0) {
                 int b = 0;
-                int64_t m = r;
+                int64_t m = r + A.ray_offset;                        // global ray slot (a rank of a sharded batch starts mid-list)
                 const int64_t n0 = (int64_t)A.batch[0].K * A.batch[0].n;
                 if (A.n_batches > 1 && m >= n0) { b = 1; m -= n0; }
                 const usl_ray_batch_t &B = A.batch[b];
@@ -270,7 +270,7 @@ __global__ void ray_setup_kernel(const __grid_constant__ usl_ray_setup_t A) {
         const float cur = out;
         const float lower = (k == 0) ? cur : __fmul_rn(0.5f, __fadd_rn(cur, zr[k - 1]));
         const float upper = (k == S - 1) ? cur : __fmul_rn(0.5f, __fadd_rn(zr[k + 1], cur));
-        out = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), A.t_rand[r * S + k]));
+        out = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), A.t_rand[(r + A.ray_offset) * S + k]));
     }
     A.z[r * S + k] = out;
 }
@@ -497,6 +497,12 @@ int usl_ray_setup(const usl_ray_setup_t *a, usl_stream_t stream) {
     const int S = a->zs.n_stratified + a->zs.n_importance;
     if (S < 2 || S > 128) { set_error("usl_ray_setup: n_stratified + n_importance must be in 2..128"); return 1; }
     if (a->mode == 0 && (a->n_batches < 1 || a->n_batches > 2)) { set_error("usl_ray_setup: 1 or 2 keyframe batches"); return 1; }
+    if (a->ray_offset != 0 && a->mode != 0) { set_error("usl_ray_setup: ray_offset is a mode-0 (keyframe batches) feature"); return 1; }
+    if (a->mode == 0) {
+        int64_t total = 0;
+        for (int b = 0; b < a->n_batches; ++b) total += (int64_t)a->batch[b].K * a->batch[b].n;
+        if (a->ray_offset < 0 || a->ray_offset + a->n_rays > total) { set_error("usl_ray_setup: ray range outside the batches"); return 1; }
+    }
     if (a->mode == 1 && (a->H0 < 0 || a->H1 > a->H || a->W0 < 0 || a->W1 > a->W || a->H1 <= a->H0 || a->W1 <= a->W0)) { set_error("usl_ray_setup: bad window"); return 1; }
     if (a->mode == 2 && (a->pixel_begin < 0 || a->pixel_begin + a->n_rays > (int64_t)a->H * a->W || !a->depth_img)) { set_error("usl_ray_setup: pixel range outside the frame"); return 1; }
     if (a->mode != 2 && (!a->gt_color || !a->dirs_out)) { set_error("usl_ray_setup: gt_color / dirs_out are required in modes 0 and 1"); return 1; }

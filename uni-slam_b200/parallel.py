@@ -7,10 +7,13 @@
 * dense SDF query: y-slabs of the (ny, nx, nz) volume, no data-path collective, slabs gathered to rank 0.
 * tracking: replicas only (single GPU, BASELINE.json north_star).
 """
-from typing import Tuple
+from ctypes import byref, c_int64, c_void_p
+from typing import Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+from . import _lib as L
 
 
 def slab_range(ny: int, rank: int, world: int) -> Tuple[int, int]:
@@ -18,6 +21,126 @@ def slab_range(ny: int, rank: int, world: int) -> Tuple[int, int]:
     base, rem = divmod(ny, world)
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+class PeerGroup:
+    """Peer-mapped (symmetric) memory for the hand-written exchange kernels of csrc/collective.cu.
+
+    torch.distributed's symmetric-memory allocator is the plumbing: one allocation + rendezvous per buffer maps every
+    rank's copy into every rank's address space (CUDA IPC over NVLink / NVSwitch).  The kernels then read and write the
+    peers' buffers directly; NCCL is not called on the iteration's critical path.
+
+      alloc(numel)          zero-filled fp32 symmetric tensor (pass as MappingStep(grad_alloc=pg.alloc): the flat gradient buffer)
+      exchange_sums(acc)    usl_exchange_sums: the 16 loss sums / counts become global (between loss_fwd and the backward)
+      allreduce(t, n)       usl_allreduce_sum over the first n floats of a tensor obtained from alloc()
+      FusedShardedAdam      usl_allreduce_adam_step (see below)
+    """
+
+    def __init__(self, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._sm = symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.gname = self.group.group_name
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 8:
+            raise RuntimeError("PeerGroup: at most 8 ranks (one NVSwitch domain)")
+        self.device = device
+        self._handles = {}
+        nb = L.load().usl_peer_ctrl_bytes()
+        self.ctrl = self._symm_zeros(nb // 4)
+        self._ctrl_ptrs = self._handles[self.ctrl.data_ptr()].buffer_ptrs
+
+    @classmethod
+    def single(cls, device):
+        """World of one rank without torch.distributed: the 'peers' are this process's own buffers.  The kernels run
+        unchanged (used by the single-GPU tests of collective.cu and by callers that want one code path for N = 1)."""
+        self = cls.__new__(cls)
+        self._sm, self.group, self.gname, self.rank, self.world, self.device = None, None, None, 0, 1, device
+        self._handles = {}
+        self.ctrl = self._symm_zeros(L.load().usl_peer_ctrl_bytes() // 4)
+        self._ctrl_ptrs = self._handles[self.ctrl.data_ptr()].buffer_ptrs
+        return self
+
+    def _symm_zeros(self, numel):
+        if self._sm is None:                               # single(): plain device memory
+            t = torch.zeros(int(numel), dtype=torch.float32, device=self.device)
+            self._handles[t.data_ptr()] = type("LocalHandle", (), {"buffer_ptrs": [t.data_ptr()]})()
+            return t
+        t = self._sm.empty(int(numel), dtype=torch.float32, device=self.device)
+        h = self._sm.rendezvous(t, group=self.gname)
+        t.zero_()
+        torch.cuda.synchronize()
+        dist.barrier(self.group)                       # nobody touches a peer's buffer before it is zeroed
+        self._handles[t.data_ptr()] = h
+        return t
+
+    def alloc(self, numel):
+        return self._symm_zeros(numel)
+
+    def peers(self, t: torch.Tensor) -> L.Peers:
+        """usl_peers_t for a tensor obtained from alloc(): every rank's copy of it + the control blocks."""
+        h = self._handles.get(t.data_ptr())
+        if h is None:
+            raise ValueError("PeerGroup.peers: tensor was not allocated by this PeerGroup")
+        P = L.Peers()
+        P.rank, P.world = self.rank, self.world
+        for p in range(self.world):
+            P.buf[p] = h.buffer_ptrs[p]
+            P.ctrl[p] = self._ctrl_ptrs[p]
+        return P
+
+    def exchange_sums(self, acc: torch.Tensor):
+        P = self.peers(self.ctrl)
+        L.call("usl_exchange_sums", byref(P), L.ptr(acc), L.stream())
+
+    def allreduce(self, t: torch.Tensor, n_floats: int, offset_floats: int = 0):
+        P = self.peers(t)
+        L.call("usl_allreduce_sum", byref(P), int(offset_floats), int(n_floats), L.stream())
+
+    def barrier(self):
+        P = self.peers(self.ctrl)
+        L.call("usl_peer_barrier", byref(P), L.stream())
+
+
+class FusedShardedAdam:
+    """usl_allreduce_adam_step: gradient reduction, Adam and parameter broadcast in one pass over peer memory.
+
+    ``params`` and ``grads`` are flat symmetric buffers of the same layout (PeerGroup.alloc); ``ranges`` = [(begin, end, lr)]
+    in floats gives the learning rate of each stretch of the layout (the groups of Mapper.create_optimizer,
+    src/Mapper.py:111-139); rank r owns slice r of the buffers and keeps Adam state for that slice only."""
+
+    def __init__(self, pg: PeerGroup, params: torch.Tensor, grads: torch.Tensor, n_floats: int, ranges: Sequence[Tuple[int, int, float]],
+                 betas=(0.9, 0.999), eps=1e-8):
+        self.pg, self.params, self.grads, self.n = pg, params, grads, int(n_floats)
+        sl = c_int64(0)
+        L.call("usl_allreduce_adam_slice_floats", pg.world, self.n, byref(sl))
+        self.exp_avg = torch.zeros(sl.value, device=params.device, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(sl.value, device=params.device, dtype=torch.float32)
+        self.ranges = (L.AdamRange * len(ranges))()
+        for a, (b, e, lr) in zip(self.ranges, ranges):
+            a.begin, a.end, a.lr = int(b), int(e), float(lr)
+        self.betas, self.eps = betas, eps
+        self.step_dev = torch.zeros((1,), device=params.device, dtype=torch.int64)
+        hp = pg._handles[params.data_ptr()]
+        self._pptrs = (c_void_p * 8)(*[hp.buffer_ptrs[p] for p in range(pg.world)] + [None] * (8 - pg.world))
+
+    @torch.no_grad()
+    def step(self):
+        self.step_dev += 1                                            # device-side step count: CUDA-graph replayable
+        P = self.pg.peers(self.grads)
+        L.call("usl_allreduce_adam_step", byref(P), self._pptrs, 0, self.n, L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), self.ranges,
+               len(self.ranges), self.betas[0], self.betas[1], self.eps, 0, L.ptr(self.step_dev), L.stream())
+
+
+def attach_peer_collectives(step, pg: PeerGroup):
+    """Wire the hand-written exchange steps onto a MappingStep whose gradient buffer came from pg.alloc.  Returns
+    reduce_grads(), to be called after step.run(): one usl_allreduce_sum over [tables | decoders | beta | poses]."""
+    step.acc_hook = pg.exchange_sums
+    fs = step.fs
+
+    def reduce_grads():
+        pg.allreduce(fs.g_all, fs.n_grad_padded)
+    return reduce_grads
 
 
 def attach_mapping_collectives(step, group=None, overlap: bool = False):

@@ -57,7 +57,7 @@ class _FieldState:
     """Tables + decoder tensors + beta, their packed descriptor and persistent gradient buffers."""
 
     def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec: Sequence[torch.Tensor], beta: torch.Tensor,
-                 with_grads: bool, max_frames: int = 1):
+                 with_grads: bool, max_frames: int = 1, grad_alloc=None):
         self.meta, self.sdf_table, self.rgb_table, self.dec, self.beta = meta, sdf_table, rgb_table, list(dec), beta
         self.field = meta.pack(sdf_table, rgb_table, self.dec)
         if with_grads:
@@ -68,7 +68,9 @@ class _FieldState:
             sizes = [sdf_table.numel(), rgb_table.numel()] + [t.numel() for t in self.dec] + [1, max_frames * 7]   # ..., beta, d pose
             pad = (-sum(sizes)) % 32                                  # keep the scratch block 128-byte aligned (16-byte vector atomics)
             sizes += [pad, max(n_scratch, 4), L.LOSS_SLOTS, max_frames * 12]   # + loss accumulators + d c2w: one memset clears all
-            self.g_all = torch.zeros(sum(sizes), device=sdf_table.device, dtype=torch.float32)
+            # grad_alloc(numel) -> zero-filled fp32 tensor: multi-GPU runs hand out peer-mapped (symmetric) memory here so that
+            # the exchange kernels of collective.cu can read / write every rank's buffer directly (parallel.PeerGroup)
+            self.g_all = grad_alloc(sum(sizes)) if grad_alloc is not None else torch.zeros(sum(sizes), device=sdf_table.device, dtype=torch.float32)
             views, o = [], 0
             for s_ in sizes:
                 views.append(self.g_all[o:o + s_])
@@ -81,6 +83,7 @@ class _FieldState:
             self.acc = views[-2]
             self.d_c2w = views[-1].view(max_frames, 12)
             self.n_grad = sum(sizes[:-4])
+            self.n_grad_padded = sum(sizes[:-3])                     # + the zero pad: a multiple of 32 floats (16-byte vector exchange)
             self.g_grads = self.g_all[:self.n_grad]                  # what a multi-GPU all-reduce must sum
             self.g_flat = self.g_all[sizes[0] + sizes[1]:self.n_grad]   # decoder + beta + pose gradients
             self.g_mlp = meta.pack_grads(self.g_dec)
@@ -110,9 +113,9 @@ class MappingStep(_Profiled):
 
     def __init__(self, meta: ops.FieldMeta, sdf_table, rgb_table, dec, beta, *, n_stratified, n_importance, truncation,
                  weights=(5.0, 200.0, 10.0, 0.1, 5.0), max_rays: int, max_frames: int = 1, perturb: bool = True,
-                 mask_mode: str = "original"):
+                 mask_mode: str = "original", grad_alloc=None):
         dev = sdf_table.device
-        self.fs = _FieldState(meta, sdf_table, rgb_table, dec, beta, with_grads=True, max_frames=max_frames)
+        self.fs = _FieldState(meta, sdf_table, rgb_table, dec, beta, with_grads=True, max_frames=max_frames, grad_alloc=grad_alloc)
         self.zs = ops.ZSampler(n_stratified, n_importance, truncation, dev)
         self.S = self.zs.S
         self.perturb = perturb
@@ -158,10 +161,12 @@ class MappingStep(_Profiled):
         return dict(dec=self.fs.g_dec, beta=self.fs.g_beta, sdf_table=self.fs.g_sdf_table, rgb_table=self.fs.g_rgb_table)
 
     def run(self, batches, t_rand, t_rand_uni=None, u_pdf=None, cam_poses: Optional[torch.Tensor] = None,
-            c2w_fixed: Optional[torch.Tensor] = None, has_holes: bool = True):
+            c2w_fixed: Optional[torch.Tensor] = None, has_holes: bool = True, ray_range=None):
         """batches: list of (c2ws|None, depths (K,P), colors (K,P,3), dirs_cam (K,P,3), indices (K*n,), n, frame_base).
         When cam_poses (K-1,7) is given (joint_opt, Mapper.py:372-376) the camera matrices are rebuilt on
-        device as cat(c2w_fixed[None], pose_to_matrix(cam_poses)) and pose gradients land in self.d_pose."""
+        device as cat(c2w_fixed[None], pose_to_matrix(cam_poses)) and pose gradients land in self.d_pose.
+        ray_range = (begin, end): process only that contiguous slice of the batch's global ray list (multi-GPU strong
+        scaling, SURVEY 8e: every rank holds the same draws and takes its slice); the draws stay indexed by GLOBAL ray slot."""
         st = stream()
         fs, S = self.fs, self.S
         fs.refresh()
@@ -201,18 +206,27 @@ class MappingStep(_Profiled):
             b_.dirs_cam, b_.indices = cptr(dirs_cam, f32, Kb * P * 3, "dirs_cam"), cptr(indices, i64, Kb * n, "indices")
             b_.P, b_.K, b_.n, b_.frame_base = P, Kb, n, frame_base
             R += Kb * n
+        R_global, ray_off = R, 0
+        if ray_range is not None:
+            ray_off, ray_end = int(ray_range[0]), int(ray_range[1])
+            if not 0 <= ray_off <= ray_end <= R_global:
+                raise ValueError(f"MappingStep: ray_range {ray_range} outside the batch of {R_global} rays")
+            R = ray_end - ray_off
         if R > self.max_rays:
             raise RuntimeError(f"MappingStep: {R} rays requested, buffers sized for max_rays={self.max_rays}")
         if self.perturb:
-            cptr(t_rand, f32, R * S, "t_rand (R,S)")
+            cptr(t_rand, f32, R_global * S, "t_rand (R,S)")
         if has_holes:
             if u_pdf is None or (self.perturb and t_rand_uni is None):
                 raise ValueError("MappingStep: rays without sensor depth need the draws of the no-depth branch "
                                  "(t_rand_uni (R,n_stratified), u_pdf (R,n_importance); Renderer.py:103-130); "
                                  "pass has_holes=False only if every sampled pixel has depth > 0")
-            cptr(u_pdf, f32, R * self.zs.n_importance, "u_pdf (R,n_importance)")
+            cptr(u_pdf, f32, R_global * self.zs.n_importance, "u_pdf (R,n_importance)")
             if self.perturb:
-                cptr(t_rand_uni, f32, R * self.zs.n_stratified, "t_rand_uni (R,n_stratified)")
+                cptr(t_rand_uni, f32, R_global * self.zs.n_stratified, "t_rand_uni (R,n_stratified)")
+            if ray_off:                                     # rows of this rank's slice (contiguous)
+                u_pdf = u_pdf[ray_off:ray_off + R]
+                t_rand_uni = t_rand_uni[ray_off:ray_off + R] if t_rand_uni is not None else None
         if joint:
             cptr(cam_poses, f32, (K - 1) * 7, "cam_poses (K-1,7)"); cptr(c2w_fixed, f32, 12, "c2w_fixed")
         self.n_rays = R
@@ -221,7 +235,7 @@ class MappingStep(_Profiled):
         rs.c2w_fixed = ptr(c2w_fixed) if joint else None
         rs.bound, rs.require_depth, rs.zs = fs.meta.bound, 0, self.zs.args
         rs.t_rand = ptr(t_rand) if self.perturb else None
-        rs.n_rays = R
+        rs.n_rays, rs.ray_offset = R, ray_off
         rs.rays_o, rs.rays_d, rs.gt_depth, rs.gt_color, rs.dirs_out = v(self.rays_o), v(self.rays_d), v(self.gt_depth), v(self.gt_color), v(self.dirs)
         rs.frame_id, rs.valid, rs.z = v(self.frame_id), v(self.valid), v(self.z)
         self._call("usl_ray_setup", byref(rs), st)
