@@ -335,6 +335,7 @@ def run_ours(args, rank, world, local_rank):
         k["gbs"] = k["alg_bytes"] / sec / 1e9 if sec else None
         k["frac"] = k["gbs"] / peak if k["gbs"] else None
         t = traffic.get(name) if args.config == "replica_room0" else None     # the ncu capture is of the replica workload
+        t = t if isinstance(t, dict) else None
         k["dram_traffic_bytes_ncu"] = t.get("dram_bytes") if t else None
         if t and sec:
             l2_bytes = 32.0 * (t["lts_sectors_read"] + t["lts_sectors_write"] + t["lts_sectors_red"])
