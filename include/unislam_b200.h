@@ -333,6 +333,8 @@ typedef struct usl_peers {
     int32_t rank, world;
     void *buf[USL_MAX_PEERS];             /* buf[p]: rank p's flat gradient buffer as mapped HERE (buf[rank] = the local one) */
     void *ctrl[USL_MAX_PEERS];            /* ctrl[p]: rank p's control block as mapped here */
+    void *mc;                             /* multicast (NVLS) mapping of the same buffer, or NULL: when set, the reductions run as
+                                           * multimem.ld_reduce (summed inside the NVSwitch) + multimem.st (replicated by the switch) */
 } usl_peers_t;
 USL_API int usl_peer_ctrl_bytes(void);
 /* acc[USL_LOSS_SLOTS] (device, local) <- sum over ranks of acc: the loss sums / counts of usl_loss_fwd become global, so
@@ -346,14 +348,15 @@ USL_API int usl_allreduce_sum(const usl_peers_t *P, int64_t offset_floats, int64
  * (no weight decay / amsgrad) to its slice of the parameters and pushes the NEW PARAMETERS to every rank's param[p]
  * (same flat layout as the gradient buffers).  exp_avg / exp_avg_sq: this rank's state for its own slice only
  * (usl_allreduce_adam_slice_floats() floats each, zero-initialised).  ranges: learning rate per [begin,end) of the flat
- * layout (floats outside every range are left untouched).  step / step_dev as in usl_adam_step. */
+ * layout (floats outside every range are left untouched).  param_mc: multicast mapping of the parameter buffers (or NULL).
+ * step / step_dev as in usl_adam_step. */
 #define USL_ADAM_MAX_RANGES 8
 typedef struct usl_adam_range {
     int64_t begin, end;
     float lr, _pad;
 } usl_adam_range_t;
 USL_API int usl_allreduce_adam_slice_floats(int world, int64_t n_floats, int64_t *slice_floats);
-USL_API int usl_allreduce_adam_step(const usl_peers_t *P, float *const *param, int64_t offset_floats, int64_t n_floats,
+USL_API int usl_allreduce_adam_step(const usl_peers_t *P, float *const *param, float *param_mc, int64_t offset_floats, int64_t n_floats,
                                     float *exp_avg, float *exp_avg_sq, const usl_adam_range_t *ranges, int n_ranges,
                                     float beta1, float beta2, float eps, int64_t step, const int64_t *step_dev,
                                     usl_stream_t stream);

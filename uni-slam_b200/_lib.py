@@ -79,7 +79,7 @@ class AdamGroup(Structure):
 
 
 class Peers(Structure):
-    _fields_ = [("rank", c_int32), ("world", c_int32), ("buf", c_void_p * 8), ("ctrl", c_void_p * 8)]
+    _fields_ = [("rank", c_int32), ("world", c_int32), ("buf", c_void_p * 8), ("ctrl", c_void_p * 8), ("mc", c_void_p)]
 
 
 class AdamRange(Structure):
@@ -127,7 +127,7 @@ _SIGS = {
     "usl_peer_barrier": [POINTER(Peers), _P],
     "usl_allreduce_sum": [POINTER(Peers), c_int64, c_int64, _P],
     "usl_allreduce_adam_slice_floats": [c_int, c_int64, POINTER(c_int64)],
-    "usl_allreduce_adam_step": [POINTER(Peers), POINTER(c_void_p), c_int64, c_int64, _P, _P, POINTER(AdamRange), c_int, c_float, c_float, c_float,
+    "usl_allreduce_adam_step": [POINTER(Peers), POINTER(c_void_p), _P, c_int64, c_int64, _P, _P, POINTER(AdamRange), c_int, c_float, c_float, c_float,
                                 c_int64, _P, _P],
     "usl_bench_stream_read": [_P, c_int64, c_int, _P, _P],
     "usl_bench_gather": [_P, c_uint32, c_int64, c_int, _P, _P],

@@ -34,9 +34,12 @@ class PeerGroup:
       exchange_sums(acc)    usl_exchange_sums: the 16 loss sums / counts become global (between loss_fwd and the backward)
       allreduce(t, n)       usl_allreduce_sum over the first n floats of a tensor obtained from alloc()
       FusedShardedAdam      usl_allreduce_adam_step (see below)
-    """
 
-    def __init__(self, device, group=None):
+    use_multicast=True runs the reductions through the NVSwitch (multimem.ld_reduce / multimem.st on the allocator's
+    multicast mapping).  Measured on this pool's B200 boxes for the 51.6 MB gradient buffer: N = 2: 176 us vs 111 us for
+    the peer-to-peer form, N = 4: 169 us vs 155 us (NCCL: 120 / 156 us) -- so the default is peer-to-peer loads / stores."""
+
+    def __init__(self, device, group=None, use_multicast: bool = False):
         import torch.distributed._symmetric_memory as symm_mem
         self._sm = symm_mem
         self.group = group if group is not None else dist.group.WORLD
@@ -46,6 +49,7 @@ class PeerGroup:
             raise RuntimeError("PeerGroup: at most 8 ranks (one NVSwitch domain)")
         self.device = device
         self._handles = {}
+        self.use_multicast = use_multicast
         nb = L.load().usl_peer_ctrl_bytes()
         self.ctrl = self._symm_zeros(nb // 4)
         self._ctrl_ptrs = self._handles[self.ctrl.data_ptr()].buffer_ptrs
@@ -57,6 +61,7 @@ class PeerGroup:
         self = cls.__new__(cls)
         self._sm, self.group, self.gname, self.rank, self.world, self.device = None, None, None, 0, 1, device
         self._handles = {}
+        self.use_multicast = False
         self.ctrl = self._symm_zeros(L.load().usl_peer_ctrl_bytes() // 4)
         self._ctrl_ptrs = self._handles[self.ctrl.data_ptr()].buffer_ptrs
         return self
@@ -87,7 +92,14 @@ class PeerGroup:
         for p in range(self.world):
             P.buf[p] = h.buffer_ptrs[p]
             P.ctrl[p] = self._ctrl_ptrs[p]
+        P.mc = self.multicast_ptr(t) if self.use_multicast else None
         return P
+
+    def multicast_ptr(self, t: torch.Tensor):
+        """NVLS multicast mapping of a buffer from alloc() (None when the fabric / allocator offers none)."""
+        h = self._handles.get(t.data_ptr())
+        mc = getattr(h, "multicast_ptr", 0) if h is not None else 0
+        return int(mc) if mc else None
 
     def exchange_sums(self, acc: torch.Tensor):
         P = self.peers(self.ctrl)
@@ -128,7 +140,7 @@ class FusedShardedAdam:
     def step(self):
         self.step_dev += 1                                            # device-side step count: CUDA-graph replayable
         P = self.pg.peers(self.grads)
-        L.call("usl_allreduce_adam_step", byref(P), self._pptrs, 0, self.n, L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), self.ranges,
+        L.call("usl_allreduce_adam_step", byref(P), self._pptrs, self.pg.multicast_ptr(self.params) if self.pg.use_multicast else None, 0, self.n, L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), self.ranges,
                len(self.ranges), self.betas[0], self.betas[1], self.eps, 0, L.ptr(self.step_dev), L.stream())
 
 
