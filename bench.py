@@ -461,6 +461,10 @@ def run_ours(args, rank, world, local_rank):
         e1.record(); torch.cuda.synchronize()
         extra["fused_adam_ms_per_step"] = e0.elapsed_time(e1) / 10     # usl_adam_step (f1)
         extra.update(bench_tracking(P, wl, meta, tabs, dec, beta, cfg, dev, args))
+    if rank == 0 and world == 1 and not args.no_extras:
+        if args.config == "replica_room0":
+            extra.update(bench_scannet_mapping(P, dev, args))
+        extra.update(bench_slam_loop(P, cfg, dev, args))
     dq = bench_dense_query(P, wl, meta, tabs, dec, dev, rank, world, dist)      # every rank: its y-slab
     ri = bench_render_img(P, cfg, meta, tabs, dec, beta, dev, rank, world, dist)  # every rank: its rows of the frame
     if rank == 0:
@@ -657,6 +661,88 @@ def multi_gpu_legs(args, P, par, pg, step, wl, one_step, mode, flat_idx, flat_u,
     return out
 
 
+def bench_scannet_mapping(P, dev, args):
+    """BASELINE config 3 in the driver-run line: the ScanNet-shaped mapping iteration (620x460 frames, 5982 rays x 56 samples,
+    nn.Linear decoders with two hidden layers, 2^16 tables), graph-replayed and timed like the headline."""
+    wlmod = importlib.import_module("uni-slam_b200.workload")
+    cfg = P.synthetic.CONFIGS["scannet_scene0000"]
+    wl = wlmod.build_mapping_workload(cfg, dev, seed=1)
+    meta, tabs, dec, beta = wlmod.init_field_tensors(cfg, wl.bound, wl.per_level_scale, dev, seed=0)
+    R, S = wl.n_rays, wl.S
+    step = P.MappingStep(meta, tabs[0], tabs[1], dec, beta, n_stratified=cfg.n_stratified, n_importance=cfg.n_importance,
+                         truncation=cfg.truncation, max_rays=R, max_frames=wl.K)
+    cam_poses = wl.cam_poses.clone()
+    params = [tabs[0], tabs[1], beta] + dec + [cam_poses]
+    grads = [step.fs.g_sdf_table, step.fs.g_rgb_table, step.fs.g_beta] + step.fs.g_dec + [step.d_pose[:wl.K - 1]]
+    for p_, g_ in zip(params, grads):
+        p_.requires_grad_(True); p_.grad = g_
+    opt = P.FusedAdam([{"params": dec + [beta], "lr": 1e-3}, {"params": [tabs[0], tabs[1]], "lr": cfg.hash_lr}, {"params": [cam_poses], "lr": 1e-3}])
+    gen = torch.Generator(device=dev).manual_seed(5)
+    flat_idx, flat_u, bufs = wl.alloc_draws()
+
+    def one():
+        flat_idx.random_(0, wl.P, generator=gen); flat_u.uniform_(generator=gen)
+        step.run(wl.batches(bufs[0], bufs[1]), bufs[2], bufs[3], bufs[4], cam_poses=cam_poses.detach(), c2w_fixed=wl.c2ws[0])
+    for _ in range(min(args.prefit, 30)):
+        one(); opt.step()
+    run, graph = one, None
+    if not args.no_graph:
+        try:
+            s_ = torch.cuda.Stream(); s_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_):
+                one(); one()
+            torch.cuda.current_stream().wait_stream(s_); torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph(); graph.register_generator_state(gen)
+            with torch.cuda.graph(graph):
+                one()
+            run = graph.replay
+        except Exception as e:                                           # noqa: BLE001
+            print(f"[bench] scannet graph capture failed ({e}); eager", file=sys.stderr); graph = None; torch.cuda.synchronize()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record(); evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    step.profile = True; step.events = {}
+    for _ in range(5):
+        flush.zero_(); one()
+    torch.cuda.synchronize()
+    kms = step.kernel_ms()
+    peak, _ = _peaks()
+    alg = R * S * (2 * 1024 + 16)
+    out = {"scannet_workload": f"scannet_scene0000 mapping iteration: {wl.K}-frame window, {R} rays x {S} samples, joint_opt, decoder variant A, fp32",
+           "scannet_ms_per_step": ms, "scannet_value": R * S / (ms * 1e-3), "scannet_loss": float(step.loss), "scannet_kernel_ms": kms}
+    for k_ in ("usl_field_fwd", "usl_field_bwd"):
+        if kms.get(k_):
+            out[f"scannet_{k_[4:]}_frac_of_hbm_peak"] = alg / (kms[k_] * 1e-3) / 1e9 / peak
+    del graph
+    return out
+
+
+def bench_slam_loop(P, cfg, dev, args):
+    """BASELINE config 2: the Tracker + Mapper loop (src/Tracker.py:271-372, src/Mapper.py:461-575) over a synthetic sequence of
+    >= 200 full-resolution frames on one GPU: frames/s, in-loop tracking iterations/s and mapping samples/s, trajectory error
+    against the analytic ground truth (a sanity number, not a parity claim).  Frames are rendered before the clock starts."""
+    slam = importlib.import_module("uni-slam_b200.slam")
+    n = args.slam_frames
+    if n <= 0:
+        return {}
+    r = slam.run_slam(cfg, n_frames=n, device=dev, scale_hw=1.0, pregenerate=True)
+    H, W = cfg.cam.H, cfg.cam.W
+    return {"slam_workload": f"{cfg.name}: {n} frames {W}x{H}, {cfg.track_iters} tracking iterations/frame x {cfg.track_pixels} rays, mapping every "
+                             f"{cfg.map_every} frames x {cfg.map_iters} iterations (eager launches, one process)",
+            "slam_frames": n, "slam_frames_per_s": r.frames_per_s, "slam_seconds": r.seconds, "slam_ate_rmse_m": r.ate_rmse,
+            "slam_ate_rmse_constant_velocity_prior_m": r.ate_rmse_no_tracking, "slam_tracking_iters": r.tracking_iters,
+            "slam_tracking_iters_per_s": r.tracking_iters / r.seconds, "slam_mapping_iters": r.mapping_iters,
+            "slam_mapping_samples_per_s": r.mapping_samples / r.seconds, "slam_loss_first_map": r.loss_first_map, "slam_loss_last_map": r.loss_last_map}
+
+
 def bench_tracking(P, wl, meta, tabs, dec, beta, cfg, dev, args):
     """Tracking iterations/s: optimize_tracking-equivalent iterations (2000-ray draw, fwd, loss, pose grad, Adam on 7 dof)."""
     cam = cfg.cam
@@ -832,8 +918,24 @@ def cpu_baseline_leg(wl, step, tabs, dec, beta, cam_poses, dev):
         if it > 0:
             times.append(time.perf_counter() - t0)
     val = wl_cpu.n_rays * wl_cpu.S * len(times) / sum(times)
-    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"3 full mapping iterations ({wl_cpu.n_rays} rays x {wl_cpu.S} samples) after 1 warm-up, oracle port, torch CPU fp32"}, parity
+    base = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"3 full mapping iterations ({wl_cpu.n_rays} rays x {wl_cpu.S} samples) after 1 warm-up, oracle port, torch CPU fp32"}
+    # one Tracker iteration and one 500k-point eval_points chunk on the same host cores
+    wl_t, field_t, pose, cam, e = F.oracle_tracking_setup(wl, tabs, dec, beta)
+    gt_ = torch.Generator().manual_seed(2)
+    tt = []
+    for it in range(4):
+        t0 = time.perf_counter()
+        F.oracle_tracking_iteration(wl_t, field_t, pose, cam, e, gt_)
+        if it > 0:
+            tt.append(time.perf_counter() - t0)
+    base["tracking_iters_per_s"] = len(tt) / sum(tt)
+    base["tracking_sample"] = f"3 tracking iterations ({wl.cfg.track_pixels} rays x {wl_cpu.S} samples, forward + loss + pose gradient) after 1 warm-up"
+    t0 = time.perf_counter()
+    m = F.oracle_dense_query_chunk(wl_t, field_t, 500000)
+    base["dense_query_points_per_s"] = m / (time.perf_counter() - t0)
+    base["dense_query_sample"] = f"one eval_points chunk of {m} points (points_batch_size 500000, Mesher.py:134-166), SDF grid + SDF decoder"
+    return base, parity
 
 
 def main():
@@ -850,6 +952,8 @@ def main():
                     help="workload: BASELINE configs[1] (default, the metric's config) or configs[2] (ScanNet-shaped; extra)")
     ap.add_argument("--overlap", action="store_true", help="N>1: all-reduce the colour-table gradient on a side stream while the sdf half of "
                     "field_bwd runs (measured SLOWER at N=2: 0.80 vs 0.75 ms/step -- NCCL's reduction and the atomics contend for L2)")
+    ap.add_argument("--slam-frames", type=int, default=200, help="frames of the full-resolution Tracker+Mapper loop leg (0 = skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the ScanNet-shaped mapping leg and the SLAM loop leg")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N>1: gradient / loss-sum exchange by the hand-written peer-memory kernels (csrc/collective.cu, default) or by NCCL")
     ap.add_argument("--quick", action="store_true", help="mapping step only (used under ncu): skip e2e / tracking / dense query / Adam / cpu baseline")

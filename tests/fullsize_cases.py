@@ -268,6 +268,57 @@ def run_tracking_fullsize(config_name, device="cuda:0", scale_hw=1.0):
     return res
 
 
+def oracle_tracking_setup(wl, tabs, dec, beta, device_pose_offset=True):
+    """CPU oracle field + one tracking problem (pose, window, draws) at the reference's size, for bench.py's CPU baseline."""
+    P = pkg()
+    wlmod = importlib.import_module("uni-slam_b200.workload")
+    wl_cpu = to_cpu(wl)
+    cfg = wl.cfg
+    col, dep, c2w = wl_cpu.cur_frame
+    H, W = dep.shape
+    sc = W / cfg.cam.W
+    cam = (H, W, cfg.cam.fx * sc, cfg.cam.fy * sc, cfg.cam.cx * sc, cfg.cam.cy * sc)
+    e = int(cfg.ignore_edge * sc)
+    field = oracle_field(wl_cpu, tabs, dec, beta)
+    for t in field.parameters():
+        t.requires_grad_(False)
+    pose = wlmod._matrix_to_cam_pose(c2w[None]).contiguous()
+    pose[:, 4:] += torch.tensor([0.012, -0.008, 0.005])
+    return wl_cpu, field, pose, cam, e
+
+
+def oracle_tracking_iteration(wl_cpu, field, pose, cam, e, gen):
+    """One Tracker.optimize_tracking iteration (src/Tracker.py:149-244) through oracle/path_ref on the host CPU: draw, forward,
+    loss, pose gradient."""
+    cfg = wl_cpu.cfg
+    H, W, fx, fy, cx, cy = cam
+    col, dep, _ = wl_cpu.cur_frame
+    n = cfg.track_pixels
+    S = cfg.n_stratified + cfg.n_importance
+    idx = torch.randint((H - 2 * e) * (W - 2 * e), (n,), generator=gen)
+    cam_pose = pose.clone().requires_grad_(True)
+    draw = lambda shape: torch.rand(shape, generator=gen)
+    loss, _ = path_ref.tracking_iteration(field, cam_pose, dep[None], col[None], H, W, fx, fy, cx, cy, e, e, idx, cfg.truncation,
+                                          cfg.n_stratified, cfg.n_importance, draw)
+    loss.backward()
+    return float(loss.detach()), cam_pose.grad
+
+
+def oracle_dense_query_chunk(wl_cpu, field, n_points=500000):
+    """Mesher.eval_points (src/utils/Mesher.py:134-166) on one points_batch_size chunk of the 1 cm query grid, SDF channel,
+    through oracle/path_ref on the host CPU.  Returns the number of points evaluated."""
+    axes = path_ref.mesh_grid_axes([[lo, hi] for lo, hi in wl_cpu.cfg.bound_yaml], resolution=0.01)
+    nx, ny, nz = [a.numel() for a in axes]
+    # a chunk of consecutive points in the reference's flattening order (meshgrid 'xy': y slowest, then x, then z)
+    m = min(n_points, nx * ny * nz)
+    flat = torch.arange(m)
+    iz = flat % nz; ix = (flat // nz) % nx; iy = flat // (nz * nx)
+    pts = torch.stack([axes[0][ix], axes[1][iy + ny // 2], axes[2][iz]], dim=1)
+    with torch.no_grad():
+        path_ref.eval_points_sdf(field, pts)
+    return m
+
+
 def tracking_ok(r):
     bad = [k for k in ("rays_o_mismatch", "rays_d_mismatch", "valid_mismatch", "z_mismatch") if r[k] != 0]
     bad += [k for k in ("term_rel", "pixel_unc_rel", "depth_rel", "rgb_rel", "loss_rel") if not r[k] < 1e-4]

@@ -41,7 +41,7 @@ class SlamResult:
 
 def run_slam(cfg: syn.SceneCfg = syn.REPLICA_ROOM0, n_frames: int = 40, device="cuda:0", scale_hw: float = 0.5,
              frame_stride: int = 1, track_iters: int = None, map_iters: int = None, map_iters_first: int = 10,
-             seed: int = 0, prior_noise_m: float = 0.0, verbose: bool = False) -> SlamResult:
+             seed: int = 0, prior_noise_m: float = 0.0, verbose: bool = False, pregenerate: bool = False) -> SlamResult:
     torch.manual_seed(seed)
     seq = syn.SyntheticSequence(cfg, n_frames=max(200, n_frames * frame_stride), device=device, seed=1, scale_hw=scale_hw)
     cam = seq.cam
@@ -73,10 +73,13 @@ def run_slam(cfg: syn.SceneCfg = syn.REPLICA_ROOM0, n_frames: int = 40, device="
     loss_first = loss_last = float("nan")
     to_pose = wlmod._matrix_to_cam_pose
     npx_win = (H - 2 * edge) * (W - 2 * edge)
+    # pregenerate: render the synthetic RGB-D frames before the clock starts (they stand in for the dataset on disk, which the
+    # reference's loader threads read ahead of the tracker); otherwise frame synthesis is part of the measured loop
+    frames = [seq.frame(k * frame_stride) for k in range(n_frames)] if pregenerate else None
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for k in range(n_frames):
-        col, dep, c2w_gt = seq.frame(k * frame_stride)
+        col, dep, c2w_gt = frames[k] if frames is not None else seq.frame(k * frame_stride)
         gt[k] = c2w_gt
         # ---------------- tracking (Tracker.py:306-368) ----------------
         if k == 0:
