@@ -323,6 +323,34 @@ typedef struct usl_adam_group {
 USL_API int usl_adam_step(const usl_adam_group_t *groups, int n_groups, int64_t step, const int64_t *step_dev,
                           int zero_grad, usl_stream_t stream);
 
+/* ---- f4: marching cubes on the device-resident SDF volume (src/utils/Mesher.py:230-258) ----------------------------------
+ * Replaces the D2H copy of the volume + skimage.measure.marching_cubes(volume[x,y,z], level, spacing) + the origin shift.
+ * A vertex on every grid edge whose end values straddle the level (inside = value < level) at the linear interpolation
+ * t = (level - v0)/(v1 - v0); indexed triangles from a 256-case table (csrc/mc_tables.h, generated; crack-free, differs from
+ * skimage's Lewiner tables only in how ambiguous configurations are triangulated; normals point towards larger values).
+ * Works on one y-slab of the volume as usl_sdf_query_grid wrote it: vol[(iy*nx + ix)*nz + iz], iy in [0, rows); a slab that is
+ * not the last carries one halo row (rows = own_rows + 1).  Call order: usl_mc_classify -> usl_scan_u8(pflags, popcount=1) ->
+ * usl_scan_u8(ctri, popcount=0) -> allocate verts[V,3] / faces[T,3] -> usl_mc_emit. */
+typedef struct usl_mc_args {
+    const float *vol;
+    int32_t nx, nz, rows, own_rows;
+    int32_t y_begin;                  /* global row index of the slab's first row */
+    float level;
+    float origin[3], spacing[3];      /* world position of grid index (0,0,0) of the whole volume, grid spacing */
+    uint8_t *pflags;                  /* [rows*nx*nz] out (classify), in (emit): bit a = a vertex on the edge towards +axis a */
+    uint8_t *ctri;                    /* [rows*nx*nz] out (classify), in (emit): triangles of the cell rooted at this point */
+    const uint32_t *voff, *toff;      /* emit: exclusive prefix sums of popcount(pflags) / ctri */
+    float *verts;                     /* emit: [V,3] world coordinates */
+    int64_t *vkeys;                   /* emit, nullable: [V] 3*(global point index) + axis -- what a multi-GPU merge welds by */
+    int32_t *faces;                   /* emit: [T,3] indices into this slab's vertex array */
+} usl_mc_args_t;
+USL_API int usl_mc_classify(const usl_mc_args_t *a, usl_stream_t stream);
+USL_API int usl_mc_emit(const usl_mc_args_t *a, usl_stream_t stream);
+/* out[i] = sum_{j<i} f(in[j]), f = popcount or identity; total[0] = sum of all; block_sums: workspace of usl_scan_u8_blocks(n) uint32 */
+USL_API int usl_scan_u8(const uint8_t *in, int64_t n, int popcount, uint32_t *out, uint32_t *block_sums, uint32_t *total,
+                        usl_stream_t stream);
+USL_API int usl_scan_u8_blocks(int64_t n, int64_t *n_blocks);
+
 /* ---- 8e: multi-GPU exchange steps of the sharded mapping iteration, over peer memory (NVLink / NVSwitch) -----------
  * The reference is single-GPU; these entry points are what its proposed `allreduce_grads` seam becomes.
  * The host layer maps every rank's buffers into every rank's address space (CUDA IPC / symmetric memory: one allocation

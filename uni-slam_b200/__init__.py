@@ -12,13 +12,15 @@ Public surface (mirrors the reference's operator API for the path, SURVEY.md sec
   RenderImageStep           forward-only whole-frame renderer      (f3, Renderer.render_img)
   FusedAdam                 one-launch torch.optim.Adam equivalent (a-12 / f1)
   KeyframeStore             device-resident keyframe subsets + window views (f2, Mapper.py:315-356,528-541)
+  mesh                      marching cubes on the device-resident volume, vertex colours, PLY (f4, Mesher.py:230-276)
+  parallel                  multi-GPU: peer-memory exchange kernels, slab / ray-range sharding (8e)
   ops                       thin per-kernel wrappers over the C-ABI
 There is no CPU path: every op raises RuntimeError if lib/libunislam_b200.so is missing.
 """
-from . import _lib, ops, synthetic  # noqa: F401
+from . import _lib, mesh, ops, synthetic  # noqa: F401
 from .modules import Decoders, Encoding, Network, Renderer  # noqa: F401
 from .keyframes import KeyframeStore  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .steps import DenseSdfQuery, MappingStep, RenderImageStep, TrackingStep  # noqa: F401
 
-__all__ = ["Encoding", "Network", "Decoders", "Renderer", "MappingStep", "TrackingStep", "DenseSdfQuery", "RenderImageStep", "FusedAdam", "KeyframeStore", "ops", "synthetic"]
+__all__ = ["Encoding", "Network", "Decoders", "Renderer", "MappingStep", "TrackingStep", "DenseSdfQuery", "RenderImageStep", "FusedAdam", "KeyframeStore", "ops", "mesh", "synthetic"]

@@ -86,6 +86,12 @@ class AdamRange(Structure):
     _fields_ = [("begin", c_int64), ("end", c_int64), ("lr", c_float), ("_pad", c_float)]
 
 
+class McArgs(Structure):
+    _fields_ = [("vol", c_void_p), ("nx", c_int32), ("nz", c_int32), ("rows", c_int32), ("own_rows", c_int32), ("y_begin", c_int32),
+                ("level", c_float), ("origin", c_float * 3), ("spacing", c_float * 3), ("pflags", c_void_p), ("ctri", c_void_p),
+                ("voff", c_void_p), ("toff", c_void_p), ("verts", c_void_p), ("vkeys", c_void_p), ("faces", c_void_p)]
+
+
 ADAM_MAX_GROUPS = 24
 _P = c_void_p
 _SIGS = {
@@ -123,6 +129,10 @@ _SIGS = {
     "usl_composite_loss_bwd": [POINTER(LossArgs), _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, POINTER(Bound),
                                _P, _P, _P, _P, _P, _P],
     "usl_adam_step": [POINTER(AdamGroup), c_int, c_int64, _P, c_int, _P],
+    "usl_mc_classify": [POINTER(McArgs), _P],
+    "usl_mc_emit": [POINTER(McArgs), _P],
+    "usl_scan_u8": [_P, c_int64, c_int, _P, _P, _P, _P],
+    "usl_scan_u8_blocks": [c_int64, POINTER(c_int64)],
     "usl_exchange_sums": [POINTER(Peers), _P, _P],
     "usl_peer_barrier": [POINTER(Peers), _P],
     "usl_allreduce_sum": [POINTER(Peers), c_int64, c_int64, _P],
@@ -168,7 +178,7 @@ LAUNCHES = 0   # number of kernel-launching C-ABI calls made so far (bench.py re
 def call(name, *args):
     global LAUNCHES
     lib = load()
-    if name not in ("usl_grid_build", "usl_field_bwd_scratch_floats", "usl_field_stash_floats", "usl_allreduce_adam_slice_floats"):
+    if name not in ("usl_grid_build", "usl_field_bwd_scratch_floats", "usl_field_stash_floats", "usl_allreduce_adam_slice_floats", "usl_scan_u8_blocks"):
         LAUNCHES += 1
     rc = getattr(lib, name)(*args)
     if rc != 0:
