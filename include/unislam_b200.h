@@ -222,6 +222,11 @@ typedef struct usl_points {
 USL_API int usl_field_stash_floats(int64_t n_points, int64_t *n_floats);
 USL_API int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac,
                   usl_stream_t stream);
+/* usl_field_fwd with the Jacobian's tangent contraction on the 5th-generation tensor cores (tcgen05.mma kind::tf32, TMEM
+ * accumulators; csrc/field_tc.cu).  Same arguments and outputs (raw bit-identical, jac within the gradient tolerance).  Measured
+ * slower than the CUDA-core kernel on the mapping workload (the kernel is bound by the gather side), hence a separate entry point. */
+USL_API int usl_field_fwd_tc(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac,
+                     usl_stream_t stream);
 /* d_raw[n,4] -> table gradients (scatter), decoder gradients (gm[2], may be NULL to skip).  Of `p` only n is read (the
  * points themselves come from the stash).  Persistent kernel: stash / d_raw / raw tiles arrive by cp.async.bulk when
  * n % 4 == 0 and raw, feat, d_raw are 16-byte aligned, by ordinary loads otherwise (same results).
@@ -316,6 +321,8 @@ typedef struct usl_adam_group {
     float *param, *grad, *exp_avg, *exp_avg_sq; /* device, n floats each */
     int64_t n;
     float lr, beta1, beta2, eps;
+    int64_t step;                               /* this tensor's own 1-based step count (torch keeps state['step'] per parameter);
+                                                 * 0 = use the call's `step` / `step_dev` */
 } usl_adam_group_t;
 /* One fused launch over all groups; same update rule as torch.optim.Adam (no weight decay / amsgrad).
  * step: 1-based step count of this update (bias correction); step_dev (nullable): device int64 holding it instead

@@ -405,6 +405,35 @@ def test_fused_adam_matches_torch_adam():
     o_z = P.FusedAdam(mk(ours), zero_grad_in_step=True)
     o_z.step()
     assert all(float(o.grad.abs().max()) == 0 for o in ours)
+    # per-parameter step counts (torch keeps state['step'] per parameter): a tensor without a gradient in the first steps
+    a_ref = [torch.randn(64, generator=g).to(DEV).requires_grad_(True) for _ in range(2)]
+    a_our = [r.detach().clone().requires_grad_(True) for r in a_ref]
+    t_ref, t_our = torch.optim.Adam(a_ref, lr=0.01), P.FusedAdam(a_our, lr=0.01)
+    for it in range(4):
+        for k, (r, o) in enumerate(zip(a_ref, a_our)):
+            if k == 1 and it < 2:
+                r.grad = None; o.grad = None                            # joins at step 3 with bias correction of ITS step 1
+                continue
+            gr = torch.randn(64, generator=g).to(DEV)
+            r.grad = gr.clone(); o.grad = gr.clone()
+        t_ref.step(); t_our.step()
+    for r, o in zip(a_ref, a_our):
+        assert rel_err(o.detach().cpu(), r.detach().cpu()) < 1e-6
+    # checkpoints interchange with torch.optim.Adam
+    sd = t_our.state_dict()
+    t_ref2 = torch.optim.Adam([o.detach().clone().requires_grad_(True) for o in a_our], lr=0.01)
+    t_ref2.load_state_dict(sd)
+    t_our2 = P.FusedAdam([o.detach().clone().requires_grad_(True) for o in a_our], lr=0.01)
+    t_our2.load_state_dict(t_ref.state_dict())
+    gr = torch.randn(64, generator=g).to(DEV)
+    for opt_ in (t_ref2, t_our2):
+        for p_ in opt_.param_groups[0]["params"]:
+            p_.grad = gr.clone()
+        opt_.step()
+    for r, o in zip(t_ref2.param_groups[0]["params"], t_our2.param_groups[0]["params"]):
+        assert rel_err(o.detach().cpu(), r.detach().cpu()) < 1e-6
+    with pytest.raises(ValueError):
+        P.FusedAdam([torch.zeros(1, device=DEV, requires_grad=True) for _ in range(25)])   # the launch limit is reported at construction
 
 
 def test_tcgen05_forward_matches_cuda_core_forward(monkeypatch):
@@ -417,12 +446,11 @@ def test_tcgen05_forward_matches_cuda_core_forward(monkeypatch):
     x = torch.rand(n, 3, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3)) * 1.1 - 0.05   # some points clamp
     from ctypes import byref
     outs = []
-    for flag in ("0", "1"):
-        monkeypatch.setenv("USL_TCGEN05", flag)
+    for entry in ("usl_field_fwd", "usl_field_fwd_tc"):
         raw = torch.zeros(n, 4, device=DEV); jac = torch.zeros(12, n, device=DEV)
         f = meta.pack(tabs[0], tabs[1], dec)
         pts = P.ops._points_from_x(x)
-        P._lib.call("usl_field_fwd", byref(f), byref(pts), P._lib.ptr(raw), None, P._lib.ptr(jac), P._lib.stream())
+        P._lib.call(entry, byref(f), byref(pts), P._lib.ptr(raw), None, P._lib.ptr(jac), P._lib.stream())
         torch.cuda.synchronize()
         outs.append((raw.cpu(), jac.cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) or (outs[0][0] - outs[1][0]).abs().max() < 1e-6

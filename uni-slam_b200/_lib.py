@@ -75,7 +75,7 @@ class LossArgs(Structure):
 
 class AdamGroup(Structure):
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("n", c_int64),
-                ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float)]
+                ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("step", c_int64)]
 
 
 class Peers(Structure):
@@ -110,6 +110,7 @@ _SIGS = {
     "usl_zsample_depth": [POINTER(ZSampleArgs), _P, _P, _P, _P, c_int64, _P, _P],
     "usl_zsample_nodepth": [POINTER(ZSampleArgs), POINTER(Field), _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P],
     "usl_field_fwd": [POINTER(Field), POINTER(Points), _P, _P, _P, _P],
+    "usl_field_fwd_tc": [POINTER(Field), POINTER(Points), _P, _P, _P, _P],
     "usl_field_bwd": [POINTER(Field), POINTER(Points), _P, _P, _P, _P, _P, POINTER(Mlp), _P, c_int, _P],
     "usl_field_bwd_scratch_floats": [POINTER(Field), POINTER(c_int64)],
     "usl_field_stash_floats": [c_int64, POINTER(c_int64)],

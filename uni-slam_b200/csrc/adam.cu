@@ -82,7 +82,9 @@ using namespace usl;
 
 extern "C" int usl_adam_step(const usl_adam_group_t *groups, int n_groups, int64_t step, const int64_t *step_dev,
                              int zero_grad, usl_stream_t stream) {
-    if (!groups || n_groups < 1 || n_groups > USL_ADAM_MAX_GROUPS || (step < 1 && !step_dev)) {
+    bool own_steps = groups != nullptr;
+    for (int i = 0; groups && i < n_groups && i < USL_ADAM_MAX_GROUPS; ++i) own_steps = own_steps && groups[i].step > 0;
+    if (!groups || n_groups < 1 || n_groups > USL_ADAM_MAX_GROUPS || (step < 1 && !step_dev && !own_steps)) {
         set_error("usl_adam_step: bad arguments (1..%d groups, step >= 1)", USL_ADAM_MAX_GROUPS);
         return 1;
     }
@@ -93,7 +95,7 @@ extern "C" int usl_adam_step(const usl_adam_group_t *groups, int n_groups, int64
         A.g[i] = groups[i];
         A.first_block[i] = blocks;
         blocks += (int)((groups[i].n + per_block - 1) / per_block);
-        const double t = (double)(step < 1 ? 1 : step);
+        const double t = (double)(groups[i].step > 0 ? groups[i].step : (step < 1 ? 1 : step));
         A.step_size[i] = (float)((double)groups[i].lr / (1.0 - std::pow((double)groups[i].beta1, t)));
         A.bc2_sqrt[i] = (float)std::sqrt(1.0 - std::pow((double)groups[i].beta2, t));
     }

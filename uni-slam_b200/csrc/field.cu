@@ -442,7 +442,6 @@ static int check_field(const usl_field_t *f, const usl_points_t *p) {
 
 using namespace usl;
 
-int usl_field_fwd_tc_launch(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac, cudaStream_t s);
 
 extern "C" {
 
@@ -458,10 +457,6 @@ int usl_field_fwd(const usl_field_t *f, const usl_points_t *p, float *raw, float
     // and profiled, but not the default: the kernel is bound by L1 sector lookups of the gather,
     // so moving 57 % of the FMA-pipe work to the tensor pipe does not shorten it (196 us vs 182 us measured).
     if (p->sample_major && !p->x && (p->n % p->S)) { set_error("usl_field_fwd: sample_major needs n == R * S"); return 1; }
-#ifdef USL_DEV
-    { const char *tc_env = getenv("USL_TCGEN05");      // development builds only: select the tensor-core variant by environment
-      if (jac && tc_env && tc_env[0] == '1' && !p->sample_major) return usl_field_fwd_tc_launch(f, p, raw, feat, jac, s); }
-#endif
     if (jac && feat) field_fwd_kernel<true, true><<<grid, USL_FWD_THREADS, 0, s>>>(A);
     else if (jac) field_fwd_kernel<true, false><<<grid, USL_FWD_THREADS, 0, s>>>(A);
     else if (feat) field_fwd_kernel<false, true><<<grid, USL_FWD_THREADS, 0, s>>>(A);

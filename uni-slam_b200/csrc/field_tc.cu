@@ -271,8 +271,16 @@ __global__ void __launch_bounds__(TC_CTA_THREADS, USL_TC_MINB) field_fwd_tc_kern
 
 using namespace usl;
 
-// Called by usl_field_fwd (field.cu) when a Jacobian is requested and 16-level grids are used.
-int usl_field_fwd_tc_launch(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac, cudaStream_t s) {
+// The tensor-core variant of usl_field_fwd with a Jacobian (same arguments, same outputs): an explicit entry point, so a caller
+// chooses it by name, not through process-wide state.
+extern "C" int usl_field_fwd_tc(const usl_field_t *f, const usl_points_t *p, float *raw, float *feat, float *jac, usl_stream_t stream) {
+    if (!f || !p || !raw || !jac) { set_error("usl_field_fwd_tc: field, points, raw and jac are required"); return 1; }
+    if (p->n <= 0) return 0;
+    if (p->sample_major) { set_error("usl_field_fwd_tc: ray-major point order only"); return 1; }
+    for (int gi = 0; gi < 2; ++gi)
+        if (f->grid[gi].n_levels != USL_IN / USL_FEATS) { set_error("field grids must have 16 levels x 2 features"); return 1; }
+    if (p->n > 0 && !p->x && (!p->rays_o || !p->rays_d || !p->z || p->S <= 0)) { set_error("points: need x or (rays_o, rays_d, z, S)"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
     FieldTcArgs A;
     A.f = *f; A.p = *p; A.raw = raw; A.feat = feat; A.jac = jac;
     dim3 grid((unsigned)((p->n + TC_THREADS - 1) / TC_THREADS), 2);

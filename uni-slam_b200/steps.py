@@ -142,7 +142,7 @@ class MappingStep(_Profiled):
         self.acc_hook = None      # multi-GPU: called with self.acc between loss_fwd and loss_bwd (all-reduce of sums/counts)
         self.rgb_grads_hook = None  # multi-GPU: called with the colour-table gradient as soon as its half of field_bwd is queued
         # independent pieces (gradient zero-fill; pose-gradient reduction) run on a side stream next to the critical path
-        self.side_branches = os.environ.get("USL_SIDE_BRANCHES", "1") != "0"
+        self.side_branches = True       # set False to run the zero-fill and the pose reduction on the main stream (ablation)
         self._side = None
         self._init_prof()
 
@@ -391,7 +391,7 @@ class RenderImageStep(_Profiled):
         self.perturb = perturb
         self.cam = (int(H), int(W), float(fx), float(fy), float(cx), float(cy))
         C = self.chunk = int(min(chunk_rays, H * W))
-        self.sample_major = os.environ.get("USL_RENDER_SAMPLE_MAJOR", "1") != "0"
+        self.sample_major = True        # set False for ray-major point order (ablation: 13.2 vs 10.7 ms per frame)
         f32 = dict(device=dev, dtype=torch.float32)
         self.rays_o = torch.empty((C, 3), **f32); self.rays_d = torch.empty((C, 3), **f32)
         self.gt_depth = torch.empty((C,), **f32); self.valid = torch.empty((C,), device=dev, dtype=torch.uint8)
