@@ -205,7 +205,7 @@ def run_ours(args, rank, world, local_rank):
 
     reduce_grads = None
     if world > 1:
-        reduce_grads = par.attach_peer_collectives(step, pg) if pg else par.attach_mapping_collectives(step, overlap=args.overlap)
+        reduce_grads = par.attach_peer_collectives(step, pg, overlap=not args.no_overlap) if pg else par.attach_mapping_collectives(step, overlap=args.overlap)
     my_rays = par.slab_range(R, rank, world)                           # strong scaling: this rank's contiguous slice of the batch
     mode = {"strong": False}                                           # flipped for the strong-scaling leg
 
@@ -523,11 +523,12 @@ def multi_gpu_legs(args, P, par, pg, step, wl, one_step, mode, flat_idx, flat_u,
     # ---- (A) split batch + exchange + all-reduce  ==  whole batch on one GPU ----
     g0 = torch.Generator(device=dev).manual_seed(4242)                 # the same draws on every rank
     flat_idx.random_(0, wl.P, generator=g0); flat_u.uniform_(generator=g0)
-    hook, step.acc_hook = step.acc_hook, None
-    step.run(wl.batches(bufs[0], bufs[1]), bufs[2], bufs[3], bufs[4], **run_args)          # whole batch, local sums only
+    saved = (step.acc_hook, step.rgb_grads_hook, step.bwd_leave_room)
+    step.acc_hook, step.rgb_grads_hook, step.bwd_leave_room = None, None, False
+    step.run(wl.batches(bufs[0], bufs[1]), bufs[2], bufs[3], bufs[4], **run_args)          # whole batch, local sums only, no exchange
     sync()
     g_full = step.fs.g_grads.double().clone(); loss_full = float(step.loss)
-    step.acc_hook = hook
+    step.acc_hook, step.rgb_grads_hook, step.bwd_leave_room = saved
     step.run(wl.batches(bufs[0], bufs[1]), bufs[2], bufs[3], bufs[4], ray_range=my_rays, **run_args)
     reduce_grads()
     sync()
@@ -632,13 +633,10 @@ def multi_gpu_legs(args, P, par, pg, step, wl, one_step, mode, flat_idx, flat_u,
         pflat = pg.alloc(n)
         # parameters in the gradient buffer's layout: [sdf table | colour table | decoders | beta | poses | pad]
         srcs = [tabs[0], tabs[1]] + list(dec) + [beta, cam_poses]
-        o = 0
-        offs = []
         for t_, g_ in zip(srcs, [fs.g_sdf_table, fs.g_rgb_table] + fs.g_dec + [fs.g_beta, fs.d_pose]):
+            o = (g_.data_ptr() - fs.g_all.data_ptr()) // 4             # the parameter sits where its gradient sits
             pflat[o:o + t_.numel()].copy_(t_.detach().reshape(-1))
-            offs.append((o, o + t_.numel()))
-            o += g_.numel()
-        n_tab = tabs[0].numel() + tabs[1].numel()
+        n_tab = tabs[0].numel() + tabs[1].numel()                      # both tables lead the layout
         ranges = [(0, n_tab, cfg.hash_lr), (n_tab, n, 1e-3)]
         fsa = par.FusedShardedAdam(pg, pflat, fs.g_all, n, ranges)
         gsum = None
@@ -976,6 +974,8 @@ def main():
                     "field_bwd runs (measured SLOWER at N=2: 0.80 vs 0.75 ms/step -- NCCL's reduction and the atomics contend for L2)")
     ap.add_argument("--slam-frames", type=int, default=200, help="frames of the full-resolution Tracker+Mapper loop leg (0 = skip)")
     ap.add_argument("--no-extras", action="store_true", help="skip the ScanNet-shaped mapping leg and the SLAM loop leg")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1, peer collectives: exchange the whole gradient buffer after the backward "
+                    "instead of overlapping the colour-table exchange with the sdf half of the backward")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N>1: gradient / loss-sum exchange by the hand-written peer-memory kernels (csrc/collective.cu, default) or by NCCL")
     ap.add_argument("--quick", action="store_true", help="mapping step only (used under ncu): skip e2e / tracking / dense query / Adam / cpu baseline")

@@ -234,7 +234,10 @@ USL_API int usl_field_fwd_tc(const usl_field_t *f, const usl_points_t *p, float 
  * small coarse levels (L2 atomics serialise on small tables) and the work-queue counters of the persistent kernel; it
  * is folded into the gradient tables before return and must be zero-filled again by the caller before the next call
  * (NULL: no replicas, static tile assignment). grid_mask: 1 = sdf grid only, 2 = colour grid
- * only, 3 = both (one launch); the halves are independent, so a caller can all-reduce one while the other runs. */
+ * only, 3 = both (one launch); the halves are independent, so a caller can all-reduce one while the other runs.
+ * | 4 (USL_BWD_LEAVE_ROOM): launch one resident CTA per SM fewer than fit, so that a small concurrent kernel (the gradient
+ * exchange of the other half) finds registers on every SM whatever the launch order. */
+#define USL_BWD_LEAVE_ROOM 4
 USL_API int usl_field_bwd_scratch_floats(const usl_field_t *f, int64_t *n_floats);
 USL_API int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw, const float *feat,
                   const float *d_raw, float *grad_table_sdf, float *grad_table_rgb,
@@ -363,6 +366,7 @@ USL_API int usl_scan_u8_blocks(int64_t n, int64_t *n_blocks);
  * The host layer maps every rank's buffers into every rank's address space (CUDA IPC / symmetric memory: one allocation
  * call per buffer at start-up) and passes the mapped pointers; nothing here calls NCCL. */
 #define USL_MAX_PEERS 8
+#define USL_PEER_CHANNELS 4
 #define USL_PEER_CTRL_BYTES 2048          /* per-rank control block (flags, exchange slots, epochs): peer-mapped, zeroed once */
 typedef struct usl_peers {
     int32_t rank, world;
@@ -370,6 +374,10 @@ typedef struct usl_peers {
     void *ctrl[USL_MAX_PEERS];            /* ctrl[p]: rank p's control block as mapped here */
     void *mc;                             /* multicast (NVLS) mapping of the same buffer, or NULL: when set, the reductions run as
                                            * multimem.ld_reduce (summed inside the NVSwitch) + multimem.st (replicated by the switch) */
+    int32_t channel;                      /* barrier channel 0..USL_PEER_CHANNELS-1: exchanges issued concurrently on different
+                                           * streams must use different channels (every rank the same one for the same exchange) */
+    int32_t max_ctas_per_sm;              /* grid cap of the reduction kernels (0 = default 8); 1 leaves the SMs to a compute kernel
+                                           * running beside the exchange (the pass is bound by the links, not by the SMs) */
 } usl_peers_t;
 USL_API int usl_peer_ctrl_bytes(void);
 /* acc[USL_LOSS_SLOTS] (device, local) <- sum over ranks of acc: the loss sums / counts of usl_loss_fwd become global, so

@@ -79,7 +79,8 @@ class AdamGroup(Structure):
 
 
 class Peers(Structure):
-    _fields_ = [("rank", c_int32), ("world", c_int32), ("buf", c_void_p * 8), ("ctrl", c_void_p * 8), ("mc", c_void_p)]
+    _fields_ = [("rank", c_int32), ("world", c_int32), ("buf", c_void_p * 8), ("ctrl", c_void_p * 8), ("mc", c_void_p),
+                ("channel", c_int32), ("max_ctas_per_sm", c_int32)]
 
 
 class AdamRange(Structure):

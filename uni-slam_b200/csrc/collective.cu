@@ -55,8 +55,8 @@ __device__ __forceinline__ void mc_st(float4 *p, const float4 &v) {
 // the loss-sum exchange (double-buffered by epoch parity) and this rank's own epoch counters.
 struct PeerCtrl {
     uint32_t flag_x[USL_MAX_PEERS];                  // exchange: flag_x[p] = epoch of the last push of rank p
-    uint32_t flag_b[USL_MAX_PEERS];                  // barrier:  flag_b[p] = epoch of the last arrival of rank p
-    uint32_t epoch_x, epoch_b, _pad[2];              // local counters (only this rank writes them)
+    uint32_t flag_b[USL_PEER_CHANNELS][USL_MAX_PEERS];   // barrier:  flag_b[c][p] = epoch of the last arrival of rank p on channel c
+    uint32_t epoch_x, epoch_b[USL_PEER_CHANNELS], _pad;  // local counters (only this rank writes them)
     float slots[2][USL_MAX_PEERS][USL_LOSS_SLOTS];   // slots[epoch & 1][p][:] = sums pushed by rank p
 };
 static_assert(sizeof(PeerCtrl) <= USL_PEER_CTRL_BYTES, "control block larger than the published size");
@@ -91,12 +91,13 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(usl_peers_t P) {
     PeerCtrl *me = reinterpret_cast<PeerCtrl *>(P.ctrl[P.rank]);
     const int t = threadIdx.x;
     uint32_t epoch = 0;
-    if (t == 0) { epoch = me->epoch_b + 1; me->epoch_b = epoch; }
+    const int c = P.channel;                                          // independent barrier sequences for concurrent streams
+    if (t == 0) { epoch = me->epoch_b[c] + 1; me->epoch_b[c] = epoch; }
     epoch = __shfl_sync(0xffffffffu, epoch, 0);
     __threadfence_system();                                           // everything this GPU wrote before is visible system-wide
     if (t < P.world) {
-        st_release_sys(&reinterpret_cast<PeerCtrl *>(P.ctrl[t])->flag_b[P.rank], epoch);
-        while (ld_acquire_sys(&me->flag_b[t]) < epoch) { }
+        st_release_sys(&reinterpret_cast<PeerCtrl *>(P.ctrl[t])->flag_b[c][P.rank], epoch);
+        while (ld_acquire_sys(&me->flag_b[c][t]) < epoch) { }
     }
 }
 
@@ -253,7 +254,9 @@ __global__ void __launch_bounds__(256) allreduce_mc_kernel(const __grid_constant
 }
 
 static int check_peers(const usl_peers_t *P, const char *who) {
-    if (!P || P->world < 1 || P->world > USL_MAX_PEERS || P->rank < 0 || P->rank >= P->world) { set_error("%s: bad peer group", who); return 1; }
+    if (!P || P->world < 1 || P->world > USL_MAX_PEERS || P->rank < 0 || P->rank >= P->world || P->channel < 0 || P->channel >= USL_PEER_CHANNELS) {
+        set_error("%s: bad peer group", who); return 1;
+    }
     for (int p = 0; p < P->world; ++p)
         if (!P->ctrl[p]) { set_error("%s: peer %d has no control block", who, p); return 1; }
     return 0;
@@ -266,7 +269,7 @@ static int launch_reduce(const ReduceArgs &A, cudaStream_t s) {
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int64_t mine = A.slice4;
     int64_t blocks = (mine + 255) / 256;
-    const int64_t cap = (int64_t)n_sm * 8;
+    const int64_t cap = (int64_t)n_sm * (A.P.max_ctas_per_sm > 0 ? A.P.max_ctas_per_sm : 8);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const bool use_mc = A.P.mc != nullptr && A.P.world > 1 && (!ADAM || A.param_mc != nullptr);

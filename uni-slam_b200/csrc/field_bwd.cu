@@ -540,7 +540,9 @@ int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw,
     if (p->n <= 0) return 0;
     if (!feat || !raw || !d_raw) { set_error("usl_field_bwd: raw, feat and d_raw are required"); return 1; }
     if (f->mlp[0].n_hidden != f->mlp[1].n_hidden) { set_error("usl_field_bwd: decoders must share n_hidden"); return 1; }
-    if (grid_mask < 1 || grid_mask > 3) { set_error("usl_field_bwd: grid_mask must be 1 (sdf), 2 (colour) or 3 (both)"); return 1; }
+    const bool leave_room = (grid_mask & USL_BWD_LEAVE_ROOM) != 0;
+    grid_mask &= 3;
+    if (grid_mask < 1 || grid_mask > 3) { set_error("usl_field_bwd: grid_mask must be 1 (sdf), 2 (colour) or 3 (both) [| USL_BWD_LEAVE_ROOM]"); return 1; }
     FieldBwd2Args A;
     A.f = *f; A.n = p->n; A.raw = raw; A.feat = feat; A.d_raw = d_raw;
     A.grad_table[0] = grad_table_sdf; A.grad_table[1] = grad_table_rgb;
@@ -573,6 +575,7 @@ int usl_field_bwd(const usl_field_t *f, const usl_points_t *p, const float *raw,
     }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, B2_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const int64_t n_items = ((p->n + B2_TILE - 1) / B2_TILE) * A.n_grids;
+    if (leave_room && per_sm > 1) --per_sm;
     int64_t nb = (int64_t)n_sm * per_sm;                      // persistent: every resident slot of the device, once
     if (nb > n_items) nb = n_items;
     const unsigned nblk = (unsigned)nb;

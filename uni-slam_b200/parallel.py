@@ -105,8 +105,11 @@ class PeerGroup:
         P = self.peers(self.ctrl)
         L.call("usl_exchange_sums", byref(P), L.ptr(acc), L.stream())
 
-    def allreduce(self, t: torch.Tensor, n_floats: int, offset_floats: int = 0):
+    def allreduce(self, t: torch.Tensor, n_floats: int, offset_floats: int = 0, channel: int = 0, max_ctas_per_sm: int = 0):
+        """channel: exchanges in flight at the same time (different streams) need different barrier channels;
+        max_ctas_per_sm=1: a small grid that shares the SMs with a compute kernel (the pass is bound by the links)."""
         P = self.peers(t)
+        P.channel, P.max_ctas_per_sm = int(channel), int(max_ctas_per_sm)
         L.call("usl_allreduce_sum", byref(P), int(offset_floats), int(n_floats), L.stream())
 
     def barrier(self):
@@ -144,15 +147,36 @@ class FusedShardedAdam:
                len(self.ranges), self.betas[0], self.betas[1], self.eps, 0, L.ptr(self.step_dev), L.stream())
 
 
-def attach_peer_collectives(step, pg: PeerGroup):
+def attach_peer_collectives(step, pg: PeerGroup, overlap: bool = True):
     """Wire the hand-written exchange steps onto a MappingStep whose gradient buffer came from pg.alloc.  Returns
-    reduce_grads(), to be called after step.run(): one usl_allreduce_sum over [tables | decoders | beta | poses]."""
+    reduce_grads(), to be called after step.run().
+
+    overlap=True (default): the backward runs as two launches, colour grid first; the colour-table gradient (87 % of the bytes,
+    the first contiguous range of the flat buffer) is exchanged on a side stream by a one-CTA-per-SM kernel WHILE the sdf half
+    of the backward runs (which leaves one CTA slot per SM free for it); reduce_grads() then exchanges the remaining range
+    [sdf table | decoders | beta | poses] and joins the side stream.  CUDA-graph capturable (fork / join on events).
+    overlap=False: one usl_allreduce_sum over the whole buffer after the backward."""
     step.acc_hook = pg.exchange_sums
     fs = step.fs
+    if not overlap:
+        def reduce_all():
+            pg.allreduce(fs.g_all, fs.n_grad_padded)
+        return reduce_all
+    side = torch.cuda.Stream()
+    n_rgb = fs.g_rgb_table.numel()
+    assert fs.g_rgb_table.data_ptr() == fs.g_all.data_ptr() and n_rgb % 4 == 0
 
-    def reduce_grads():
-        pg.allreduce(fs.g_all, fs.n_grad_padded)
-    return reduce_grads
+    def rgb_hook(_g_rgb):
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            pg.allreduce(fs.g_all, n_rgb, 0, channel=1, max_ctas_per_sm=1)
+    step.rgb_grads_hook = rgb_hook
+    step.bwd_leave_room = True
+
+    def reduce_rest():
+        pg.allreduce(fs.g_all, fs.n_grad_padded - n_rgb, n_rgb, channel=0)
+        torch.cuda.current_stream().wait_stream(side)
+    return reduce_rest
 
 
 def attach_mapping_collectives(step, group=None, overlap: bool = False):

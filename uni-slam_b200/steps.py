@@ -61,11 +61,12 @@ class _FieldState:
         self.meta, self.sdf_table, self.rgb_table, self.dec, self.beta = meta, sdf_table, rgb_table, list(dec), beta
         self.field = meta.pack(sdf_table, rgb_table, self.dec)
         if with_grads:
-            # every gradient lives in ONE flat buffer [sdf table | colour table | decoders | beta]: a single memset
-            # clears it and (multi-GPU) a single all-reduce sums it.  Table sizes are multiples of 16 floats, so the
-            # 16-byte vector atomics stay aligned.
+            # every gradient lives in ONE flat buffer [colour table | sdf table | decoders | beta | poses]: a single memset
+            # clears it and (multi-GPU) the exchange kernels sum it.  The colour table (87 % of the bytes) comes first so that
+            # its exchange -- one contiguous range -- can start while the sdf half of the backward still runs, and the rest is
+            # one more contiguous range.  Table sizes are multiples of 16 floats, so the 16-byte vector atomics stay aligned.
             n_scratch = ops.bwd_scratch_floats(self.field)
-            sizes = [sdf_table.numel(), rgb_table.numel()] + [t.numel() for t in self.dec] + [1, max_frames * 7]   # ..., beta, d pose
+            sizes = [rgb_table.numel(), sdf_table.numel()] + [t.numel() for t in self.dec] + [1, max_frames * 7]   # ..., beta, d pose
             pad = (-sum(sizes)) % 32                                  # keep the scratch block 128-byte aligned (16-byte vector atomics)
             sizes += [pad, max(n_scratch, 4), L.LOSS_SLOTS, max_frames * 12]   # + loss accumulators + d c2w: one memset clears all
             # grad_alloc(numel) -> zero-filled fp32 tensor: multi-GPU runs hand out peer-mapped (symmetric) memory here so that
@@ -75,7 +76,7 @@ class _FieldState:
             for s_ in sizes:
                 views.append(self.g_all[o:o + s_])
                 o += s_
-            self.g_sdf_table, self.g_rgb_table = views[0], views[1]
+            self.g_rgb_table, self.g_sdf_table = views[0], views[1]
             self.g_dec = [v.view(t.shape) for v, t in zip(views[2:-6], self.dec)]
             self.g_beta = views[-6]
             self.d_pose = views[-5].view(max_frames, 7)             # inside the gradient block: one all-reduce covers it
@@ -141,6 +142,7 @@ class MappingStep(_Profiled):
         self.n_rays = 0
         self.acc_hook = None      # multi-GPU: called with self.acc between loss_fwd and loss_bwd (all-reduce of sums/counts)
         self.rgb_grads_hook = None  # multi-GPU: called with the colour-table gradient as soon as its half of field_bwd is queued
+        self.bwd_leave_room = False # with the hook: the sdf half leaves one CTA slot per SM to the exchange kernel running beside it
         # independent pieces (gradient zero-fill; pose-gradient reduction) run on a side stream next to the critical path
         self.side_branches = True       # set False to run the zero-fill and the pose reduction on the main stream (ablation)
         self._side = None
@@ -279,7 +281,7 @@ class MappingStep(_Profiled):
                        ptr(fs.g_rgb_table), fs.g_mlp, ptr(fs.scratch), 2, st)
             self.rgb_grads_hook(fs.g_rgb_table)
             self._call("usl_field_bwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), v(self.d_raw), ptr(fs.g_sdf_table),
-                       ptr(fs.g_rgb_table), fs.g_mlp, ptr(fs.scratch), 1, st)
+                       ptr(fs.g_rgb_table), fs.g_mlp, ptr(fs.scratch), 1 | (4 if self.bwd_leave_room else 0), st)
         if joint:
             if fork:
                 cur.wait_stream(side)
