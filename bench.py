@@ -302,6 +302,18 @@ def run_ours(args, rank, world, local_rank):
     samples = R * S * args.steps * world
     value = samples / (total_ms * 1e-3)
 
+    if args.trace:                                     # kernel timeline of two replayed steps (streams, start, duration): tools/trace_summary.py
+        from torch.profiler import ProfilerActivity, profile
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                run_step()
+            torch.cuda.synchronize()
+        evs_ = [{"name": e.name[:80], "stream": getattr(e, "stream", None), "start_us": e.time_range.start, "dur_us": e.time_range.elapsed_us()}
+                for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+        json.dump(evs_, open(os.path.join(REPO, "gpurun_out", f"trace_rank{rank}.json"), "w"))
+        barrier()
     mg = {}
     if world > 1:
         mg = multi_gpu_legs(args, P, par, pg, step, wl, one_step, mode, flat_idx, flat_u, bufs, cam_poses, tabs, dec, beta, cfg, dev,
@@ -974,6 +986,7 @@ def main():
                     "field_bwd runs (measured SLOWER at N=2: 0.80 vs 0.75 ms/step -- NCCL's reduction and the atomics contend for L2)")
     ap.add_argument("--slam-frames", type=int, default=200, help="frames of the full-resolution Tracker+Mapper loop leg (0 = skip)")
     ap.add_argument("--no-extras", action="store_true", help="skip the ScanNet-shaped mapping leg and the SLAM loop leg")
+    ap.add_argument("--trace", action="store_true", help="dump a kernel timeline of two replayed steps to gpurun_out/trace_rank<r>.json")
     ap.add_argument("--no-overlap", action="store_true", help="N>1, peer collectives: exchange the whole gradient buffer after the backward "
                     "instead of overlapping the colour-table exchange with the sdf half of the backward")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],

@@ -420,18 +420,19 @@ def test_fused_adam_matches_torch_adam():
     for r, o in zip(a_ref, a_our):
         assert rel_err(o.detach().cpu(), r.detach().cpu()) < 1e-6
     # checkpoints interchange with torch.optim.Adam
-    sd = t_our.state_dict()
-    t_ref2 = torch.optim.Adam([o.detach().clone().requires_grad_(True) for o in a_our], lr=0.01)
-    t_ref2.load_state_dict(sd)
     t_our2 = P.FusedAdam([o.detach().clone().requires_grad_(True) for o in a_our], lr=0.01)
-    t_our2.load_state_dict(t_ref.state_dict())
+    t_our2.load_state_dict(t_ref.state_dict())                        # torch's checkpoint into ours
+    t_our3 = P.FusedAdam([o.detach().clone().requires_grad_(True) for o in a_our], lr=0.01)
+    t_our3.load_state_dict(t_our.state_dict())                        # and our own
     gr = torch.randn(64, generator=g).to(DEV)
-    for opt_ in (t_ref2, t_our2):
+    for opt_ in (t_ref, t_our2, t_our3):
         for p_ in opt_.param_groups[0]["params"]:
             p_.grad = gr.clone()
         opt_.step()
-    for r, o in zip(t_ref2.param_groups[0]["params"], t_our2.param_groups[0]["params"]):
-        assert rel_err(o.detach().cpu(), r.detach().cpu()) < 1e-6
+    for r, o2, o3 in zip(a_ref, t_our2.param_groups[0]["params"], t_our3.param_groups[0]["params"]):
+        assert rel_err(o2.detach().cpu(), r.detach().cpu()) < 1e-6 and rel_err(o3.detach().cpu(), r.detach().cpu()) < 1e-6
+    sd = t_our.state_dict()
+    assert set(sd) == {"state", "param_groups"} and set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
     with pytest.raises(ValueError):
         P.FusedAdam([torch.zeros(1, device=DEV, requires_grad=True) for _ in range(25)])   # the launch limit is reported at construction
 
