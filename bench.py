@@ -205,7 +205,7 @@ def run_ours(args, rank, world, local_rank):
 
     reduce_grads = None
     if world > 1:
-        reduce_grads = par.attach_peer_collectives(step, pg, overlap=not args.no_overlap) if pg else par.attach_mapping_collectives(step, overlap=args.overlap)
+        reduce_grads = par.attach_peer_collectives(step, pg, overlap=args.overlap) if pg else par.attach_mapping_collectives(step, overlap=args.overlap)
     my_rays = par.slab_range(R, rank, world)                           # strong scaling: this rank's contiguous slice of the batch
     mode = {"strong": False}                                           # flipped for the strong-scaling leg
 
@@ -982,13 +982,11 @@ def main():
     ap.add_argument("--no-joint", action="store_true", help="ablation: no joint pose optimisation (no Jacobian in the forward pass)")
     ap.add_argument("--config", default="replica_room0", choices=["replica_room0", "scannet_scene0000"],
                     help="workload: BASELINE configs[1] (default, the metric's config) or configs[2] (ScanNet-shaped; extra)")
-    ap.add_argument("--overlap", action="store_true", help="N>1: all-reduce the colour-table gradient on a side stream while the sdf half of "
-                    "field_bwd runs (measured SLOWER at N=2: 0.80 vs 0.75 ms/step -- NCCL's reduction and the atomics contend for L2)")
+    ap.add_argument("--overlap", action="store_true", help="N>1: exchange the colour-table gradient on a side stream while the sdf half of "
+                    "field_bwd runs (measured: 565 vs 577 us at N=2, 623 vs 613 us at N=4 -- off by default)")
     ap.add_argument("--slam-frames", type=int, default=200, help="frames of the full-resolution Tracker+Mapper loop leg (0 = skip)")
     ap.add_argument("--no-extras", action="store_true", help="skip the ScanNet-shaped mapping leg and the SLAM loop leg")
     ap.add_argument("--trace", action="store_true", help="dump a kernel timeline of two replayed steps to gpurun_out/trace_rank<r>.json")
-    ap.add_argument("--no-overlap", action="store_true", help="N>1, peer collectives: exchange the whole gradient buffer after the backward "
-                    "instead of overlapping the colour-table exchange with the sdf half of the backward")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N>1: gradient / loss-sum exchange by the hand-written peer-memory kernels (csrc/collective.cu, default) or by NCCL")
     ap.add_argument("--quick", action="store_true", help="mapping step only (used under ncu): skip e2e / tracking / dense query / Adam / cpu baseline")

@@ -147,15 +147,18 @@ class FusedShardedAdam:
                len(self.ranges), self.betas[0], self.betas[1], self.eps, 0, L.ptr(self.step_dev), L.stream())
 
 
-def attach_peer_collectives(step, pg: PeerGroup, overlap: bool = True):
+def attach_peer_collectives(step, pg: PeerGroup, overlap: bool = False):
     """Wire the hand-written exchange steps onto a MappingStep whose gradient buffer came from pg.alloc.  Returns
     reduce_grads(), to be called after step.run().
 
-    overlap=True (default): the backward runs as two launches, colour grid first; the colour-table gradient (87 % of the bytes,
-    the first contiguous range of the flat buffer) is exchanged on a side stream by a one-CTA-per-SM kernel WHILE the sdf half
+    overlap=False (default): one usl_allreduce_sum over the whole buffer after the backward.
+    overlap=True: the backward runs as two launches, colour grid first; the colour-table gradient (87 % of the bytes, the
+    first contiguous range of the flat buffer) is exchanged on a side stream by a one-CTA-per-SM kernel WHILE the sdf half
     of the backward runs (which leaves one CTA slot per SM free for it); reduce_grads() then exchanges the remaining range
     [sdf table | decoders | beta | poses] and joins the side stream.  CUDA-graph capturable (fork / join on events).
-    overlap=False: one usl_allreduce_sum over the whole buffer after the backward."""
+    Measured (kernel timeline, bench.py --trace): the exchange does run beside the sdf half, but sharing the SMs stretches
+    it from 90 to 150 us and the split backward costs 20 us more than the single launch: 565 vs 577 us per step at N = 2,
+    623 vs 613 us at N = 4 -- hence off by default."""
     step.acc_hook = pg.exchange_sums
     fs = step.fs
     if not overlap:
