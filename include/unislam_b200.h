@@ -135,6 +135,19 @@ USL_API int usl_sample_window_rays(const float *c2w, const float *depth, const f
 USL_API int usl_image_rays(const float *c2w, int H, int W, float fx, float fy, float cx, float cy,
                    float *rays_o, float *rays_d, usl_stream_t stream);
 
+/* ---- f2: keyframe store + co-visibility (src/Mapper.py:177-236, 528-541) ---------------------------------------------------
+ * A keyframe is stored as a pixel subset: gather colour[H*W,3] / depth[H*W] / camera dirs[H*W,3] at indices[P]
+ * (torch.randperm(H*W)[:P]) into the store's rows in one launch (idx_row nullable). */
+USL_API int usl_keyframe_insert(const float *color_img, const float *depth_img, const float *dirs_cam, const int64_t *indices,
+                                int64_t P, float *color_row, float *depth_row, float *dirs_row, int64_t *idx_row,
+                                usl_stream_t stream);
+/* keyframe_selection_LC's overlap measure: percent_inside[k] = fraction of the points sampled in [0.8 d, d + 0.5] along the n rays
+ * with sensor depth (num_samples each, torch.linspace) that project inside keyframe k's image minus `edge` pixels, in front of
+ * the camera (c2ws[K,4,4] estimated poses; OpenGL convention, x flipped as in Mapper.py:222). */
+USL_API int usl_keyframe_covisibility(const float *rays_o, const float *rays_d, const float *gt_depth, int64_t n, int num_samples,
+                                      const float *c2ws, int K, int H, int W, float fx, float fy, float cx, float cy,
+                                      float edge, float *percent_inside, usl_stream_t stream);
+
 /* ---- a-4: ray/bbox exit distance (Mapper.py:396-401, Tracker.py:177-183) ------------------- */
 /* t_exit[n]; valid[n] = t_exit >= gt_depth (&& gt_depth > 0 when require_depth) */
 USL_API int usl_bbox_prefilter(const float *rays_o, const float *rays_d, const float *gt_depth, int64_t n,

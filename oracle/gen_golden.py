@@ -40,6 +40,8 @@ CASES = {
     # Mesher.get_grid_uniform + eval_points (Mesher.py:134-195): the dense SDF query seam, coarse grids (ragged counts)
     "mesh_replica": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, resolution=0.37),
     "mesh_scannet": dict(yaml="configs/ScanNet/scene0000.yaml", H=23, W=31, s=0.05, resolution=0.53),
+    # Mapper.keyframe_selection_LC (Mapper.py:177-236): the co-visibility measure between the current frame and every keyframe
+    "kf_covis_replica": dict(yaml="configs/Replica/room0.yaml", H=60, W=80, s=1 / 15.0, n_kf=9),
     # Renderer.render_img (Renderer.py:160-223): whole frame in ray_batch_size chunks, last chunk ragged
     "img_replica": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, ray_batch=500),
     "img_scannet": dict(yaml="configs/ScanNet/scene0000.yaml", H=23, W=31, s=0.05, ray_batch=300),
@@ -107,6 +109,14 @@ class Recorder:
         torch.optim.Adam.step = step
         M.get_samples_all = gsa
         T.get_samples = gs
+        self._m_gs = getattr(M, "get_samples", None)      # keyframe_selection_LC samples through Mapper's own import of it
+        if self._m_gs is not None:
+            def mgs(*a, **k):
+                out = rec._m_gs(*a, **k)
+                rec.samples.append(dict(kind="win", args=[x.detach().clone() if torch.is_tensor(x) else x for x in a],
+                                        out=[o.detach().clone() for o in out]))
+                return out
+            M.get_samples = mgs
 
     def uninstall(self):
         import src.Mapper as M
@@ -117,6 +127,8 @@ class Recorder:
         torch.optim.Adam.step = self._orig["step"]
         M.get_samples_all = self._orig["gsa"]
         T.get_samples = self._orig["gs"]
+        if self._m_gs is not None:
+            M.get_samples = self._m_gs
 
 
 def _load_cfg(case):
@@ -421,6 +433,52 @@ def gen_mesh_query(name, case):
     print(name, "points", pts.shape[0], "dims", [len(a) for a in grid["xyz"]], "outside", int((ret[:, 3] == -1).sum()))
 
 
+def gen_covisibility(name, case):
+    """Runs the unmodified Mapper.keyframe_selection_LC and records its inputs, the torch.randint draw, percent_inside (the
+    argument of its torch.argmax) and the returned selection."""
+    from src.Mapper import Mapper
+    cfg = _load_cfg(case)
+    H, W = case["H"], case["W"]
+    cam = cfg["cam"]
+    n_kf = case["n_kf"]
+    frames, dirs = _frames(cfg, case, n_kf + 1, seed=17)
+    m = object.__new__(Mapper)
+    m.cfg = cfg; m.device = "cpu"
+    m.H, m.W, m.fx, m.fy, m.cx, m.cy = H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"]
+    m.LC = cfg["mapping"]["LC"]; m.LC_cnt = torch.zeros(1).int(); m.tracking_back = torch.tensor([0])
+    m.activated_mapping_mode = False
+    torch.manual_seed(23)
+    m.keyframe_list = [4 * k for k in range(n_kf)]
+    est = torch.zeros(4 * (n_kf + 1) + 1, 4, 4)
+    for k in range(n_kf):
+        c = frames[k][2].clone(); c[:3, 3] += 0.01 * torch.randn(3)
+        est[4 * k] = c
+    m.estimate_c2w_list = est
+    col, dep, c2w = frames[n_kf]
+    rec = Recorder(); rec.install()
+    percent = []
+    orig_argmax = torch.argmax
+
+    def argmax(t, *a, **k):
+        percent.append(t.detach().clone()); return orig_argmax(t, *a, **k)
+    torch.argmax = argmax
+    try:
+        torch.manual_seed(29)
+        sel = m.keyframe_selection_LC(n_kf - 2, 4 * n_kf, col, dep, c2w, 4)
+    finally:
+        torch.argmax = orig_argmax
+        rec.uninstall()
+    out = {"meta_H_W_fx_fy_cx_cy": np.array([H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"]], dtype=np.float64),
+           "color_img": _np(col), "depth_img": _np(dep), "c2w": _np(c2w), "keyframe_c2ws": _np(torch.stack([est[i] for i in m.keyframe_list])),
+           "indices": _np([t for k, t in rec.draws if k == "randint"][-1]), "percent_inside": _np(percent[0]), "selected": np.array(sel),
+           "num_samples": np.array(8), "num_rays": np.array(50), "edge": np.array(20)}
+    s_ = rec.samples[-1]
+    for nm, o in zip(("rays_o", "rays_d", "depth", "color"), s_["out"]):
+        out["sample_out_" + nm] = _np(o)
+    _save(name, out)
+    print(name, "keyframes", n_kf, "percent_inside", _np(percent[0]).round(3), "selected", sel)
+
+
 def gen_render_img(name, case):
     from src.utils.Renderer import Renderer
     cfg = _load_cfg(case)
@@ -467,6 +525,8 @@ def main():
             continue
         if name.startswith("map"):
             gen_mapping(name, case)
+        elif name.startswith("kf_covis"):
+            gen_covisibility(name, case)
         elif name.startswith("img"):
             gen_render_img(name, case)
         elif name.startswith("mesh"):

@@ -513,6 +513,33 @@ def tracking_iteration(field: Field, cam_pose, depth_img, color_img, H, W, fx, f
 
 
 # ----------------------------------------------------------------------------------------------
+# keyframe co-visibility  (src/Mapper.py:177-236)
+# ----------------------------------------------------------------------------------------------
+def keyframe_covisibility(rays_o, rays_d, gt_depth, keyframe_c2ws, H, W, fx, fy, cx, cy, num_samples=8, edge=20):
+    """percent_inside of Mapper.keyframe_selection_LC (Mapper.py:199-236): points sampled in [0.8 d, d + 0.5] along the rays
+    with sensor depth, projected into every keyframe (the caller drops the last two, Mapper.py:214)."""
+    dev = rays_o.device
+    gt_depth = gt_depth.reshape(-1, 1)
+    nz = gt_depth[:, 0] > 0
+    rays_o, rays_d, gt_depth = rays_o[nz], rays_d[nz], gt_depth[nz].repeat(1, num_samples)
+    t_vals = torch.linspace(0., 1., steps=num_samples).to(dev)
+    z_vals = gt_depth * 0.8 * (1. - t_vals) + (gt_depth + 0.5) * t_vals
+    pts = (rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]).reshape(1, -1, 3)
+    w2cs = torch.inverse(keyframe_c2ws)
+    ones = torch.ones_like(pts[..., 0]).reshape(1, -1, 1)
+    homo = torch.cat([pts, ones], dim=-1).reshape(1, -1, 4, 1).expand(w2cs.shape[0], -1, -1, -1)
+    cam = (w2cs.unsqueeze(1).expand(-1, homo.shape[1], -1, -1) @ homo)[:, :, :3]
+    K = torch.tensor([[fx, .0, cx], [.0, fy, cy], [.0, .0, 1.0]], device=dev).reshape(3, 3)
+    cam[:, :, 0] *= -1
+    uv = K @ cam
+    z = uv[:, :, -1:] + 1e-5
+    uv = uv[:, :, :2] / z
+    mask = (uv[:, :, 0] < W - edge) * (uv[:, :, 0] > edge) * (uv[:, :, 1] < H - edge) * (uv[:, :, 1] > edge)
+    mask = (mask & (z[:, :, 0] < 0)).squeeze(-1)
+    return mask.sum(dim=1) / uv.shape[1]
+
+
+# ----------------------------------------------------------------------------------------------
 # dense SDF query for meshing  (src/utils/Mesher.py:134-195)
 # ----------------------------------------------------------------------------------------------
 def mesh_grid_axes(mc_bound, resolution=0.01, padding=0.05):

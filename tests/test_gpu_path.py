@@ -610,3 +610,47 @@ def test_peer_collectives_single_rank_and_sharded_adam():
     assert rel_err(params[:split].cpu(), ref[0].detach().cpu()) < 1e-6
     assert rel_err(params[split:n - 64].cpu(), ref[1].detach().cpu()) < 1e-6
     assert torch.equal(params[n - 64:], tail)            # floats outside every learning-rate range are left untouched
+
+
+def test_keyframe_store_on_device_matches_reference():
+    """f2 on the GPU: the device-resident KeyframeStore (usl_keyframe_insert) holds the tensors the unmodified reference stacks
+    (fixture map_replica_kfstore), a MappingStep fed from its views reproduces the reference's loss, and the co-visibility
+    measure of keyframe_selection_LC (usl_keyframe_covisibility) matches the reference's percent_inside."""
+    P = pkg()
+    g = load_golden("map_replica_kfstore")
+    H, W = int(g["meta_H_W_fx_fy_cx_cy"][0]), int(g["meta_H_W_fx_fy_cx_cy"][1])
+    col, dep, gtc = T(g["frames_color"]).to(DEV), T(g["frames_depth"]).to(DEV), T(g["frames_gt_c2w"]).to(DEV)
+    dirs = T(g["dirs_cam"]).to(DEV)
+    n_kf = g["kf_indices"].shape[0]
+    store = P.KeyframeStore(capacity=8, H=H, W=W, device=DEV)
+    for k in range(n_kf):
+        store.append(int(g["kf_frame_idx"][k]), col[k], dep[k], dirs, T(g["kf_est_c2w"][k]).to(DEV), gtc[k], indices=T(g["kf_indices"][k]).to(DEV))
+    store.stage_current(col[n_kf], dep[n_kf], dirs, T(g["cur_c2w"]).to(DEV), gtc[n_kf], indices=T(g["cur_randperm"])[:store.P].to(DEV))
+    c2ws, depths, colors, rays_d = store.window()
+    for got, key in ((c2ws, "call0_c2ws"), (depths, "call0_depths"), (colors, "call0_colors"), (rays_d, "call0_rays_d_cam")):
+        assert torch.equal(got.cpu(), T(g[key])), key
+    assert torch.equal(store.pixel_idx[0].cpu(), T(g["kf_indices"][0]))
+    # the mapping iteration straight from the store's views
+    meta, tabs, dec, beta = gpu_cases.cuda_field(g, 0, DEV)
+    ns, ni = int(g["n_stratified"]), int(g["n_importance"]); S = ns + ni
+    n = int(g["call0_n"])
+    batches = store.mapping_batches(T(g["call0_indices"]).to(DEV), n)
+    R = depths.shape[0] * n
+    ro = T(g["call0_out_rays_o"]); rd = T(g["call0_out_rays_d"]); dd = T(g["call0_out_depth"])
+    inside = path_ref.bbox_exit(ro, rd, T(g["bound"])) >= dd
+    t_rand, t_uni, u_pdf, has_holes = gpu_cases._slot_draws(g, inside, dd, S, ns, ni, DEV)
+    step = P.MappingStep(meta, tabs[0], tabs[1], dec, beta, n_stratified=ns, n_importance=ni, truncation=float(g["truncation"]), max_rays=R, max_frames=8)
+    loss = step.run(batches, t_rand, t_uni, u_pdf, has_holes=has_holes)
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-4
+    # co-visibility
+    c = load_golden("kf_covis_replica")
+    Hc, Wc, fx, fy, cx, cy = [float(v) for v in c["meta_H_W_fx_fy_cx_cy"]]
+    kc = T(c["keyframe_c2ws"]).to(DEV)
+    st2 = P.KeyframeStore(capacity=12, H=int(Hc), W=int(Wc), device=DEV)
+    for k in range(kc.shape[0]):
+        st2.est_c2w[k] = kc[k]; st2.frame_idx.append(4 * k)
+    pi = st2.covisibility(T(c["sample_out_rays_o"]).to(DEV), T(c["sample_out_rays_d"]).to(DEV), T(c["sample_out_depth"]).to(DEV),
+                          int(Hc), int(Wc), fx, fy, cx, cy, int(c["num_samples"]), float(c["edge"]))
+    ref = T(c["percent_inside"])
+    n_pts = int((T(c["sample_out_depth"]) > 0).sum()) * int(c["num_samples"])
+    assert (pi.cpu() - ref).abs().max() <= 1.5 / n_pts                  # at most one borderline point (fp32 inverse vs closed form)

@@ -120,3 +120,14 @@ def test_mesh_query_matches_reference(name):
     ref = T(g["sdf"])
     assert torch.equal(sdf == -1, ref == -1)
     assert (sdf - ref).abs().max() < 1e-6
+
+
+def test_keyframe_covisibility_matches_reference():
+    """Mapper.keyframe_selection_LC's overlap measure (Mapper.py:177-236) of the unmodified reference vs the oracle's restatement."""
+    g = load_golden("kf_covis_replica")
+    H, W, fx, fy, cx, cy = [float(v) for v in g["meta_H_W_fx_fy_cx_cy"]]
+    ro, rd, d, _ = path_ref.sample_tracking_rays(0, int(H), 0, int(W), int(g["num_rays"]), fx, fy, cx, cy, T(g["c2w"])[None],
+                                                 T(g["depth_img"])[None], T(g["color_img"])[None], T(g["indices"]))
+    assert torch.equal(ro, T(g["sample_out_rays_o"])) and torch.equal(rd, T(g["sample_out_rays_d"])) and torch.equal(d, T(g["sample_out_depth"]))
+    pi = path_ref.keyframe_covisibility(ro, rd, d, T(g["keyframe_c2ws"])[:-2], int(H), int(W), fx, fy, cx, cy, int(g["num_samples"]), int(g["edge"]))
+    assert torch.equal(pi, T(g["percent_inside"]))

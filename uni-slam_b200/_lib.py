@@ -131,6 +131,8 @@ _SIGS = {
     "usl_composite_loss_bwd": [POINTER(LossArgs), _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, POINTER(Bound),
                                _P, _P, _P, _P, _P, _P],
     "usl_adam_step": [POINTER(AdamGroup), c_int, c_int64, _P, c_int, _P],
+    "usl_keyframe_insert": [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P],
+    "usl_keyframe_covisibility": [_P, _P, _P, c_int64, c_int, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, _P, _P],
     "usl_mc_classify": [POINTER(McArgs), _P],
     "usl_mc_emit": [POINTER(McArgs), _P],
     "usl_scan_u8": [_P, c_int64, c_int, _P, _P, _P, _P],

@@ -446,11 +446,107 @@ __global__ void __launch_bounds__(128) zsample_nodepth_kernel(const __grid_const
     }
 }
 
+// ---- f2: keyframe store (src/Mapper.py:528-541) and co-visibility (Mapper.py:177-236) --------------------------------
+// A frame becomes a keyframe as a 10 % pixel subset: one launch gathers colour / depth / camera direction of the drawn pixels
+// into the store's row (the reference does three boolean-free index ops + a dict of tensors per keyframe).
+__global__ void __launch_bounds__(256) keyframe_insert_kernel(const float *__restrict__ color, const float *__restrict__ depth,
+                                                              const float *__restrict__ dirs, const int64_t *__restrict__ indices,
+                                                              int64_t P, float *__restrict__ color_row, float *__restrict__ depth_row,
+                                                              float *__restrict__ dirs_row, int64_t *__restrict__ idx_row) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int64_t src = indices[i];
+    depth_row[i] = depth[src];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { color_row[i * 3 + a] = color[src * 3 + a]; dirs_row[i * 3 + a] = dirs[src * 3 + a]; }
+    if (idx_row) idx_row[i] = src;
+}
+
+// keyframe_selection_LC's overlap measure: sample num_samples points in [0.8 d, d + 0.5] along every ray with sensor depth,
+// project them into every keyframe and report the fraction that lands inside the image (minus an edge) in front of the camera.
+// One CTA per keyframe; the world-to-camera matrix is the closed-form inverse of the rigid c2w (R^T, -R^T t) in double.
+struct CovisArgs {
+    const float *rays_o, *rays_d, *gt_depth;
+    int64_t n;
+    int num_samples;
+    const float *c2ws;
+    int K, H, W;
+    float fx, fy, cx, cy, edge;
+    float *percent_inside;
+};
+__global__ void __launch_bounds__(256) keyframe_covis_kernel(const __grid_constant__ CovisArgs A) {
+    __shared__ float s_w2c[12];
+    __shared__ int s_cnt[2];
+    const int k = blockIdx.x;
+    if (threadIdx.x == 0) {
+        const float *c = A.c2ws + (int64_t)k * 16;
+        // general 3x3 inverse (adjugate / determinant) in double: equals R^T for a rotation, and stays exact enough for the
+        // un-normalised rotations the optimiser produces
+        double m[9] = {c[0], c[1], c[2], c[4], c[5], c[6], c[8], c[9], c[10]};
+        const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+        const double id = 1.0 / det;
+        double inv[9] = {(m[4] * m[8] - m[5] * m[7]) * id, (m[2] * m[7] - m[1] * m[8]) * id, (m[1] * m[5] - m[2] * m[4]) * id,
+                         (m[5] * m[6] - m[3] * m[8]) * id, (m[0] * m[8] - m[2] * m[6]) * id, (m[2] * m[3] - m[0] * m[5]) * id,
+                         (m[3] * m[7] - m[4] * m[6]) * id, (m[1] * m[6] - m[0] * m[7]) * id, (m[0] * m[4] - m[1] * m[3]) * id};
+        const double t[3] = {c[3], c[7], c[11]};
+        for (int r = 0; r < 3; ++r) {
+            s_w2c[r * 4 + 0] = (float)inv[r * 3]; s_w2c[r * 4 + 1] = (float)inv[r * 3 + 1]; s_w2c[r * 4 + 2] = (float)inv[r * 3 + 2];
+            s_w2c[r * 4 + 3] = (float)(-(inv[r * 3] * t[0] + inv[r * 3 + 1] * t[1] + inv[r * 3 + 2] * t[2]));
+        }
+        s_cnt[0] = 0; s_cnt[1] = 0;
+    }
+    __syncthreads();
+    int inside = 0, total = 0;
+    const int64_t M = A.n * A.num_samples;
+    for (int64_t j = threadIdx.x; j < M; j += blockDim.x) {
+        const int64_t r = j / A.num_samples;
+        const int q = (int)(j - r * A.num_samples);
+        const float d = A.gt_depth[r];
+        if (!(d > 0.f)) continue;                                        // nonzero_depth filter (Mapper.py:201-204)
+        ++total;
+        const float tv = (A.num_samples > 1) ? (float)q / (float)(A.num_samples - 1) : 0.f;     // torch.linspace(0, 1, num_samples)
+        const float z = (d * 0.8f) * (1.0f - tv) + (d + 0.5f) * tv;
+        float p[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) p[a] = A.rays_o[r * 3 + a] + A.rays_d[r * 3 + a] * z;
+        float cc[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) cc[a] = s_w2c[a * 4] * p[0] + s_w2c[a * 4 + 1] * p[1] + s_w2c[a * 4 + 2] * p[2] + s_w2c[a * 4 + 3];
+        cc[0] = -cc[0];                                                  // cam_cords[:, :, 0] *= -1
+        const float zz = cc[2] + 1e-5f;                                  // uv = K @ cam; z = uv_z + 1e-5
+        const float u = (A.fx * cc[0] + A.cx * cc[2]) / zz, v = (A.fy * cc[1] + A.cy * cc[2]) / zz;
+        const bool in = (u < A.W - A.edge) && (u > A.edge) && (v < A.H - A.edge) && (v > A.edge) && (zz < 0.f);
+        inside += in ? 1 : 0;
+    }
+    atomicAdd(&s_cnt[0], inside); atomicAdd(&s_cnt[1], total);
+    __syncthreads();
+    if (threadIdx.x == 0) A.percent_inside[k] = s_cnt[1] > 0 ? (float)s_cnt[0] / (float)s_cnt[1] : 0.f;
+}
+
 }  // namespace usl
 
 using namespace usl;
 
 extern "C" {
+
+int usl_keyframe_insert(const float *color_img, const float *depth_img, const float *dirs_cam, const int64_t *indices, int64_t P,
+                        float *color_row, float *depth_row, float *dirs_row, int64_t *idx_row, usl_stream_t stream) {
+    if (P <= 0) return 0;
+    if (!color_img || !depth_img || !dirs_cam || !indices || !color_row || !depth_row || !dirs_row) { set_error("usl_keyframe_insert: null argument"); return 1; }
+    keyframe_insert_kernel<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(color_img, depth_img, dirs_cam, indices, P, color_row,
+                                                                                           depth_row, dirs_row, idx_row);
+    return check_launch("usl_keyframe_insert");
+}
+
+int usl_keyframe_covisibility(const float *rays_o, const float *rays_d, const float *gt_depth, int64_t n, int num_samples,
+                              const float *c2ws, int K, int H, int W, float fx, float fy, float cx, float cy, float edge,
+                              float *percent_inside, usl_stream_t stream) {
+    if (K <= 0) return 0;
+    if (!rays_o || !rays_d || !gt_depth || !c2ws || !percent_inside || n < 0 || num_samples < 1) { set_error("usl_keyframe_covisibility: bad arguments"); return 1; }
+    CovisArgs A{rays_o, rays_d, gt_depth, n, num_samples, c2ws, K, H, W, fx, fy, cx, cy, edge, percent_inside};
+    keyframe_covis_kernel<<<(unsigned)K, 256, 0, (cudaStream_t)stream>>>(A);
+    return check_launch("usl_keyframe_covisibility");
+}
 
 int usl_sample_keyframe_rays(const float *c2ws, const float *depths, const float *colors, const float *dirs_cam,
                              const int64_t *indices, int K, int64_t P, int n, int frame_base, float *rays_o,

@@ -44,6 +44,16 @@ class KeyframeStore:
         if indices is None:
             indices = torch.randperm(self.H * self.W)[:self.P]  # CPU generator, as the reference draws it (Mapper.py:532)
         ind = indices.to(self.device)
+        if self.depth.is_cuda:
+            # one launch gathers the three arrays into the store's row (usl_keyframe_insert)
+            from . import _lib as L
+            f32 = lambda t: t.to(self.device, torch.float32).contiguous()
+            L.call("usl_keyframe_insert", L.ptr(f32(color_img)), L.ptr(f32(depth_img)), L.ptr(f32(dirs_cam)), L.ptr(ind.to(torch.int64).contiguous()),
+                   self.P, L.ptr(self.color[row]), L.ptr(self.depth[row]), L.ptr(self.rays_d[row]), L.ptr(self.pixel_idx[row]), L.stream())
+            self.est_c2w[row] = est_c2w
+            if gt_c2w is not None:
+                self.gt_c2w[row] = gt_c2w
+            return indices
         self.color[row] = color_img.reshape(-1, 3)[ind]
         self.depth[row] = depth_img.reshape(-1)[ind]
         self.rays_d[row] = dirs_cam.reshape(-1, 3)[ind]
@@ -109,6 +119,19 @@ class KeyframeStore:
             self.est_c2w[f] = c2ws[j]
         self.est_c2w[K] = c2ws[-1]
         return c2ws[-1]
+
+    # ---- co-visibility (keyframe_selection_LC, Mapper.py:177-236) -----------------------------------------------------
+    def covisibility(self, rays_o, rays_d, gt_depth, H, W, fx, fy, cx, cy, num_samples: int = 8, edge: float = 20.0, skip_last: int = 2):
+        """percent_inside over the stored keyframes except the last `skip_last` (which the mapper always includes,
+        Mapper.py:214): one launch, result stays on the device.  The selection policy built on it stays host code."""
+        from . import _lib as L
+        K = len(self) - skip_last
+        out = torch.zeros((max(K, 0),), device=self.device, dtype=torch.float32)
+        if K > 0:
+            L.call("usl_keyframe_covisibility", L.ptr(rays_o.contiguous()), L.ptr(rays_d.contiguous()), L.ptr(gt_depth.contiguous()),
+                   rays_o.shape[0], int(num_samples), L.ptr(self.est_c2w[:K].contiguous()), K, int(H), int(W), float(fx), float(fy), float(cx),
+                   float(cy), float(edge), L.ptr(out), L.stream())
+        return out
 
     # ---- wire format ---------------------------------------------------------------------------------------------------
     def as_dicts(self):
