@@ -75,8 +75,10 @@ def traffic(path):
             continue
         unit = rows[1][ci["dram__bytes_read.sum"]] if "dram__bytes_read.sum" in ci else "byte"
         mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        tunit = rows[1][ci["gpu__time_duration.sum"]] if "gpu__time_duration.sum" in ci else "us"
+        tmul = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(tunit, 1.0)
         out[key] = {
-            "duration_us_under_ncu": get(r, "gpu__time_duration.sum"),
+            "duration_us_under_ncu": get(r, "gpu__time_duration.sum") * tmul,
             "dram_bytes": (get(r, "dram__bytes_read.sum") + get(r, "dram__bytes_write.sum")) * mul,
             "lts_sectors_read": get(r, "lts__t_sectors_srcunit_tex_op_read.sum"), "lts_sectors_write": get(r, "lts__t_sectors_srcunit_tex_op_write.sum"),
             "lts_sectors_red": get(r, "lts__t_sectors_srcunit_tex_op_red.sum"),
