@@ -364,6 +364,27 @@ def test_dense_sdf_query_matches_oracle():
     assert (out - ref).abs().max() < 2e-5
 
 
+def test_dense_sdf_query_fine_grid_matches_oracle():
+    """The production spacing (1 cm): neighbouring lanes sit in the same or adjacent columns on EVERY level, i.e. the x-line
+    decode (one collapsed column per lane + a shuffle) runs on all 16 levels, incl. ragged row ends, the far bound (x = 1
+    wrap) and points outside the open bound.  Against the oracle's eval_points on the same points."""
+    P = pkg()
+    g = load_golden("map_replica_k7")
+    meta, tabs, dec, beta = gpu_cases.cuda_field(g, 0, DEV)
+    field = golden_field(g, 0, requires_grad=False)
+    b = T(g["bound"])
+    ax = [torch.arange(float(b[0, 1]) - 0.835, float(b[0, 1]) + 0.06, 0.01),        # 90 points along x, crossing the far bound
+          torch.arange(float(b[1, 0]) - 0.02, float(b[1, 0]) + 0.05, 0.01),         # 7 rows, the first two outside
+          torch.arange(0.1, 0.23, 0.01)]                                            # 13 z: one full and one ragged z tile
+    pts = path_ref.mesh_grid_points(ax)
+    with torch.no_grad():
+        ref = path_ref.eval_points_sdf(field, pts)
+    q = P.DenseSdfQuery(meta, tabs[0], tabs[1], dec, [a.to(DEV) for a in ax])
+    got = q.run(0, q.ny).cpu()
+    assert torch.equal(got == -1, ref == -1) and int((ref == -1).sum()) > 0
+    assert (got - ref).abs().max() < 2e-6
+
+
 @pytest.mark.parametrize("name", ["mesh_replica", "mesh_scannet"])
 def test_dense_sdf_query_matches_reference(name):
     """a-11 against the unmodified reference: Mesher.get_grid_uniform + eval_points output (tests/golden/mesh_*.npz),

@@ -168,8 +168,12 @@ __global__ void __launch_bounds__(256) sdf_query_grid_kernel(const __grid_consta
         float v = -1.0f;                                                                // Mesher.py:162
         if (inside) {
             float out[4], tout[4][3];
-            decode_point<false, false>(A.f.grid[0], reinterpret_cast<const float2 *>(A.f.table[0]), A.f.mlp[0], sm,
-                                       xc, nullptr, 0, out, tout);
+            // 4 levels unrolled together: 12.25 / 12.12 / 11.40 / 12.87 ms for 1 / 2 / 4 / 16.  (Tried and measured slower, 15.0-15.9 ms:
+            // an "x-line" decode in which every lane collapses its own x column over the warp-uniform (y, z) -- 4 gathers -- and
+            // fetches the neighbouring column from the lane that holds it by shuffle; the kernel is issue-bound -- ncu: 10.3 G warp
+            // instructions, 74 % of the issue rate, L1TEX lookups at 46 % of their ceiling -- and the ballots, dynamic-lane
+            // shuffles and the divergent extra gathers of a warp's last run cost more issue slots than the 4 gathers save.)
+            decode_point<false, false, 4>(A.f.grid[0], reinterpret_cast<const float2 *>(A.f.table[0]), A.f.mlp[0], sm, xc, nullptr, 0, out, tout);
             v = out[0];
         }
         // idx = (iy*nx + ix)*nz + iz within the slab (torch.meshgrid(indexing='xy') flattened, Mesher.py:192-193)

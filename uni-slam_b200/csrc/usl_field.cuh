@@ -259,4 +259,5 @@ __device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *
     mlp_tail<WITH_JAC>(m, sm, h, th, out, tout);
 }
 
+
 }  // namespace usl
