@@ -170,3 +170,33 @@ def test_workload_draw_buffers_and_mask_modes():
     assert steps._mask_mode("original", 0) == 0 and steps._mask_mode("original", 1) == 1 and steps._mask_mode("no_mask", 0) == 2
     with pytest.raises(ValueError):
         steps._mask_mode("alpha", 0)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """Every struct the Python layer passes by pointer must have the C compiler's size and field offsets: compile a probe
+    against include/unislam_b200.h with gcc and compare with ctypes."""
+    import ctypes
+    import subprocess
+    L = importlib.import_module("uni-slam_b200._lib")
+    pairs = [("usl_level_t", L.Level), ("usl_grid_t", L.Grid), ("usl_mlp_t", L.Mlp), ("usl_field_t", L.Field), ("usl_bound_t", L.Bound),
+             ("usl_points_t", L.Points), ("usl_zsample_args_t", L.ZSampleArgs), ("usl_ray_batch_t", L.RayBatch), ("usl_ray_setup_t", L.RaySetup),
+             ("usl_loss_args_t", L.LossArgs), ("usl_adam_group_t", L.AdamGroup), ("usl_peers_t", L.Peers), ("usl_adam_range_t", L.AdamRange),
+             ("usl_mc_args_t", L.McArgs)]
+    last = {"usl_ray_setup_t": "ray_offset", "usl_peers_t": "max_ctas_per_sm", "usl_mc_args_t": "faces", "usl_adam_group_t": "step",
+            "usl_points_t": "n", "usl_field_t": "bound_hi"}
+    src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(REPO, "include", "unislam_b200.h")}"', "int main(void) {"]
+    for cname, _ in pairs:
+        src.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+    for cname, fld in last.items():
+        src.append(f'  printf("{cname}.{fld} %zu\\n", offsetof({cname}, {fld}));')
+    src.append("  return 0; }")
+    c = tmp_path / "probe.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(c)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines())
+    for cname, cls in pairs:
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+    byname = dict(pairs)
+    for cname, fld in last.items():
+        assert int(out[f"{cname}.{fld}"]) == getattr(byname[cname], fld).offset, (cname, fld)
