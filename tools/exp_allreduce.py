@@ -10,7 +10,7 @@ dist.init_process_group("nccl", device_id=torch.device(dev))
 P = importlib.import_module("uni-slam_b200")
 par = importlib.import_module("uni-slam_b200.parallel")
 n = 12915392
-res = {"world": world, "bytes": n * 4}
+res = {"world": world, "bytes": n * 4, "lib": os.environ.get("USL_LIB_PATH", "default").split("/")[-1]}
 
 
 def timeit(fn, iters=30):
@@ -41,6 +41,8 @@ for mc in (False, True):
     pg.allreduce(g, n); torch.cuda.synchronize()
     res[f"{tag}_correct"] = bool((g == world).all())
     res[f"{tag}_us"] = timeit(lambda: pg.allreduce(g, n)); res[f"{tag}_bus_gbs"] = bus(res[f"{tag}_us"])
+    for cap in (2, 4, 16):
+        res[f"{tag}_us_cap{cap}"] = timeit(lambda: pg.allreduce(g, n, max_ctas_per_sm=cap))
     fsa = par.FusedShardedAdam(pg, p, g, n, [(0, n, 1e-3)])
     res[f"{tag}_allreduce_adam_us"] = timeit(fsa.step, iters=10)
     if not mc:

@@ -215,7 +215,10 @@ __global__ void __launch_bounds__(256) allreduce_mc_kernel(const __grid_constant
     const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<float *>(A.P.mc) + A.offset);
     float4 *dst = ADAM ? reinterpret_cast<float4 *>(A.param_mc + A.offset) : reinterpret_cast<float4 *>(reinterpret_cast<float *>(A.P.mc) + A.offset);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    constexpr int U = ADAM ? 1 : 4;
+#ifndef USL_MC_UNROLL
+#define USL_MC_UNROLL 4
+#endif
+    constexpr int U = ADAM ? 1 : USL_MC_UNROLL;
     for (int64_t i0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * U) {
         float4 v[U];
 #pragma unroll
@@ -269,10 +272,13 @@ static int launch_reduce(const ReduceArgs &A, cudaStream_t s) {
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int64_t mine = A.slice4;
     int64_t blocks = (mine + 255) / 256;
-    const int64_t cap = (int64_t)n_sm * (A.P.max_ctas_per_sm > 0 ? A.P.max_ctas_per_sm : 8);
+    const bool use_mc = A.P.mc != nullptr && A.P.world > 1 && (!ADAM || A.param_mc != nullptr);
+    // grid caps as measured at 51.6 MB (tools/exp_allreduce.py): multimem likes many CTAs (16/SM: 160 us at N = 8, 8/SM: 168);
+    // the peer-to-peer form at 8 ranks likes few (2/SM: 170 us, 8/SM: 190, 16/SM: 206) -- seven remote streams per thread
+    const int per_sm = A.P.max_ctas_per_sm > 0 ? A.P.max_ctas_per_sm : use_mc ? 16 : A.P.world >= 8 ? 2 : 8;
+    const int64_t cap = (int64_t)n_sm * per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    const bool use_mc = A.P.mc != nullptr && A.P.world > 1 && (!ADAM || A.param_mc != nullptr);
     if (use_mc) {
         allreduce_mc_kernel<ADAM><<<(unsigned)blocks, 256, 0, s>>>(A);
         return check_launch(ADAM ? "usl_allreduce_adam_step (multimem)" : "usl_allreduce_sum (multimem)");

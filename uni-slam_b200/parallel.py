@@ -36,10 +36,11 @@ class PeerGroup:
       FusedShardedAdam      usl_allreduce_adam_step (see below)
 
     use_multicast=True runs the reductions through the NVSwitch (multimem.ld_reduce / multimem.st on the allocator's
-    multicast mapping).  Measured on this pool's B200 boxes for the 51.6 MB gradient buffer: N = 2: 176 us vs 111 us for
-    the peer-to-peer form, N = 4: 169 us vs 155 us (NCCL: 120 / 156 us) -- so the default is peer-to-peer loads / stores."""
+    multicast mapping).  Measured on this pool's B200 boxes for the 51.6 MB gradient buffer (us; NCCL / peer-to-peer /
+    multimem): N = 2: 120 / 111 / 176, N = 4: 156 / 155 / 169, N = 8: 232 / 190 / 168 -- so "auto" uses peer-to-peer loads and
+    stores below 8 ranks and the switch-side reduction from 8."""
 
-    def __init__(self, device, group=None, use_multicast: bool = False):
+    def __init__(self, device, group=None, use_multicast="auto"):
         import torch.distributed._symmetric_memory as symm_mem
         self._sm = symm_mem
         self.group = group if group is not None else dist.group.WORLD
@@ -49,7 +50,8 @@ class PeerGroup:
             raise RuntimeError("PeerGroup: at most 8 ranks (one NVSwitch domain)")
         self.device = device
         self._handles = {}
-        self.use_multicast = use_multicast
+        # "auto": the switch-side reduction pays off from 8 ranks (measured, see the class docstring)
+        self.use_multicast = (self.world >= 8) if use_multicast == "auto" else bool(use_multicast)
         nb = L.load().usl_peer_ctrl_bytes()
         self.ctrl = self._symm_zeros(nb // 4)
         self._ctrl_ptrs = self._handles[self.ctrl.data_ptr()].buffer_ptrs
