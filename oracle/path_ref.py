@@ -331,13 +331,18 @@ def zvals_no_depth(field: Field, rays_o, rays_d, n_stratified, n_importance, t_r
 
 
 def render_batch_ray(field: Field, rays_d, rays_o, gt_depth, n_stratified, n_importance, truncation,
-                     t_rand=None, t_rand_uni=None, u_pdf=None, parts: Optional[dict] = None, nodepth_field: Optional[Field] = None):
+                     t_rand=None, t_rand_uni=None, u_pdf=None, parts: Optional[dict] = None, nodepth_field: Optional[Field] = None,
+                     z_nodepth_override=None):
     """Renderer.render_batch_ray (Renderer.py:59-152) with RNG draws passed in:
     t_rand (R_valid,S): perturbation of depth-guided rays; t_rand_uni (R0,n_strat), u_pdf (R0,n_imp):
     draws of the no-depth branch, in the order the reference consumes them.
     parts (optional) receives 'pdf_inds' (R0,n_imp): the torch.searchsorted indices of sample_pdf (common.py:70).
     nodepth_field (optional): field used for the no_grad z-sampling of depth-less rays -- an fp64 gradient check passes
-    the fp32 field here so that both runs integrate along identical sample positions."""
+    the fp32 field here so that both runs integrate along identical sample positions.
+    z_nodepth_override (optional, (R0,S)): sample positions to integrate the depth-less rays along INSTEAD of the ones computed
+    here (which parts['z_nodepth_own'] then records).  A stage-wise parity check uses it: the inverse-cdf resampling amplifies
+    ulp-level SDF differences into ~1e-5 relative shifts of z, so the checked implementation's z is first held to its own
+    bar against z_nodepth_own and then fed in, and everything downstream is compared along identical positions."""
     n_rays = rays_o.shape[0]
     S = n_stratified + n_importance
     z_vals = torch.empty([n_rays, S], device=rays_o.device, dtype=torch.float32)
@@ -347,9 +352,10 @@ def render_batch_ray(field: Field, rays_d, rays_o, gt_depth, n_stratified, n_imp
     if not gt_mask.all():
         z0, inds = zvals_no_depth(nodepth_field if nodepth_field is not None else field, rays_o[~gt_mask], rays_d[~gt_mask],
                                   n_stratified, n_importance, t_rand_uni, u_pdf)
-        z_vals[~gt_mask] = z0.to(z_vals.dtype)
         if parts is not None:
             parts["pdf_inds"] = inds
+            parts["z_nodepth_own"] = z0.to(z_vals.dtype)
+        z_vals[~gt_mask] = z0.to(z_vals.dtype) if z_nodepth_override is None else z_nodepth_override.to(z_vals.dtype)
     pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
     bound = field.bound
     pts = (pts - bound[:, 0]) / (bound[:, 1] - bound[:, 0])
@@ -472,7 +478,8 @@ def tracking_loss(ret, gt_depth, gt_color, truncation, lw: LossWeights = TRACK_W
 # whole iterations (sample -> prefilter -> render -> loss), RNG passed in
 # ----------------------------------------------------------------------------------------------
 def mapping_iteration(field: Field, batches, truncation, n_stratified, n_importance, draw_rand,
-                      lw: LossWeights = MAP_WEIGHTS, parts=None, mask_mode="original", nodepth_field: Optional[Field] = None):
+                      lw: LossWeights = MAP_WEIGHTS, parts=None, mask_mode="original", nodepth_field: Optional[Field] = None,
+                      z_nodepth_override=None):
     """Mapper.optimize_mapping body, Mapper.py:379-430. batches = [(c2ws, depths, colors, rays_d_cam,
     indices), ...]: the main get_samples_all call (:379) and, when >20 keyframes, the 200 px x last-10
     frames call (:385-393), concatenated in that order. draw_rand(shape) supplies the torch.rand
@@ -488,7 +495,7 @@ def mapping_iteration(field: Field, batches, truncation, n_stratified, n_importa
     t_uni = draw_rand((n0, n_stratified)) if n0 > 0 else None
     u_pdf = draw_rand((n0, n_importance)) if n0 > 0 else None
     ret = render_batch_ray(field, rays_d, rays_o, gt_depth, n_stratified, n_importance, truncation,
-                           t_rand, t_uni, u_pdf, parts, nodepth_field)
+                           t_rand, t_uni, u_pdf, parts, nodepth_field, z_nodepth_override)
     if parts is not None:
         parts.update(inside=inside, ret=ret, gt_depth=gt_depth, gt_color=gt_color, rays_o=rays_o, rays_d=rays_d)
     return mapping_loss(ret, gt_depth, gt_color, truncation, lw, parts, mask_mode)

@@ -81,10 +81,11 @@ def cpu_draws(wl, gen):
             torch.rand((R, wl.cfg.n_importance), generator=gen))
 
 
-def oracle_mapping_iteration(wl_cpu, field, draws, joint=True, nodepth_field=None):
+def oracle_mapping_iteration(wl_cpu, field, draws, joint=True, nodepth_field=None, z_slots_override=None):
     """One reference-path mapping iteration (src/Mapper.py:366-445 up to loss.backward()) through oracle/path_ref on the
     host CPU; draws are slot-indexed and compacted here the way the reference would have drawn them.  Returns a dict
-    with the loss, the sampling / rendering intermediates and the gradients."""
+    with the loss, the sampling / rendering intermediates and the gradients.  z_slots_override (R,S): slot-indexed sample
+    positions whose depth-less rows replace the oracle's own (path_ref.render_batch_ray, z_nodepth_override)."""
     idx_main, idx_recent, t_rand, t_uni, u_pdf = draws
     cam_poses = wl_cpu.cam_poses.clone().requires_grad_(joint)
     c2ws = torch.cat([wl_cpu.c2ws[0:1], path_ref.cam_pose_to_matrix(cam_poses)], dim=0) if joint else wl_cpu.c2ws
@@ -102,7 +103,8 @@ def oracle_mapping_iteration(wl_cpu, field, draws, joint=True, nodepth_field=Non
     parts = {}
     cfg = wl_cpu.cfg
     loss = path_ref.mapping_iteration(field, batches, cfg.truncation, cfg.n_stratified, cfg.n_importance,
-                                      lambda shape: queue.pop(0), parts=parts, nodepth_field=nodepth_field)
+                                      lambda shape: queue.pop(0), parts=parts, nodepth_field=nodepth_field,
+                                      z_nodepth_override=z_slots_override[holes] if (z_slots_override is not None and holes.any()) else None)
     loss.backward()
     return dict(loss=float(loss.detach()), rays_o=ro, rays_d=rd, gt_depth=gd, inside=inside, has=has, holes=holes, parts=parts,
                 pose_grad=cam_poses.grad if joint else None, n_inside=int(inside.sum()))
@@ -130,15 +132,20 @@ def compare_mapping(step, wl, tabs, dec, beta, draws_cpu, cam_poses, device, fp6
     torch.cuda.synchronize()
     field = oracle_field(wl_cpu, tabs, dec, beta)
     field.tape = [] if fp64_tables else None
-    o = oracle_mapping_iteration(wl_cpu, field, draws_cpu)
+    # stage-wise: the depth-less rays' z is compared with the oracle's own resampling (bars below); everything downstream
+    # of it (outputs, loss, gradients) is compared along the SAME sample positions -- the inverse-cdf step amplifies ulp-level
+    # SDF differences, and an offset of 1e-5 of the range in z would otherwise be charged to the renderer as well
+    z_gpu = step.z[:R].cpu()
+    o = oracle_mapping_iteration(wl_cpu, field, draws_cpu, z_slots_override=z_gpu)
     ins, has, holes = o["inside"], o["has"], o["holes"]
     ret = o["parts"]["ret"]
     res = {"rays": R, "samples_per_ray": S, "rays_inside": o["n_inside"], "rays_without_depth": int(holes.sum())}
     res["rays_o_mismatch"] = int((step.rays_o[:R].cpu() != o["rays_o"]).sum())
     res["rays_d_mismatch"] = int((step.rays_d[:R].cpu() != o["rays_d"]).sum())
     res["valid_mismatch"] = int((step.valid[:R].cpu().bool() != ins).sum())
-    z_gpu = step.z[:R].cpu()
     z_ref = torch.zeros_like(z_gpu); z_ref[ins] = ret[5]
+    if holes.any():
+        z_ref[holes] = o["parts"]["z_nodepth_own"]
     res["z_depth_mismatch"] = int((z_gpu[has] != z_ref[has]).sum())
     res["z_hole_mismatch"] = int((z_gpu[holes] != z_ref[holes]).sum())
     res["z_hole_maxabs"] = float((z_gpu[holes] - z_ref[holes]).abs().max()) if holes.any() else 0.0
