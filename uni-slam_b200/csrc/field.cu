@@ -135,18 +135,95 @@ struct QueryArgs {
     float *out;
 };
 
-// CTA = tile of 32 (x) x 8 (z) grid points of one y row; lane = x.  The dense levels store entries x-fastest and the
-// hash's x coefficient is 1, so the 32 lanes of a gather hit neighbouring entries (a few 32-byte sectors) instead of 32
-// sectors a z-line of points would touch -- the kernel is bound by L1TEX sector requests, not by FLOPs or DRAM.  The 8
-// warps of the CTA cover 8 consecutive z, i.e. exactly one 32-byte sector of the z-fastest output per (y, x): the
-// partial stores of a CTA combine in L2.
+// CTA = tile of 32 (x) x 2 * QP_WARPS (z) grid points of one y row; lane = x, and every thread owns a PAIR of consecutive
+// z.  Lane = x because the dense levels store entries x-fastest and the hash's x coefficient is 1: the 32 lanes of a gather
+// hit neighbouring entries (a few 32-byte sectors) instead of the 32 sectors a z-line of lanes would touch.
+// The one-point-per-thread form of this kernel was issue- and latency-bound, not byte-bound (ncu: 10.3 G warp instructions
+// for 132 M points, 74 % of the issue rate, L1TEX lookups at 46 % of their ceiling), so this form spends fewer instructions
+// per point and hides its own latency:
+//   * along z the two points of a pair sit in the same or in neighbouring cells of most levels (mesh spacing <= cell), so
+//     per level the thread does the x / y cell arithmetic and the (x, y) half of the hash once and gathers z-PLANES (4
+//     corners, collapsed bilinearly in x then y) instead of cells: 2 planes when the pair shares a cell, 3 when the second
+//     point is in the next cell, 4 otherwise -- against 4 planes' worth for independent points; each point finishes with one
+//     lerp along z; interpolation in packed pairs (feature 0 | feature 1: FFMA2 / FADD2);
+//   * software pipeline over the levels: the gathers of level l + 1 are issued before the 64 first-layer FMAs of level l;
+//   * the first-layer weights of a level are read once for both points.
+// The lerp order (x, y, z), the cell indices and the FMA order of the first layer are those of decode_point: the values are
+// bit-identical to the one-point-per-thread form.  Measured on the 132 M-point Replica volume: 12.3 ms one point per thread,
+// 11.4 with 4 levels of gathers in flight, 10.6 / 9.9 ms for runs of 4 / 2 z without the pipeline (164 / 122 registers),
+// 9.4 ms for this kernel at 125 registers / 4 CTAs per SM; 10.3 ms at 3 or at 5 CTAs per SM (137 registers / 96 with spills),
+// 13.0 at 6.
 #define QT_X 32
-#define QT_Z 8
-__global__ void __launch_bounds__(256) sdf_query_grid_kernel(const __grid_constant__ QueryArgs A) {
+
+// z-planes of one level for one thread.  Keys and offsets are BYTE offsets into the level (entry index << 3), so that one
+// LOP3 (hashed) or one add + conditional subtract (dense) yields the load offset.
+template <bool HASHED>
+struct PlaneKey {
+    uint32_t k[4];        // hashed: ((gx + dx) ^ ((gy + dy) * PRIME_Y)) << 3; dense: (gx + dx + (gy + dy) * res) << 3
+    uint32_t zstep;       // hashed: PRIME_Z << 3; dense: (res * res) << 3
+    uint32_t lim;         // hashed: (size - 1) << 3 (mask); dense: size << 3
+    __device__ __forceinline__ PlaneKey(const usl_level_t &lv, uint32_t gx, uint32_t gy) {
+        if (HASHED) {
+            const uint32_t hy0 = gy * USL_PRIME_Y, hy1 = hy0 + USL_PRIME_Y;
+            k[0] = (gx ^ hy0) << 3; k[1] = ((gx + 1u) ^ hy0) << 3; k[2] = (gx ^ hy1) << 3; k[3] = ((gx + 1u) ^ hy1) << 3;
+            zstep = USL_PRIME_Z << 3; lim = (lv.size - 1u) << 3;
+        } else {
+            const uint32_t b = gx + gy * lv.res;
+            k[0] = b << 3; k[1] = (b + 1u) << 3; k[2] = (b + lv.res) << 3; k[3] = (b + lv.res + 1u) << 3;
+            zstep = (lv.res * lv.res) << 3; lim = lv.size << 3;
+        }
+    }
+    // the four corners of plane gz (zoff = gz * zstep), as packed (feature 0, feature 1) pairs
+    __device__ __forceinline__ void gather(const char *__restrict__ tab, uint32_t zoff, f32x2_t v[4]) const {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t o;
+            if (HASHED) o = (k[q] ^ zoff) & lim;                       // shifting commutes with xor / and: same entry as grid_index
+            else { o = k[q] + zoff; if (o >= lim) o -= lim; }          // clamped coordinates: one conditional subtract is the exact modulo
+            v[q] = ldg_f32x2(tab + o);
+        }
+    }
+};
+
+__device__ __forceinline__ f32x2_t plane_collapse(const f32x2_t v[4], f32x2_t wx, f32x2_t wy) {   // lerp x, then y (level_interp's order)
+    return lerp2(wy, lerp2(wx, v[0], v[1]), lerp2(wx, v[2], v[3]));
+}
+
+// Plane slots of a level: A = plane(gz0), B = plane(gz0 + 1) always; C = plane(gz1 + 1) unless both points share a cell;
+// D = plane(gz1) only when the second point is more than one cell away.
+#ifndef QP_WARPS
+#define QP_WARPS 4
+#endif
+#ifndef QP_MINB
+#define QP_MINB 4
+#endif
+struct PairLevel {               // what the consuming half of an iteration needs about the level whose values are in flight
+    f32x2_t wx2, wy2, wz0, wz1;
+    bool same, adj;
+};
+
+template <bool HASHED>
+__device__ __forceinline__ void pair_issue(const usl_level_t &lv, const char *__restrict__ tab, uint32_t gx, uint32_t gy, uint32_t gz0,
+                                           uint32_t gz1, bool same, bool adj, f32x2_t (*v)[4]) {
+    const PlaneKey<HASHED> K(lv, gx, gy);
+    const uint32_t z0 = gz0 * K.zstep;
+    K.gather(tab, z0, v[0]);
+    K.gather(tab, z0 + K.zstep, v[1]);
+    if (!same) {
+        const uint32_t z1 = gz1 * K.zstep;
+        K.gather(tab, z1 + K.zstep, v[2]);
+        if (!adj) K.gather(tab, z1, v[3]);
+    }
+}
+
+__global__ void __launch_bounds__(QT_X * QP_WARPS, QP_MINB) sdf_query_grid_kernel(const __grid_constant__ QueryArgs A) {
     __shared__ MlpSmem sm;
     stage_mlp(A.f.mlp[0], sm);
     __syncthreads();
-    const int tx = (A.nx + QT_X - 1) / QT_X, tz = (A.nz + QT_Z - 1) / QT_Z;
+    const usl_grid_t &g = A.f.grid[0];
+    const float2 *table = reinterpret_cast<const float2 *>(A.f.table[0]);
+    constexpr int TZ = 2 * QP_WARPS;
+    const int tx = (A.nx + QT_X - 1) / QT_X, tz = (A.nz + TZ - 1) / TZ;
     const int64_t tiles = (int64_t)(A.y_end - A.y_begin) * tx * tz;
     const int lx = threadIdx.x & (QT_X - 1), lz = threadIdx.x / QT_X;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -154,30 +231,72 @@ __global__ void __launch_bounds__(256) sdf_query_grid_kernel(const __grid_consta
         const int64_t r = t / tz;
         const int bx = (int)(r % tx);
         const int iy = (int)(r / tx) + A.y_begin;
-        const int ix = bx * QT_X + lx, iz = bz * QT_Z + lz;
-        if (ix >= A.nx || iz >= A.nz) continue;
-        const float p[3] = {A.ax[ix], A.ay[iy], A.az[iz]};
-        bool inside = true;
-        float xc[3];
+        const int ix = bx * QT_X + lx, iz0 = bz * TZ + lz * 2;
+        if (ix >= A.nx || iz0 >= A.nz) continue;
+        auto norm = [&](float p, int d, bool &in) {                 // Mesher.py:147-156
+            in = (p < A.f.bound_hi[d]) && (p > A.f.bound_lo[d]);
+            const float x = __fdiv_rn(__fsub_rn(p, A.f.bound_lo[d]), __fsub_rn(A.f.bound_hi[d], A.f.bound_lo[d]));
+            return fminf(fmaxf(x, 0.f), 1.f);
+        };
+        bool in_x, in_y, in_z0, in_z1;
+        const float xn = norm(A.ax[ix], 0, in_x), yn = norm(A.ay[iy], 1, in_y);
+        const float zn0 = norm(A.az[iz0], 2, in_z0), zn1 = norm(A.az[min(iz0 + 1, A.nz - 1)], 2, in_z1);
+
+        f32x2_t hp0[USL_HID / 2], hp1[USL_HID / 2];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            inside = inside && (p[d] < A.f.bound_hi[d]) && (p[d] > A.f.bound_lo[d]);   // strict, Mesher.py:151-154
-            const float x = __fdiv_rn(__fsub_rn(p[d], A.f.bound_lo[d]), __fsub_rn(A.f.bound_hi[d], A.f.bound_lo[d]));
-            xc[d] = fminf(fmaxf(x, 0.f), 1.f);
+        for (int q = 0; q < USL_HID / 2; ++q) hp0[q] = hp1[q] = pack2(sm.b1[2 * q], sm.b1[2 * q + 1]);
+
+        f32x2_t v[4][4];
+        PairLevel nx_;
+        auto issue = [&](int l) {
+            const usl_level_t &lv = g.levels[l];
+            const char *tab = reinterpret_cast<const char *>(table + lv.offset);
+            uint32_t gx, gy, gz0, gz1;
+            float wx, wy, wz0, wz1;
+            pos_fract(lv.scale, xn, gx, wx); pos_fract(lv.scale, yn, gy, wy);
+            pos_fract(lv.scale, zn0, gz0, wz0); pos_fract(lv.scale, zn1, gz1, wz1);
+            nx_.same = gz1 == gz0; nx_.adj = gz1 == gz0 + 1u;
+            nx_.wx2 = pack2(wx, wx); nx_.wy2 = pack2(wy, wy); nx_.wz0 = pack2(wz0, wz0); nx_.wz1 = pack2(wz1, wz1);
+            if (lv.hashed) pair_issue<true>(lv, tab, gx, gy, gz0, gz1, nx_.same, nx_.adj, v);
+            else pair_issue<false>(lv, tab, gx, gy, gz0, gz1, nx_.same, nx_.adj, v);
+        };
+        issue(0);
+#pragma unroll 1
+        for (int l = 0; l < g.n_levels; ++l) {
+            // consume level l: collapse the planes in flight, pick each point's pair, lerp along z
+            const PairLevel cur = nx_;
+            const f32x2_t pa = plane_collapse(v[0], cur.wx2, cur.wy2), pb = plane_collapse(v[1], cur.wx2, cur.wy2);
+            f32x2_t lo1 = pa, hi1 = pb;
+            if (!cur.same) {
+                hi1 = plane_collapse(v[2], cur.wx2, cur.wy2);
+                lo1 = pb;
+                if (!cur.adj) lo1 = plane_collapse(v[3], cur.wx2, cur.wy2);
+            }
+            const float2 f0 = unpack2(lerp2(cur.wz0, pa, pb)), f1 = unpack2(lerp2(cur.wz1, lo1, hi1));
+            // level l + 1's gathers go out now and land while the 64 FMAs below issue
+            if (l + 1 < g.n_levels) issue(l + 1);
+            const f32x2_t fx0 = pack2(f0.x, f0.x), fy0 = pack2(f0.y, f0.y), fx1 = pack2(f1.x, f1.x), fy1 = pack2(f1.y, f1.y);
+            const ulonglong2 *wa = reinterpret_cast<const ulonglong2 *>(sm.w1t[2 * l]);
+            const ulonglong2 *wb = reinterpret_cast<const ulonglong2 *>(sm.w1t[2 * l + 1]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const ulonglong2 a = wa[q], b = wb[q];
+                ffma2(hp0[2 * q], a.x, fx0); ffma2(hp0[2 * q], b.x, fy0); ffma2(hp0[2 * q + 1], a.y, fx0); ffma2(hp0[2 * q + 1], b.y, fy0);
+                ffma2(hp1[2 * q], a.x, fx1); ffma2(hp1[2 * q], b.x, fy1); ffma2(hp1[2 * q + 1], a.y, fx1); ffma2(hp1[2 * q + 1], b.y, fy1);
+            }
         }
-        float v = -1.0f;                                                                // Mesher.py:162
-        if (inside) {
-            float out[4], tout[4][3];
-            // 4 levels unrolled together: 12.25 / 12.12 / 11.40 / 12.87 ms for 1 / 2 / 4 / 16.  (Tried and measured slower, 15.0-15.9 ms:
-            // an "x-line" decode in which every lane collapses its own x column over the warp-uniform (y, z) -- 4 gathers -- and
-            // fetches the neighbouring column from the lane that holds it by shuffle; the kernel is issue-bound -- ncu: 10.3 G warp
-            // instructions, 74 % of the issue rate, L1TEX lookups at 46 % of their ceiling -- and the ballots, dynamic-lane
-            // shuffles and the divergent extra gathers of a warp's last run cost more issue slots than the 4 gathers save.)
-            decode_point<false, false, 4>(A.f.grid[0], reinterpret_cast<const float2 *>(A.f.table[0]), A.f.mlp[0], sm, xc, nullptr, 0, out, tout);
-            v = out[0];
+        float res[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            float h[USL_HID], th[1][USL_HID], out[4], tout[4][3];
+#pragma unroll
+            for (int q = 0; q < USL_HID / 2; ++q) { const float2 u = unpack2(p ? hp1[q] : hp0[q]); h[2 * q] = u.x; h[2 * q + 1] = u.y; }
+            mlp_tail<false>(A.f.mlp[0], sm, h, th, out, tout);
+            res[p] = (in_x && in_y && (p ? in_z1 : in_z0)) ? out[0] : -1.0f;     // Mesher.py:162
         }
-        // idx = (iy*nx + ix)*nz + iz within the slab (torch.meshgrid(indexing='xy') flattened, Mesher.py:192-193)
-        __stcs(A.out + ((int64_t)(iy - A.y_begin) * A.nx + ix) * A.nz + iz, v);
+        float *o = A.out + ((int64_t)(iy - A.y_begin) * A.nx + ix) * A.nz + iz0;   // (iy*nx + ix)*nz + iz, Mesher.py:192-193
+        if ((A.nz & 1) == 0 && (reinterpret_cast<uintptr_t>(A.out) & 7) == 0) __stcs(reinterpret_cast<float2 *>(o), make_float2(res[0], res[1]));
+        else { __stcs(o, res[0]); if (iz0 + 1 < A.nz) __stcs(o + 1, res[1]); }
     }
 }
 
@@ -508,13 +627,13 @@ int usl_sdf_query_grid(const usl_field_t *f, const float *ax, const float *ay, c
     if (total <= 0) return 0;
     QueryArgs A;
     A.f = *f; A.ax = ax; A.ay = ay; A.az = az; A.nx = nx; A.ny = ny; A.nz = nz; A.y_begin = y_begin; A.y_end = y_end; A.out = out;
-    int64_t blocks = (int64_t)(y_end - y_begin) * ((nx + QT_X - 1) / QT_X) * ((nz + QT_Z - 1) / QT_Z);   // one tile per CTA and pass
+    int64_t blocks = (int64_t)(y_end - y_begin) * ((nx + QT_X - 1) / QT_X) * ((nz + 2 * QP_WARPS - 1) / (2 * QP_WARPS));   // one tile per CTA and pass
     int dev = 0, n_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int64_t cap = (int64_t)(n_sm > 0 ? n_sm : 1) * 64;     // persistent tile loop: a few waves of resident CTAs per SM
     if (blocks > cap) blocks = cap;
-    sdf_query_grid_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A);
+    sdf_query_grid_kernel<<<(unsigned)blocks, QT_X * QP_WARPS, 0, (cudaStream_t)stream>>>(A);
     return check_launch("usl_sdf_query_grid");
 }
 

@@ -301,6 +301,20 @@ __device__ __forceinline__ void ffma2(f32x2_t &acc, f32x2_t a, f32x2_t b) {     
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
 
+__device__ __forceinline__ f32x2_t fsub2(f32x2_t a, f32x2_t b) {                    // a - b (element-wise, round to nearest)
+    f32x2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t lerp2(f32x2_t w, f32x2_t a, f32x2_t b) {          // fmaf(w, b - a, a) on both halves
+    f32x2_t r = a;
+    ffma2(r, w, fsub2(b, a));
+    return r;
+}
+__device__ __forceinline__ f32x2_t ldg_f32x2(const void *p) {                        // 8-byte read-only load straight into a packed pair
+    return __ldg(reinterpret_cast<const unsigned long long *>(p));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
