@@ -306,6 +306,11 @@ __device__ __forceinline__ f32x2_t fsub2(f32x2_t a, f32x2_t b) {                
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ f32x2_t fmul2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ f32x2_t lerp2(f32x2_t w, f32x2_t a, f32x2_t b) {          // fmaf(w, b - a, a) on both halves
     f32x2_t r = a;
     ffma2(r, w, fsub2(b, a));

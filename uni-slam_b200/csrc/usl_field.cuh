@@ -85,7 +85,7 @@ __device__ __forceinline__ void mlp_tail(const usl_mlp_t &m, const MlpSmem &sm, 
 // part 1: cell arithmetic + the 8 gathers (4 corners of this lane's x side for A and for B); nothing waits on the loads here,
 // so a caller can issue the gathers of several levels back to back before touching any value.
 __device__ __forceinline__ void pair_gather(const usl_level_t &lv, const float2 *__restrict__ table, const float xA[3],
-                                            const float xB[3], uint32_t side, float2 v[2][4], float w[2][3]) {
+                                            const float xB[3], uint32_t side, f32x2_t v[2][4], float w[2][3]) {
     const float2 *tab = table + lv.offset;
 #pragma unroll
     for (int pnt = 0; pnt < 2; ++pnt) {
@@ -111,45 +111,48 @@ __device__ __forceinline__ void pair_gather(const usl_level_t &lv, const float2 
             }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[pnt][q] = ldg2(tab + idx[q]);
+        for (int q = 0; q < 4; ++q) v[pnt][q] = ldg_f32x2(tab + idx[q]);      // (feature 0 | feature 1) stays a packed pair
     }
 }
 
 // part 2: bilinear in (y, z) on this lane's x side for both points, exchange of the side values inside the lane pair,
 // lerp along x for the lane's own point (A on the even lane, B on the odd lane).
 template <bool WITH_JAC>
-__device__ __forceinline__ void pair_finish(float scale, const float2 v[2][4], const float w[2][3], uint32_t side, float2 &f,
+__device__ __forceinline__ void pair_finish(float scale, const f32x2_t v[2][4], const float w[2][3], uint32_t side, float2 &f,
                                             float2 df[3]) {
-    float2 b[2], by[2], bz[2];
+    // every lerp acts on both features at once (FFMA2 / FADD2; each half rounds like the scalar op)
+    f32x2_t b[2], by[2], bz[2];
 #pragma unroll
     for (int pnt = 0; pnt < 2; ++pnt) {
-        const float w1 = w[pnt][1], w2 = w[pnt][2];
-        const float2 dy0 = make_float2(v[pnt][1].x - v[pnt][0].x, v[pnt][1].y - v[pnt][0].y);
-        const float2 dy1 = make_float2(v[pnt][3].x - v[pnt][2].x, v[pnt][3].y - v[pnt][2].y);
-        const float2 a0 = make_float2(fmaf(w1, dy0.x, v[pnt][0].x), fmaf(w1, dy0.y, v[pnt][0].y));
-        const float2 a1 = make_float2(fmaf(w1, dy1.x, v[pnt][2].x), fmaf(w1, dy1.y, v[pnt][2].y));
-        bz[pnt] = make_float2(a1.x - a0.x, a1.y - a0.y);
-        b[pnt] = make_float2(fmaf(w2, bz[pnt].x, a0.x), fmaf(w2, bz[pnt].y, a0.y));
-        if (WITH_JAC) by[pnt] = make_float2(fmaf(w2, dy1.x - dy0.x, dy0.x), fmaf(w2, dy1.y - dy0.y, dy0.y));
+        const f32x2_t w1 = pack2(w[pnt][1], w[pnt][1]), w2 = pack2(w[pnt][2], w[pnt][2]);
+        const f32x2_t dy0 = fsub2(v[pnt][1], v[pnt][0]), dy1 = fsub2(v[pnt][3], v[pnt][2]);
+        f32x2_t a0 = v[pnt][0], a1 = v[pnt][2];
+        ffma2(a0, w1, dy0); ffma2(a1, w1, dy1);
+        bz[pnt] = fsub2(a1, a0);
+        b[pnt] = a0; ffma2(b[pnt], w2, bz[pnt]);
+        if (WITH_JAC) { by[pnt] = dy0; ffma2(by[pnt], w2, fsub2(dy1, dy0)); }
     }
-    auto xchg = [&](const float2 (&t)[2], float2 &s0, float2 &s1) {
-        const float2 send = side ? t[0] : t[1];            // partner's point, my side
-        const float2 mine = side ? t[1] : t[0];            // my point, my side
-        const float2 recv = make_float2(__shfl_xor_sync(0xffffffffu, send.x, 1), __shfl_xor_sync(0xffffffffu, send.y, 1));
+    auto xchg = [&](const f32x2_t (&t)[2], f32x2_t &s0, f32x2_t &s1) {
+        const f32x2_t send = side ? t[0] : t[1];           // partner's point, my side
+        const f32x2_t mine = side ? t[1] : t[0];           // my point, my side
+        const f32x2_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
         s0 = side ? recv : mine; s1 = side ? mine : recv;  // side-0 / side-1 value of my point
     };
-    const float w0 = side ? w[1][0] : w[0][0];
-    float2 s0, s1;
+    const float w0s = side ? w[1][0] : w[0][0];
+    const f32x2_t w0 = pack2(w0s, w0s);
+    f32x2_t s0, s1;
     xchg(b, s0, s1);
-    const float2 dx = make_float2(s1.x - s0.x, s1.y - s0.y);
-    f = make_float2(fmaf(w0, dx.x, s0.x), fmaf(w0, dx.y, s0.y));
+    const f32x2_t dx = fsub2(s1, s0);
+    f32x2_t fp = s0; ffma2(fp, w0, dx);
+    f = unpack2(fp);
     if (WITH_JAC) {
-        float2 y0, y1, z0, z1;
+        const f32x2_t sc = pack2(scale, scale);
+        f32x2_t y0, y1, z0, z1;
         xchg(by, y0, y1);
         xchg(bz, z0, z1);
-        df[0] = make_float2(scale * dx.x, scale * dx.y);
-        df[1] = make_float2(scale * fmaf(w0, y1.x - y0.x, y0.x), scale * fmaf(w0, y1.y - y0.y, y0.y));
-        df[2] = make_float2(scale * fmaf(w0, z1.x - z0.x, z0.x), scale * fmaf(w0, z1.y - z0.y, z0.y));
+        f32x2_t ty = y0, tz = z0;
+        ffma2(ty, w0, fsub2(y1, y0)); ffma2(tz, w0, fsub2(z1, z0));
+        df[0] = unpack2(fmul2(sc, dx)); df[1] = unpack2(fmul2(sc, ty)); df[2] = unpack2(fmul2(sc, tz));
     }
 }
 
@@ -203,10 +206,28 @@ __device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *
             }
         }
     };
-    if (LANEPAIR && UNR == 1) {
+#ifndef USL_FWD_PIPE
+#define USL_FWD_PIPE 1
+#endif
+    if (LANEPAIR && UNR == 1 && USL_FWD_PIPE) {
+        // software pipeline over the levels: level l's corner values are reduced to its feature (+ tangents), then the
+        // gathers of level l + 1 go out, and only then the first-layer FMAs of level l issue -- a warp covers its own L2
+        // latency with its own arithmetic instead of relying on the other (register-limited, 16 per SM) warps
+        f32x2_t v[2][4];
+        float w[2][3];
+        pair_gather(g.levels[0], table, xA, xB, side, v, w);
 #pragma unroll 1
         for (int l = 0; l < g.n_levels; ++l) {
-            float2 v[2][4], f, df[3];
+            float2 f, df[3];
+            pair_finish<WITH_JAC>(g.levels[l].scale, v, w, side, f, df);
+            if (l + 1 < g.n_levels) pair_gather(g.levels[l + 1], table, xA, xB, side, v, w);
+            accumulate(l, f, df);
+        }
+    } else if (LANEPAIR && UNR == 1) {
+#pragma unroll 1
+        for (int l = 0; l < g.n_levels; ++l) {
+            f32x2_t v[2][4];
+            float2 f, df[3];
             float w[2][3];
             pair_gather(g.levels[l], table, xA, xB, side, v, w);
             pair_finish<WITH_JAC>(g.levels[l].scale, v, w, side, f, df);
@@ -219,7 +240,7 @@ __device__ __forceinline__ void decode_point(const usl_grid_t &g, const float2 *
         // 122 registers / 16 warps -- resident warps hide more latency than deeper per-thread batches.)
 #pragma unroll 1
         for (int l0 = 0; l0 < g.n_levels; l0 += UNR) {
-            float2 v[UNR][2][4];
+            f32x2_t v[UNR][2][4];
             float w[UNR][2][3];
 #pragma unroll
             for (int u = 0; u < UNR; ++u)
