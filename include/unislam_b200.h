@@ -300,6 +300,13 @@ USL_API int usl_loss_bwd(const usl_loss_args_t *a, const float *raw, const float
                  const float *gt_color, const uint8_t *valid, const uint8_t *mask, const float *depth,
                  const float *rgb, const float *acc, const float *g_loss, int64_t R, int S,
                  float *g_depth, float *g_rgb, float *g_sdf, usl_stream_t stream);
+/* usl_composite_fwd + usl_loss_fwd in one launch for the modes whose ray mask needs no global quantity (0 and 2; mode 1 is
+ * refused: the tracker's mask needs the median over all rays first).  Same outputs as the two calls (Renderer.py:140-158 +
+ * Mapper.py:141-175,412-430); acc is ADDED to. */
+USL_API int usl_composite_loss_fwd(const usl_loss_args_t *a, const float *raw, const float *z, const float *beta,
+                                   const uint8_t *valid, int64_t R, int S, const float *gt_depth, const float *gt_color,
+                                   float *term, float *pixel_unc, float *depth, float *rgb, float *depth_unc, float *acc,
+                                   uint8_t *mask_out, usl_stream_t stream);
 USL_API int usl_composite_loss_bwd(const usl_loss_args_t *a, const float *raw, const float *z, const float *beta,
                                    const uint8_t *valid, const uint8_t *mask, int64_t R, int S, const float *gt_depth,
                                    const float *gt_color, const float *depth, const float *rgb, const float *acc,

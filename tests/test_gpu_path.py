@@ -480,6 +480,43 @@ def test_tcgen05_forward_matches_cuda_core_forward(monkeypatch):
     assert (outs[1][1] - outs[0][1]).abs().max() < 2e-3 * outs[0][1].abs().max()
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+def test_fused_composite_loss_forward_equals_the_two_calls(mode):
+    """usl_composite_loss_fwd (one launch) vs usl_composite_fwd + usl_loss_fwd: identical per-ray outputs and masks, the
+    same loss sums / counts; the tracker's mode (median mask) is refused."""
+    from ctypes import byref
+    P = pkg(); L = P._lib
+    gen = torch.Generator(device=DEV).manual_seed(11 + mode)
+    R, S = 1003, 40                                              # ragged last CTA
+    raw = torch.rand(R, S, 4, device=DEV, generator=gen); raw[..., 3] = raw[..., 3] * 2 - 1
+    z = (torch.rand(R, S, device=DEV, generator=gen) * 3).sort(dim=1).values.contiguous()
+    beta = torch.tensor([8.0], device=DEV)
+    valid = (torch.rand(R, device=DEV, generator=gen) > 0.1).to(torch.uint8)
+    gt_d = torch.rand(R, device=DEV, generator=gen) * 3; gt_d[::17] = 0.0
+    gt_c = torch.rand(R, 3, device=DEV, generator=gen)
+    la = P.ops.make_loss_args(0.06, 5.0, 200.0, 10.0, 0.1, 5.0, mode)
+
+    def outs():
+        return [torch.full((R,), 7.0, device=DEV) for _ in range(3)] + [torch.full((R, 3), 7.0, device=DEV), torch.full((R,), 7.0, device=DEV),
+                torch.zeros(16, device=DEV), torch.full((R,), 9, device=DEV, dtype=torch.uint8)]
+    a = outs(); b = outs()
+    st = L.stream()
+    L.call("usl_composite_fwd", L.ptr(raw), L.ptr(z), L.ptr(beta), L.ptr(valid), R, S, L.ptr(a[0]), L.ptr(a[1]), L.ptr(a[2]), L.ptr(a[3]), L.ptr(a[4]), None, st)
+    L.call("usl_loss_fwd", byref(la), L.ptr(raw), L.ptr(z), L.ptr(gt_d), L.ptr(gt_c), L.ptr(valid), L.ptr(a[1]), L.ptr(a[2]), L.ptr(a[3]), None, R, S,
+           L.ptr(a[5]), L.ptr(a[6]), st)
+    L.call("usl_composite_loss_fwd", byref(la), L.ptr(raw), L.ptr(z), L.ptr(beta), L.ptr(valid), R, S, L.ptr(gt_d), L.ptr(gt_c), L.ptr(b[0]), L.ptr(b[1]),
+           L.ptr(b[2]), L.ptr(b[3]), L.ptr(b[4]), L.ptr(b[5]), L.ptr(b[6]), st)
+    torch.cuda.synchronize()
+    for i in (0, 1, 2, 3, 4, 6):
+        assert torch.equal(a[i], b[i]), i
+    assert float(a[5][5:11].sub(b[5][5:11]).abs().max()) == 0.0             # counts are exact
+    assert rel_err(b[5], a[5]) < 1e-6                                         # sums: atomics reorder the additions
+    la1 = P.ops.make_loss_args(0.06, 5.0, 200.0, 10.0, 0.1, 5.0, 1)
+    with pytest.raises(RuntimeError, match="median"):
+        L.call("usl_composite_loss_fwd", byref(la1), L.ptr(raw), L.ptr(z), L.ptr(beta), L.ptr(valid), R, S, L.ptr(gt_d), L.ptr(gt_c), L.ptr(b[0]),
+               L.ptr(b[1]), L.ptr(b[2]), L.ptr(b[3]), L.ptr(b[4]), L.ptr(b[5]), L.ptr(b[6]), st)
+
+
 def test_tracking_converges_on_held_out_frame():
     """End to end: fit the field on a keyframe window with MappingStep + FusedAdam, then TrackingStep + FusedAdam must pull a
     held-out frame's pose (perturbed by 2.7 cm / 1 deg) back to the analytic ground truth."""
@@ -502,6 +539,12 @@ def test_slam_loop_runs_and_stays_on_track():
     r = slam.run_slam(pkg().synthetic.REPLICA_ROOM0, n_frames=24, scale_hw=0.25)
     assert r.loss_last_map < 0.05 * r.loss_first_map
     assert r.ate_rmse < 0.03 and r.tracking_iters == 23 * 8 and r.mapping_iters == 10 + 5 * 15
+    # the same loop with every iteration after the first of its shape replayed from a CUDA graph: same iteration counts,
+    # same behaviour (RNG streams differ between captured and eager draws, so the trajectories are not bit-identical)
+    g = slam.run_slam(pkg().synthetic.REPLICA_ROOM0, n_frames=24, scale_hw=0.25, graphs=True)
+    assert g.loss_last_map < 0.05 * g.loss_first_map
+    assert g.ate_rmse < 0.03 and g.tracking_iters == 23 * 8 and g.mapping_iters == 10 + 5 * 15
+    assert abs(g.ate_rmse - r.ate_rmse) < 0.01
 
 
 def test_empty_and_degenerate_inputs():

@@ -118,6 +118,7 @@ _SIGS = {
     "usl_field_sdf": [POINTER(Field), POINTER(Points), _P, _P],
     "usl_composite_fwd": [_P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P],
     "usl_composite_bwd": [_P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, POINTER(Bound), _P, _P, _P, _P, _P],
+    "usl_composite_loss_fwd": [POINTER(LossArgs), _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "usl_loss_fwd": [POINTER(LossArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P],
     "usl_loss_finalize": [POINTER(LossArgs), _P, _P, _P],
     "usl_loss_bwd": [POINTER(LossArgs), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P],

@@ -104,6 +104,90 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_fwd_kernel(
     }
 }
 
+// composite_fwd + loss_fwd for the modes whose ray mask needs no global quantity (mapping 'original', 'no_mask'): the warp that
+// composited a ray still holds its samples, so the loss sums cost no second pass over raw / z and no second launch.
+struct CompLossFwdArgs {
+    const float *raw, *z, *beta, *gt_depth, *gt_color;
+    const uint8_t *valid;
+    int64_t R;
+    int S;
+    float *term, *punc, *depth, *rgb, *dunc, *acc;
+    uint8_t *mask_out;
+    usl_loss_args_t la;
+};
+
+__global__ void __launch_bounds__(CMP_WARPS * 32) composite_loss_fwd_kernel(const __grid_constant__ CompLossFwdArgs A) {
+    __shared__ float s_acc[CMP_WARPS][12];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ray = (int64_t)blockIdx.x * CMP_WARPS + warp;
+    const int S = A.S;
+    float v[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) v[q] = 0.f;
+    if (ray < A.R && A.valid && !A.valid[ray]) {
+        if (lane == 0) {
+            A.term[ray] = 0.f; A.punc[ray] = 0.f; A.depth[ray] = 0.f; A.dunc[ray] = 0.f;
+            A.rgb[ray * 3] = 0.f; A.rgb[ray * 3 + 1] = 0.f; A.rgb[ray * 3 + 2] = 0.f;
+            if (A.mask_out) A.mask_out[ray] = 0;
+        }
+    } else if (ray < A.R) {
+        const float beta = A.beta[0];
+        Sample smp[CMP_MAX_CHUNKS];
+        float term, depth, rgb[3];
+        ray_forward(A.raw, A.z, beta, ray, S, lane, smp, term, depth, rgb);
+        float dv = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < CMP_MAX_CHUNKS; ++ch) { const float dz = depth - smp[ch].z; dv += smp[ch].w * dz * dz; }
+        dv = warp_sum(dv);
+        const float om = 1.0f - term, pu = om * om;                // Renderer.py:148
+        const float gt = A.gt_depth[ray];
+        const bool m = ray_mask(A.la, gt, pu, depth, nullptr);
+        if (m) {                                                   // same per-lane accumulation order as loss_fwd_kernel
+            const float tr = A.la.truncation, tr04 = A.la.truncation_center;
+#pragma unroll
+            for (int ch = 0; ch < CMP_MAX_CHUNKS; ++ch) {
+                if (ch * 32 + lane >= S) continue;
+                const float zz = smp[ch].z, sd = smp[ch].sdf;
+                const int c = sample_class(zz, gt, tr, tr04);
+                if (c == 0) { const float e = sd - 1.0f; v[A_FS] += e * e; v[N_FRONT] += 1.f; }
+                else if (c < 3) {
+                    const float e = (zz + sd * tr) - gt;
+                    if (c == 1) { v[A_CENTER] += e * e; v[N_CENTER] += 1.f; }
+                    else { v[A_TAIL] += e * e; v[N_TAIL] += 1.f; }
+                }
+            }
+        }
+        if (lane == 0) {
+            A.term[ray] = term; A.punc[ray] = pu; A.depth[ray] = depth;
+            A.dunc[ray] = sqrtf(dv);                               // Renderer.py:150
+            A.rgb[ray * 3] = rgb[0]; A.rgb[ray * 3 + 1] = rgb[1]; A.rgb[ray * 3 + 2] = rgb[2];
+            if (A.mask_out) A.mask_out[ray] = m ? 1 : 0;
+            v[N_RAYS] = 1.f;
+            v[A_PUNC] = pu;
+            if (m) { const float e = gt - depth; v[A_DEPTH] = e * e; v[N_MASK] = 1.f; }
+            if (A.la.mode == 0 || m) {                             // Mapper.py:427 (all rays) / no_mask
+                float cs = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { const float e = A.gt_color[ray * 3 + k] - rgb[k]; cs += e * e; }
+                v[A_COLOR] = cs; v[N_COLOR] = 3.f;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 12; ++q) v[q] = warp_sum(v[q]);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q) s_acc[warp][q] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < CMP_WARPS; ++w) t += s_acc[w][threadIdx.x];
+        if (t != 0.f) atomicAdd(A.acc + threadIdx.x, t);
+    }
+}
+
 struct CompBwdArgs {
     const float *raw, *z, *beta;
     const uint8_t *valid;
@@ -131,6 +215,16 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) composite_bwd_kernel(const __g
         for (int s = lane; s < S; s += 32) reinterpret_cast<float4 *>(A.d_raw)[ray * S + s] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (A.jac && lane < 3) { A.d_rays_o[ray * 3 + lane] = 0.f; A.d_rays_d[ray * 3 + lane] = 0.f; }
     } else if (live) {
+        if (A.jac) {
+            // the Jacobian rows are only needed after two dependent scans: start them towards L1 now, so the kernel pays one
+            // memory round trip (raw / z, below) instead of two in sequence
+            const int64_t npts = A.R * (int64_t)S;
+            for (int s = lane; s < S; s += 32) {
+                const float *jp = A.jac + ray * S + s;
+#pragma unroll
+                for (int c = 0; c < 12; ++c) asm volatile("prefetch.global.L1 [%0];" ::"l"(jp + (int64_t)c * npts));
+            }
+        }
         const float beta = A.beta[0];
         Sample smp[CMP_MAX_CHUNKS];
         float term, depth, rgb[3];
@@ -261,6 +355,22 @@ int usl_composite_fwd(const float *raw, const float *z, const float *beta, const
     composite_fwd_kernel<<<(unsigned)((R + CMP_WARPS - 1) / CMP_WARPS), CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         raw, z, beta, valid, R, S, term, pixel_unc, depth, rgb, depth_unc, weights);
     return check_launch("usl_composite_fwd");
+}
+
+int usl_composite_loss_fwd(const usl_loss_args_t *a, const float *raw, const float *z, const float *beta, const uint8_t *valid,
+                           int64_t R, int S, const float *gt_depth, const float *gt_color, float *term, float *pixel_unc,
+                           float *depth, float *rgb, float *depth_unc, float *acc, uint8_t *mask_out, usl_stream_t stream) {
+    if (R <= 0) return 0;
+    if (S < 1 || S > CMP_MAX_CHUNKS * 32) { set_error("usl_composite_loss_fwd: S must be in 1..128"); return 1; }
+    if (!a || !raw || !z || !beta || !gt_depth || !gt_color || !term || !pixel_unc || !depth || !rgb || !depth_unc || !acc) {
+        set_error("usl_composite_loss_fwd: null argument"); return 1;
+    }
+    if (a->mode == 1) { set_error("usl_composite_loss_fwd: the tracking mask needs the median of all rays: use usl_composite_fwd + usl_depth_error_median + usl_loss_fwd"); return 1; }
+    CompLossFwdArgs A;
+    A.raw = raw; A.z = z; A.beta = beta; A.gt_depth = gt_depth; A.gt_color = gt_color; A.valid = valid; A.R = R; A.S = S;
+    A.term = term; A.punc = pixel_unc; A.depth = depth; A.rgb = rgb; A.dunc = depth_unc; A.acc = acc; A.mask_out = mask_out; A.la = *a;
+    composite_loss_fwd_kernel<<<(unsigned)((R + CMP_WARPS - 1) / CMP_WARPS), CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(A);
+    return check_launch("usl_composite_loss_fwd");
 }
 
 int usl_composite_bwd(const float *raw, const float *z, const float *beta, const uint8_t *valid, int64_t R, int S,

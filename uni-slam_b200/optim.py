@@ -72,6 +72,17 @@ class FusedAdam:
             a.step = 0 if self._step_dev is not None else st["step"]
         L.call("usl_adam_step", arr, len(items), 1, L.ptr(self._step_dev), int(self.zero_grad_in_step), L.stream())
 
+    @torch.no_grad()
+    def reset_state(self):
+        """Back to a freshly constructed optimiser (zero moments, step 0) without reallocating: what the host code gets by
+        building a new torch.optim.Adam per tracked / mapped frame (Tracker.py:324-329, Mapper.py:364), but with stable
+        state pointers, so a CUDA graph that captured step() stays valid across frames."""
+        for st in self.state.values():
+            st["step"] = 0
+            st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+        if self._step_dev is not None:
+            self._step_dev.zero_()
+
     def zero_grad(self, set_to_none=False):
         for g in self.param_groups:
             for p in g["params"]:

@@ -250,13 +250,11 @@ class MappingStep(_Profiled):
         pts.x = None; pts.rays_o, pts.rays_d, pts.z, pts.valid = v(self.rays_o), v(self.rays_d), v(self.z), v(self.valid)
         pts.S, pts.n = S, R * S
         self._call("usl_field_fwd", byref(fs.field), byref(pts), v(self.raw), ptr(self.feat), ptr(self.jac) if joint else None, st)
-        self._call("usl_composite_fwd", v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), R, S, v(self.term), v(self.punc), v(self.depth),
-                   v(self.rgb), v(self.dunc), None, st)
         if fork:
             cur.wait_stream(side)
-        # ---- a-9: losses, phase 1 (sums + counts) ----
-        self._call("usl_loss_fwd", byref(self.loss_args), v(self.raw), v(self.z), v(self.gt_depth), v(self.gt_color), v(self.valid), v(self.punc),
-                   v(self.depth), v(self.rgb), None, R, S, ptr(self.acc), v(self.mask), st)
+        # ---- a-8 + a-9 phase 1: compositing and the loss sums / counts in one launch (the mapper's mask is per ray) ----
+        self._call("usl_composite_loss_fwd", byref(self.loss_args), v(self.raw), v(self.z), ptr(fs.beta), v(self.valid), R, S, v(self.gt_depth),
+                   v(self.gt_color), v(self.term), v(self.punc), v(self.depth), v(self.rgb), v(self.dunc), ptr(self.acc), v(self.mask), st)
         if self.acc_hook is not None:
             self.acc_hook(self.acc)
         # ---- backward: loss gradient + compositing adjoint (+ loss value) in one launch, then the field ----
