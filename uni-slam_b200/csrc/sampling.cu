@@ -344,11 +344,17 @@ __device__ __forceinline__ float decode_sdf_batched(const usl_grid_t &g, const f
     return out[0];
 }
 
-__global__ void __launch_bounds__(128) zsample_nodepth_kernel(const __grid_constant__ NoDepthArgs A) {
+// ND_WARPS rays per CTA.  Depth-less rays are a few per cent of a batch, scattered, and each is one long dependent chain
+// (ray -> stratified z -> two rounds of 8 levels of gathers -> decoder -> sequential cdf -> searchsorted -> rank merge), so the
+// kernel's duration is that chain's latency: 1, 2 and 4 rays per CTA all measure 25 us on the mapping workload.
+#ifndef ND_WARPS
+#define ND_WARPS 4
+#endif
+__global__ void __launch_bounds__(ND_WARPS * 32) zsample_nodepth_kernel(const __grid_constant__ NoDepthArgs A) {
     __shared__ MlpSmem sm;
-    __shared__ float s_z[4][ND_MAX_STRAT], s_w[4][ND_MAX_STRAT], s_cdf[4][ND_MAX_STRAT], s_smp[4][ND_MAX_IMP];
+    __shared__ float s_z[ND_WARPS][ND_MAX_STRAT], s_w[ND_WARPS][ND_MAX_STRAT], s_cdf[ND_WARPS][ND_MAX_STRAT], s_smp[ND_WARPS][ND_MAX_IMP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t r = (int64_t)blockIdx.x * 4 + warp;
+    const int64_t r = (int64_t)blockIdx.x * ND_WARPS + warp;
     // only rays with gt_depth == 0 take this branch (gt_mask, Renderer.py:83,104): skip the weight staging otherwise
     const bool mine = r < A.n_rays && (!A.valid || A.valid[r]) && !(A.gt_depth[r] > 0.f);
     if (!__syncthreads_or(mine ? 1 : 0)) return;
@@ -630,7 +636,7 @@ int usl_zsample_nodepth(const usl_zsample_args_t *a, const usl_field_t *f, const
     NoDepthArgs A;
     A.a = *a; A.f = *f; A.beta = beta; A.rays_o = rays_o; A.rays_d = rays_d; A.gt_depth = gt_depth;
     A.t_rand_uni = t_rand_uni; A.u_pdf = u_pdf; A.valid = valid; A.row_map = row_map; A.n_rays = n_rays; A.z = z; A.pdf_inds = pdf_inds;
-    zsample_nodepth_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, (cudaStream_t)stream>>>(A);
+    zsample_nodepth_kernel<<<(unsigned)((n_rays + ND_WARPS - 1) / ND_WARPS), ND_WARPS * 32, 0, (cudaStream_t)stream>>>(A);
     return check_launch("usl_zsample_nodepth");
 }
 
