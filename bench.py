@@ -584,7 +584,11 @@ def multi_gpu_legs(args, P, par, pg, step, wl, one_step, mode, flat_idx, flat_u,
         return float(tt[0])
     nbytes = n * 4
     bus = lambda ms: 2 * (world - 1) / world * nbytes / (ms * 1e-3) / 1e9
-    coll = {"bytes": nbytes, "collective": "usl_allreduce_sum (two-shot over peer memory)" if pg is not None else "ncclAllReduce"}
+    label = "ncclAllReduce"
+    if pg is not None:
+        label = ("usl_allreduce_sum (two-shot, multimem.ld_reduce / multimem.st through the NVSwitch)" if pg.use_multicast
+                 else "usl_allreduce_sum (two-shot over peer memory, peer-to-peer loads / stores)")
+    coll = {"bytes": nbytes, "collective": label}
     ms = timeit(lambda: dist.all_reduce(step.fs.g_all[:n]))
     coll["nccl_us"] = ms * 1e3; coll["nccl_bus_gbs"] = bus(ms)
     if pg is not None:
@@ -992,6 +996,12 @@ def main():
     ap.add_argument("--quick", action="store_true", help="mapping step only (used under ncu): skip e2e / tracking / dense query / Adam / cpu baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # libraries write banners to file descriptor 1 ("NCCL version ..."): send everything but our own prints to stderr, so
+        # that stdout carries the one JSON line and nothing else
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = os.fdopen(keep, "w", buffering=1)
     if args.impl == "reference":
         if args.steps > 5:
             args.steps = 5          # bounded sample: a CPU iteration takes seconds

@@ -456,6 +456,23 @@ def test_fused_adam_matches_torch_adam():
     assert set(sd) == {"state", "param_groups"} and set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
     with pytest.raises(ValueError):
         P.FusedAdam([torch.zeros(1, device=DEV, requires_grad=True) for _ in range(25)])   # the launch limit is reported at construction
+    # reset_state() == a freshly built optimiser (the host code builds a new Adam per frame), also with the device step counter
+    for dev_counter in (False, True):
+        w0 = torch.randn(257, generator=g).to(DEV)
+        pa, pb = w0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+        used, fresh = P.FusedAdam([pa], lr=0.02), P.FusedAdam([pb], lr=0.02)
+        if dev_counter:
+            used.enable_graph_step_counter(DEV); fresh.enable_graph_step_counter(DEV)
+        for _ in range(3):
+            pa.grad = torch.randn(257, generator=g).to(DEV); used.step()
+        with torch.no_grad():
+            pa.copy_(w0)
+        used.reset_state()
+        for _ in range(2):
+            gr = torch.randn(257, generator=g).to(DEV)
+            pa.grad = gr.clone(); pb.grad = gr.clone()
+            used.step(); fresh.step()
+        assert torch.equal(pa.detach(), pb.detach())
 
 
 def test_tcgen05_forward_matches_cuda_core_forward(monkeypatch):
