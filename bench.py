@@ -186,7 +186,8 @@ def run_ours(args, rank, world, local_rank):
     meta, tabs, dec, beta = wlmod.init_field_tensors(cfg, wl.bound, wl.per_level_scale, dev, seed=0)
     R, S = wl.n_rays, wl.S
     par = importlib.import_module("uni-slam_b200.parallel")
-    pg = par.PeerGroup(dev) if (world > 1 and args.collective == "peer") else None
+    pg = par.PeerGroup(dev, use_multicast={"auto": "auto", "on": True, "off": False}[args.multicast]) if (world > 1 and args.collective == "peer") else None
+    overlap = True if args.overlap else False if args.no_overlap else None      # None: the library's measured default
     step = P.MappingStep(meta, tabs[0], tabs[1], dec, beta, n_stratified=cfg.n_stratified, n_importance=cfg.n_importance,
                          truncation=cfg.truncation, max_rays=R, max_frames=wl.K, grad_alloc=pg.alloc if pg else None)
     cam_poses = wl.cam_poses.clone()
@@ -205,7 +206,8 @@ def run_ours(args, rank, world, local_rank):
 
     reduce_grads = None
     if world > 1:
-        reduce_grads = par.attach_peer_collectives(step, pg, overlap=args.overlap) if pg else par.attach_mapping_collectives(step, overlap=args.overlap)
+        reduce_grads = (par.attach_peer_collectives(step, pg, overlap=overlap, side_ctas_per_sm=args.overlap_ctas) if pg
+                        else par.attach_mapping_collectives(step, overlap=bool(overlap)))
     my_rays = par.slab_range(R, rank, world)                           # strong scaling: this rank's contiguous slice of the batch
     mode = {"strong": False}                                           # flipped for the strong-scaling leg
 
@@ -498,6 +500,11 @@ def run_ours(args, rank, world, local_rank):
                 "value_l2_warm": samples / (warm_ms * 1e-3), "prefit_loss": losses[:1] + losses[-1:], **mg, **extra}
         if world > 1:
             line["config"]["collective"] = mg.get("collective", {}).get("collective")
+            ov = step.rgb_grads_hook is not None
+            line["config"]["exchange_overlapped_with_backward"] = bool(ov)
+            if pg is not None:
+                line["config"]["exchange_in_step"] = ("colour-table gradient through the NVSwitch (multimem) beside the sdf half of the backward, rest after it"
+                                                      if ov else line["config"]["collective"])
         print(json.dumps(line), flush=True)
     if world > 1:
         # clean teardown: drop every captured graph (they hold communicator / peer-memory work), synchronise, then destroy the
@@ -987,7 +994,11 @@ def main():
     ap.add_argument("--config", default="replica_room0", choices=["replica_room0", "scannet_scene0000"],
                     help="workload: BASELINE configs[1] (default, the metric's config) or configs[2] (ScanNet-shaped; extra)")
     ap.add_argument("--overlap", action="store_true", help="N>1: exchange the colour-table gradient on a side stream while the sdf half of "
-                    "field_bwd runs (measured: 565 vs 577 us at N=2, 623 vs 613 us at N=4 -- off by default)")
+                    "field_bwd runs (default: on with the multimem exchange, i.e. from 8 ranks; off with peer-to-peer loads, where it "
+                    "measured 565 vs 577 us at N=2 and 623 vs 613 us at N=4)")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one exchange after the backward")
+    ap.add_argument("--multicast", default="auto", choices=["auto", "on", "off"], help="N>1: reduce through the NVSwitch (multimem); auto = from 8 ranks")
+    ap.add_argument("--overlap-ctas", type=int, default=1, help="with --overlap: CTAs per SM of the exchange kernel that runs beside the backward")
     ap.add_argument("--slam-frames", type=int, default=200, help="frames of the full-resolution Tracker+Mapper loop leg (0 = skip)")
     ap.add_argument("--no-extras", action="store_true", help="skip the ScanNet-shaped mapping leg and the SLAM loop leg")
     ap.add_argument("--trace", action="store_true", help="dump a kernel timeline of two replayed steps to gpurun_out/trace_rank<r>.json")

@@ -50,7 +50,9 @@ class PeerGroup:
             raise RuntimeError("PeerGroup: at most 8 ranks (one NVSwitch domain)")
         self.device = device
         self._handles = {}
-        # "auto": the switch-side reduction pays off from 8 ranks (measured, see the class docstring)
+        # "auto": for a stand-alone exchange the switch-side reduction pays off from 8 ranks (measured, see the class docstring);
+        # an exchange that runs BESIDE the backward (attach_peer_collectives) uses it at every world size
+        self.multicast_mode = use_multicast
         self.use_multicast = (self.world >= 8) if use_multicast == "auto" else bool(use_multicast)
         nb = L.load().usl_peer_ctrl_bytes()
         self.ctrl = self._symm_zeros(nb // 4)
@@ -63,7 +65,7 @@ class PeerGroup:
         self = cls.__new__(cls)
         self._sm, self.group, self.gname, self.rank, self.world, self.device = None, None, None, 0, 1, device
         self._handles = {}
-        self.use_multicast = False
+        self.use_multicast = False; self.multicast_mode = False
         self.ctrl = self._symm_zeros(L.load().usl_peer_ctrl_bytes() // 4)
         self._ctrl_ptrs = self._handles[self.ctrl.data_ptr()].buffer_ptrs
         return self
@@ -84,8 +86,9 @@ class PeerGroup:
     def alloc(self, numel):
         return self._symm_zeros(numel)
 
-    def peers(self, t: torch.Tensor) -> L.Peers:
-        """usl_peers_t for a tensor obtained from alloc(): every rank's copy of it + the control blocks."""
+    def peers(self, t: torch.Tensor, multicast=None) -> L.Peers:
+        """usl_peers_t for a tensor obtained from alloc(): every rank's copy of it + the control blocks.
+        multicast: None = the group's default for stand-alone exchanges; True / False = this call's choice."""
         h = self._handles.get(t.data_ptr())
         if h is None:
             raise ValueError("PeerGroup.peers: tensor was not allocated by this PeerGroup")
@@ -94,7 +97,7 @@ class PeerGroup:
         for p in range(self.world):
             P.buf[p] = h.buffer_ptrs[p]
             P.ctrl[p] = self._ctrl_ptrs[p]
-        P.mc = self.multicast_ptr(t) if self.use_multicast else None
+        P.mc = self.multicast_ptr(t) if (self.use_multicast if multicast is None else multicast) else None
         return P
 
     def multicast_ptr(self, t: torch.Tensor):
@@ -107,10 +110,10 @@ class PeerGroup:
         P = self.peers(self.ctrl)
         L.call("usl_exchange_sums", byref(P), L.ptr(acc), L.stream())
 
-    def allreduce(self, t: torch.Tensor, n_floats: int, offset_floats: int = 0, channel: int = 0, max_ctas_per_sm: int = 0):
+    def allreduce(self, t: torch.Tensor, n_floats: int, offset_floats: int = 0, channel: int = 0, max_ctas_per_sm: int = 0, multicast=None):
         """channel: exchanges in flight at the same time (different streams) need different barrier channels;
         max_ctas_per_sm=1: a small grid that shares the SMs with a compute kernel (the pass is bound by the links)."""
-        P = self.peers(t)
+        P = self.peers(t, multicast)
         P.channel, P.max_ctas_per_sm = int(channel), int(max_ctas_per_sm)
         L.call("usl_allreduce_sum", byref(P), int(offset_floats), int(n_floats), L.stream())
 
@@ -149,18 +152,29 @@ class FusedShardedAdam:
                len(self.ranges), self.betas[0], self.betas[1], self.eps, 0, L.ptr(self.step_dev), L.stream())
 
 
-def attach_peer_collectives(step, pg: PeerGroup, overlap: bool = False):
+def attach_peer_collectives(step, pg: PeerGroup, overlap=None, side_ctas_per_sm: int = 1):
     """Wire the hand-written exchange steps onto a MappingStep whose gradient buffer came from pg.alloc.  Returns
     reduce_grads(), to be called after step.run().
 
-    overlap=False (default): one usl_allreduce_sum over the whole buffer after the backward.
+    overlap=False: one usl_allreduce_sum over the whole buffer after the backward.
     overlap=True: the backward runs as two launches, colour grid first; the colour-table gradient (87 % of the bytes, the
     first contiguous range of the flat buffer) is exchanged on a side stream by a one-CTA-per-SM kernel WHILE the sdf half
     of the backward runs (which leaves one CTA slot per SM free for it); reduce_grads() then exchanges the remaining range
     [sdf table | decoders | beta | poses] and joins the side stream.  CUDA-graph capturable (fork / join on events).
-    Measured (kernel timeline, bench.py --trace): the exchange does run beside the sdf half, but sharing the SMs stretches
-    it from 90 to 150 us and the split backward costs 20 us more than the single launch: 565 vs 577 us per step at N = 2,
-    623 vs 613 us at N = 4 -- hence off by default."""
+    overlap=None (default): on, with both exchanges going through the switch (multimem), whenever the fabric offers a multicast
+    mapping and the group was not built with use_multicast=False; off otherwise.  Measured:
+      * peer-to-peer loads / stores (kernel timeline, bench.py --trace): the exchange does run beside the sdf half, but its
+        loads and the scatter's atomics share the SMs' LSU path -- it stretches from 90 to 150 us and the split backward costs
+        20 us more than the single launch: 565 vs 577 us per step at N = 2, 623 vs 613 us at N = 4 -- no gain;
+      * multimem: the switch does the arithmetic, one CTA per SM keeps the links busy, and the exchange hides almost
+        completely behind the sdf half: N = 8: 614 -> 540 us per step (1 CTA per SM; 547 / 545 us with 2 / 4); N = 2: 559
+        (peer-to-peer, not overlapped) -> 543 us, although the stand-alone multimem exchange is the slower one there (639 us
+        per step when it is not overlapped)."""
+    fs = step.fs
+    mc_ok = pg.world > 1 and pg.multicast_mode is not False and pg.multicast_ptr(fs.g_all) is not None
+    if overlap is None:
+        overlap = mc_ok
+    mc = True if (overlap and mc_ok) else None              # beside the backward: through the switch at every world size
     step.acc_hook = pg.exchange_sums
     fs = step.fs
     if not overlap:
@@ -174,12 +188,12 @@ def attach_peer_collectives(step, pg: PeerGroup, overlap: bool = False):
     def rgb_hook(_g_rgb):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            pg.allreduce(fs.g_all, n_rgb, 0, channel=1, max_ctas_per_sm=1)
+            pg.allreduce(fs.g_all, n_rgb, 0, channel=1, max_ctas_per_sm=side_ctas_per_sm, multicast=mc)
     step.rgb_grads_hook = rgb_hook
     step.bwd_leave_room = True
 
     def reduce_rest():
-        pg.allreduce(fs.g_all, fs.n_grad_padded - n_rgb, n_rgb, channel=0)
+        pg.allreduce(fs.g_all, fs.n_grad_padded - n_rgb, n_rgb, channel=0, multicast=mc)
         torch.cuda.current_stream().wait_stream(side)
     return reduce_rest
 
