@@ -879,7 +879,10 @@ def bench_dense_query(P, wl, meta, tabs, dec, dev, rank, world, dist=None):
     npts = q.slab_points(0, ny)
     peak, _ = _peaks()
     return {"dense_query_points": npts, "dense_query_ms": ms, "dense_query_points_per_s": npts / (ms * 1e-3),
-            "dense_query_alg_gbs": npts * 1028 / (ms * 1e-3) / 1e9, "dense_query_frac_of_hbm_peak_per_gpu": npts * 1028 / (ms * 1e-3) / 1e9 / peak / world,
+            # not an HBM-roofline statement: neighbouring grid points re-hit the same corners in L1 / L2.  Compulsory DRAM traffic is
+            # the 6.6 MB table + the 4 B / point output; the kernel is bound by instruction issue (ncu in profiles/)
+            "dense_query_gathered_bytes_per_s_gbs": npts * 1028 / (ms * 1e-3) / 1e9,
+            "dense_query_output_gbs": npts * 4 / (ms * 1e-3) / 1e9, "dense_query_bound": "instruction issue + latency (ncu: profiles/rNN_ncu_targets.txt)",
             "dense_query_gather_ms": gather_ms,
             "mesh_marching_cubes_ms": float(tm[0]), "mesh_vertex_colors_ms": float(tm[1]), "mesh_vertices": int(tm[2]), "mesh_faces": int(tm[3]),
             "mesh_note": "usl_mc_classify + 2 scans + usl_mc_emit on the device-resident slab(s), vertex colours by the fused field query; "

@@ -29,6 +29,6 @@ def test_generator_reproduces_committed_fixtures(tmp_path):
 
 def test_generator_does_not_import_the_product_package():
     """Test infrastructure must not depend on product code: the generator's scene lives in oracle/scene.py."""
-    for f in ("gen_golden.py", "scene.py"):
+    for f in ("gen_golden.py", "scene.py", "time_reference_cpu.py"):
         src = open(os.path.join(REPO, "oracle", f)).read()
         assert "import_module" not in src and "from uni" not in src, f
