@@ -64,6 +64,33 @@ def test_mapping_iteration_matches_reference(name):
         assert rel_err(cam_poses.grad, g["grad_cam_poses"]) < 1e-5
 
 
+def test_nodepth_z_override_is_what_the_renderer_integrates_along():
+    """The stage-wise full-size gate (tests/fullsize_cases.py) feeds the checked implementation's depth-less sample positions
+    to the oracle: the override must replace exactly those rows, leave the oracle's own resampling on record, and reproduce
+    the unmodified result when it equals it."""
+    g = load_golden("map_replica_k7")
+    assert "u_pdf" in g                                            # the case has depth-less rays
+    c2ws = T(g["call0_c2ws"])
+    batches = [(c2ws, T(g["call0_depths"]), T(g["call0_colors"]), T(g["call0_rays_d_cam"]), T(g["call0_indices"]))]
+    args = (float(g["truncation"]), int(g["n_stratified"]), int(g["n_importance"]))
+
+    def run(override):
+        parts = {}
+        loss = path_ref.mapping_iteration(golden_field(g, 0), batches, *args, _draws(g), parts=parts, z_nodepth_override=override)
+        return float(loss), parts
+    loss0, p0 = run(None)
+    own = p0["z_nodepth_own"]
+    holes = ~(p0["gt_depth"] > 0)
+    assert torch.equal(p0["ret"][5][holes], own) and int(holes.sum()) == own.shape[0] > 0
+    loss1, p1 = run(own.clone())                                   # override == own z: nothing changes
+    assert loss1 == loss0 and torch.equal(p1["ret"][5], p0["ret"][5])
+    shifted = own + 1e-3
+    loss2, p2 = run(shifted)
+    assert torch.equal(p2["ret"][5][holes], shifted) and torch.equal(p2["ret"][5][~holes], p0["ret"][5][~holes])
+    assert torch.equal(p2["z_nodepth_own"], own) and torch.equal(p2["pdf_inds"], p0["pdf_inds"])
+    assert loss2 != loss0
+
+
 @pytest.mark.parametrize("name", ["track_replica", "track_scannet", "track_scannet_nomask"])
 def test_tracking_iteration_matches_reference(name):
     g = load_golden(name)
