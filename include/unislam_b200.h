@@ -381,6 +381,40 @@ USL_API int usl_scan_u8(const uint8_t *in, int64_t n, int popcount, uint32_t *ou
                         usl_stream_t stream);
 USL_API int usl_scan_u8_blocks(int64_t n, int64_t *n_blocks);
 
+/* ---- f4: mesh culling after marching cubes (src/tools/cull_mesh.py:31-148; called from src/Mapper.py:556,570 and
+ * src/utils/Mesher.py:274) ---------------------------------------------------------------------------------------------------
+ * usl_mesh_cull_frames = the frame loop of cull_mesh (cull_mesh.py:58-99): seen[v] |= "some frame k has vertex v inside its
+ * image (0 < u < W, 0 < v < H, edge = 0), in front of the camera (0 <= -z), and -- eval_rec, cfg['meshing']['eval_rec'] -- not
+ * behind the bilinearly sampled sensor depth + truncation".  Projection as the reference writes it: cam = w2c @ [p,1], x negated,
+ * uv = K @ cam, z = uv_z + 1e-5, depth sampled by F.grid_sample(align_corners=True, zeros) at 2*(u/W, v/H) - 1.
+ * seen is OR-accumulated: the caller zero-fills it once and may call again per range of frames (whole_mask = !seen). */
+typedef struct usl_cull_frames_args {
+    const float *verts;               /* [V,3] mesh vertices as stored in the PLY (world frame, already divided by scale) */
+    int64_t V;
+    const float *w2c;                 /* [K,4,4] torch.inverse(c2w) of every frame (estimated or ground-truth poses, cull_mesh.py:63-69) */
+    const float *depths;              /* [K,H,W] sensor depth frames; may be null when eval_rec == 0 */
+    int32_t K, H, W;
+    float fx, fy, cx, cy, truncation;
+    int32_t eval_rec;
+    int32_t frames_per_cta;           /* frames one CTA tests before it moves on (their depth images share L2): 0 = default 16, max 64 */
+    uint8_t *seen;                    /* [V] in/out */
+} usl_cull_frames_args_t;
+USL_API int usl_mesh_cull_frames(const usl_cull_frames_args_t *a, usl_stream_t stream);
+/* cull_out_bound_mesh's mesh_bound.contains(vertices) (cull_mesh.py:136-142) for a closed CONVEX bound (the reference's bound is
+ * the convex hull Mesher.get_bound_from_frames returns): inside[v] = all_f (planes[f,0:3] . p + planes[f,3] <= 0); planes[F,4]
+ * outward, on the device. */
+USL_API int usl_mesh_cull_hull(const float *verts, int64_t V, const float *planes, int32_t F, uint8_t *inside, usl_stream_t stream);
+/* The face rule + trimesh's update_faces / remove_unreferenced_vertices (cull_mesh.py:101-104, 143-146), order-preserving:
+ *   usl_mesh_face_keep: keep[t] = any (require_all = 0, cull_mesh: vmask = seen) / all (require_all = 1, bound: vmask = inside) of
+ *                       the face's three vertex flags; vref[v] = 1 for every vertex of a kept face (caller zero-fills vref)
+ *   usl_scan_u8(keep) -> foff, T';  usl_scan_u8(vref) -> voff, V'   (popcount = 0)
+ *   usl_mesh_compact:   verts_out[voff[v]] = verts[v] (+ colours, [V,3] u8, both or neither), faces_out[foff[t]] = voff[faces[t]] */
+USL_API int usl_mesh_face_keep(const int32_t *faces, int64_t T, const uint8_t *vmask, int64_t V, int32_t require_all, uint8_t *keep,
+                               uint8_t *vref, usl_stream_t stream);
+USL_API int usl_mesh_compact(const float *verts, const uint8_t *colors, int64_t V, const int32_t *faces, int64_t T,
+                             const uint8_t *keep, const uint8_t *vref, const uint32_t *voff, const uint32_t *foff,
+                             float *verts_out, uint8_t *colors_out, int32_t *faces_out, usl_stream_t stream);
+
 /* ---- 8e: multi-GPU exchange steps of the sharded mapping iteration, over peer memory (NVLink / NVSwitch) -----------
  * The reference is single-GPU; these entry points are what its proposed `allreduce_grads` seam becomes.
  * The host layer maps every rank's buffers into every rank's address space (CUDA IPC / symmetric memory: one allocation

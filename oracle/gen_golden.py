@@ -45,6 +45,9 @@ CASES = {
     # Renderer.render_img (Renderer.py:160-223): whole frame in ray_batch_size chunks, last chunk ragged
     "img_replica": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, ray_batch=500),
     "img_scannet": dict(yaml="configs/ScanNet/scene0000.yaml", H=23, W=31, s=0.05, ray_batch=300),
+    # src/tools/cull_mesh.py: cull_mesh (frustum + occlusion test against the frames, both eval_rec settings) and
+    # cull_out_bound_mesh (convex bound) on a small marching-cubes mesh of the analytic room
+    "cull_replica": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, n_frames=7, voxel=0.31),
 }
 
 
@@ -516,6 +519,117 @@ def gen_render_img(name, case):
     print(name, "pixels", H * W, "holes", int((dep == 0).sum()), "draws", len(rands), "mean depth", float(ret[0].mean()))
 
 
+class _Mesh:
+    """Stand-in for the trimesh.Trimesh container methods cull_mesh.py calls (trimesh is not in this image): vertices,
+    faces, update_faces(mask), remove_unreferenced_vertices(), process(), export()."""
+
+    def __init__(self, vertices, faces):
+        self.vertices = np.asarray(vertices, dtype=np.float64); self.faces = np.asarray(faces, dtype=np.int64)
+        self.face_masks = []
+
+    def update_faces(self, mask):
+        self.face_masks.append(np.asarray(mask).copy())
+        self.faces = self.faces[np.asarray(mask)]
+
+    def remove_unreferenced_vertices(self):
+        ref = np.zeros(len(self.vertices), dtype=bool)
+        ref[self.faces.reshape(-1)] = True
+        remap = np.cumsum(ref) - 1
+        self.vertices = self.vertices[ref]; self.faces = remap[self.faces]
+
+    def process(self, validate=False):
+        pass                      # trimesh's vertex merge: the test mesh has no duplicate vertices
+
+    def export(self, path):
+        self.exported = path
+
+
+class _Hull:
+    """mesh_bound of Mesher.get_bound_from_frames: a closed convex hull; contains() as the half-space test."""
+
+    def __init__(self, planes):
+        self.planes = planes
+
+    def contains(self, pts):
+        from oracle import cull_ref
+        return cull_ref.inside_hull(pts, self.planes)[0]
+
+
+def gen_cull(name, case):
+    """Runs the unmodified cull_mesh (eval_rec True and False) and cull_out_bound_mesh.  The per-vertex visibility is read
+    off one degenerate face (i,i,i) per vertex appended to the face list: update_faces() receives ~whole_mask[i] for it."""
+    import scipy.spatial
+    import src.tools.cull_mesh as CM
+    from oracle import cull_ref, mc_ref
+    from oracle import scene as syn
+    cfg = _load_cfg(case)
+    H, W = case["H"], case["W"]
+    cam = cfg["cam"]
+    K = case["n_frames"]
+    frames, dirs = _frames(cfg, case, 12 * K, seed=31)
+    frames = frames[::12]                                              # poses 48 trajectory steps apart
+    torch.manual_seed(37)
+    est = []
+    for _, _, c2w in frames:
+        c = c2w.clone(); c[:3, 3] += 0.01 * torch.randn(3); est.append(c)
+    # the mesh: marching cubes (oracle) of the analytic room on a coarse grid, PLY precision (fp32)
+    room = syn.AnalyticRoom(cfg["mapping"]["bound"])
+    b = np.asarray(cfg["mapping"]["bound"], dtype=np.float64)
+    axes = [np.arange(lo - 0.2, hi + 0.2, case["voxel"], dtype=np.float32) for lo, hi in b]
+    gx, gy, gz = np.meshgrid(axes[0], axes[1], axes[2], indexing="xy")            # (ny, nx, nz) like the Mesher's volume
+    vol = room.sdf(torch.from_numpy(np.stack([gx, gy, gz], -1))).numpy()
+    verts, faces, _ = mc_ref.marching_cubes(vol, 0.0, [a[0] for a in axes], [case["voxel"]] * 3)
+    V = len(verts)
+    faces_aug = np.concatenate([faces, np.repeat(np.arange(V)[:, None], 3, axis=1)], axis=0)
+    reader = [(k, frames[k][0], frames[k][1], frames[k][2], dirs) for k in range(K)]
+    orig = (CM.get_dataset, getattr(CM.trimesh, "load", None))
+    CM.get_dataset = lambda cfg_, args_, scale_, device="cpu": reader
+    out = {"meta_H_W_fx_fy_cx_cy": np.array([H, W, cam["fx"], cam["fy"], cam["cx"], cam["cy"]], dtype=np.float64),
+           "truncation": np.array(cfg["model"]["truncation"]), "verts": verts, "faces": faces,
+           "c2ws": _np(torch.stack(est)), "depths": _np(torch.stack([f[1] for f in frames]))}
+    try:
+        for tag, eval_rec in (("rec", True), ("vis", False)):
+            mesh = _Mesh(verts, faces_aug)
+            CM.trimesh.load = lambda f, process=False, _m=mesh: _m
+            CM.cull_mesh("mesh.ply", cfg, None, "cpu", eval_rec, estimate_c2w_list=est)
+            keep = mesh.face_masks[0]
+            out[f"seen_{tag}"] = keep[len(faces):]                      # per vertex: ~whole_mask
+            out[f"face_keep_{tag}"] = keep[:len(faces)]
+            assert mesh.exported == "mesh_culled.ply"
+            m2 = _Mesh(verts, faces)                                     # the culled mesh without the probe faces
+            m2.update_faces(keep[:len(faces)]); m2.remove_unreferenced_vertices()
+            out[f"culled_verts_{tag}"] = m2.vertices.astype(np.float32); out[f"culled_faces_{tag}"] = m2.faces
+        # convex bound: hull of the camera centres and a subset of back-projected depth points, scaled about its centre
+        # (what get_bound_from_frames assembles from the TSDF fusion; Mesher.py:117-131): with a handful of frames it cuts the mesh
+        pts = [c[:3, 3].numpy() for c in est]
+        for (_, dep, _), c in zip(frames, est):
+            d = (dirs.reshape(-1, 3) @ c[:3, :3].T) * dep.reshape(-1, 1) + c[:3, 3]
+            pts.append(d[dep.reshape(-1) > 0][::17].numpy())
+        pts = np.concatenate([np.atleast_2d(p) for p in pts], axis=0).astype(np.float64)
+        ctr = pts.mean(axis=0)
+        pts = ctr + cfg["meshing"]["mesh_bound_scale"] * (pts - ctr)
+        hull = scipy.spatial.ConvexHull(pts)
+        hv = pts[hull.vertices]
+        remap = -np.ones(len(pts), dtype=np.int64); remap[hull.vertices] = np.arange(len(hull.vertices))
+        hf = remap[hull.simplices]
+        planes = cull_ref.hull_planes(hv, hf)
+        mesh = _Mesh(verts, faces_aug)
+        ret = CM.cull_out_bound_mesh(mesh, _Hull(planes), cfg, None, "cpu", est)
+        keep = mesh.face_masks[0]
+        out["hull_verts"] = hv; out["hull_faces"] = hf
+        out["inside_hull"] = keep[len(faces):]; out["face_keep_hull"] = keep[:len(faces)]
+        m2 = _Mesh(verts, faces)
+        m2.update_faces(keep[:len(faces)]); m2.remove_unreferenced_vertices()
+        out["culled_verts_hull"] = m2.vertices.astype(np.float32); out["culled_faces_hull"] = m2.faces
+    finally:
+        CM.get_dataset = orig[0]
+        if orig[1] is not None:
+            CM.trimesh.load = orig[1]
+    _save(name, out)
+    print(name, "vertices", V, "faces", len(faces), "seen rec/vis", int(out["seen_rec"].sum()), int(out["seen_vis"].sum()),
+          "inside hull", int(out["inside_hull"].sum()), "hull faces", len(hf))
+
+
 def main():
     _setup_paths()
     torch.set_num_threads(8)
@@ -531,6 +645,8 @@ def main():
             gen_render_img(name, case)
         elif name.startswith("mesh"):
             gen_mesh_query(name, case)
+        elif name.startswith("cull"):
+            gen_cull(name, case)
         else:
             gen_tracking(name, case)
 

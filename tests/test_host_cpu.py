@@ -181,9 +181,9 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     pairs = [("usl_level_t", L.Level), ("usl_grid_t", L.Grid), ("usl_mlp_t", L.Mlp), ("usl_field_t", L.Field), ("usl_bound_t", L.Bound),
              ("usl_points_t", L.Points), ("usl_zsample_args_t", L.ZSampleArgs), ("usl_ray_batch_t", L.RayBatch), ("usl_ray_setup_t", L.RaySetup),
              ("usl_loss_args_t", L.LossArgs), ("usl_adam_group_t", L.AdamGroup), ("usl_peers_t", L.Peers), ("usl_adam_range_t", L.AdamRange),
-             ("usl_mc_args_t", L.McArgs)]
+             ("usl_mc_args_t", L.McArgs), ("usl_cull_frames_args_t", L.CullFramesArgs)]
     last = {"usl_ray_setup_t": "ray_offset", "usl_peers_t": "max_ctas_per_sm", "usl_mc_args_t": "faces", "usl_adam_group_t": "step",
-            "usl_points_t": "n", "usl_field_t": "bound_hi"}
+            "usl_points_t": "n", "usl_field_t": "bound_hi", "usl_cull_frames_args_t": "seen"}
     src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(REPO, "include", "unislam_b200.h")}"', "int main(void) {"]
     for cname, _ in pairs:
         src.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')

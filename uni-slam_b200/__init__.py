@@ -12,7 +12,8 @@ Public surface (mirrors the reference's operator API for the path, SURVEY.md sec
   RenderImageStep           forward-only whole-frame renderer      (f3, Renderer.render_img)
   FusedAdam                 one-launch torch.optim.Adam equivalent (a-12 / f1)
   KeyframeStore             device-resident keyframe subsets + window views (f2, Mapper.py:315-356,528-541)
-  mesh                      marching cubes on the device-resident volume, vertex colours, PLY (f4, Mesher.py:230-276)
+  mesh                      marching cubes on the device-resident volume, vertex colours, frame / bound culling, PLY
+                            (f4, Mesher.py:230-276, tools/cull_mesh.py)
   parallel                  multi-GPU: peer-memory exchange kernels, slab / ray-range sharding (8e)
   ops                       thin per-kernel wrappers over the C-ABI
 There is no CPU path: every op raises RuntimeError if lib/libunislam_b200.so is missing.

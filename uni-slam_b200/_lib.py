@@ -93,6 +93,12 @@ class McArgs(Structure):
                 ("voff", c_void_p), ("toff", c_void_p), ("verts", c_void_p), ("vkeys", c_void_p), ("faces", c_void_p)]
 
 
+class CullFramesArgs(Structure):
+    _fields_ = [("verts", c_void_p), ("V", c_int64), ("w2c", c_void_p), ("depths", c_void_p), ("K", c_int32), ("H", c_int32), ("W", c_int32),
+                ("fx", c_float), ("fy", c_float), ("cx", c_float), ("cy", c_float), ("truncation", c_float), ("eval_rec", c_int32),
+                ("frames_per_cta", c_int32), ("seen", c_void_p)]
+
+
 ADAM_MAX_GROUPS = 24
 _P = c_void_p
 _SIGS = {
@@ -138,6 +144,10 @@ _SIGS = {
     "usl_mc_emit": [POINTER(McArgs), _P],
     "usl_scan_u8": [_P, c_int64, c_int, _P, _P, _P, _P],
     "usl_scan_u8_blocks": [c_int64, POINTER(c_int64)],
+    "usl_mesh_cull_frames": [POINTER(CullFramesArgs), _P],
+    "usl_mesh_cull_hull": [_P, c_int64, _P, c_int32, _P, _P],
+    "usl_mesh_face_keep": [_P, c_int64, _P, c_int64, c_int32, _P, _P, _P],
+    "usl_mesh_compact": [_P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P],
     "usl_exchange_sums": [POINTER(Peers), _P, _P],
     "usl_peer_barrier": [POINTER(Peers), _P],
     "usl_allreduce_sum": [POINTER(Peers), c_int64, c_int64, _P],

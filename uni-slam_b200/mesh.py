@@ -10,8 +10,13 @@ moving the 504 MiB volume to the host.
 
 Triangulation: a generated, crack-free 256-case table (csrc/mc_tables.h); the reference's skimage uses Lewiner's tables,
 which differ in ambiguous configurations only (oracle/mc_ref.py, parity unpinned for the triangulation -- scikit-image is
-not in this image).  The frustum / bound culling the reference applies afterwards (cull_mesh.py) needs the dataset frames
-and open3d and stays host policy; `cull_by_bound` below is the bound part of it on the device arrays.
+not in this image).
+
+Culling (src/tools/cull_mesh.py), on the device arrays marching cubes left:
+  MeshCuller.cull_by_frames  = cull_mesh (cull_mesh.py:31-109; Mapper.py:556,570): drop what no frame sees
+  MeshCuller.cull_by_hull    = cull_out_bound_mesh (cull_mesh.py:112-148; Mesher.py:274): drop what lies outside the convex bound
+The convex bound itself (Mesher.get_bound_from_frames: open3d TSDF fusion + convex hull, Mesher.py:64-131) is an INPUT here
+(hull vertices + faces); building it is third-party geometry outside the path.
 """
 from ctypes import byref, c_int64
 from typing import Optional, Sequence, Tuple
@@ -21,7 +26,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from ._lib import call, ptr, stream
+from ._lib import call, cptr, ptr, stream
 
 
 class MeshExtractor:
@@ -80,6 +85,102 @@ def vertex_colors(meta: ops.FieldMeta, sdf_table, rgb_table, dec, verts: torch.T
     with torch.no_grad():
         raw = ops.field_points(meta, x, sdf_table.detach(), rgb_table.detach(), [d.detach() for d in dec])
     return (raw[:, :3].clamp(0, 1) * 255).round().to(torch.uint8)
+
+
+def hull_planes(hull_verts, hull_faces) -> np.ndarray:
+    """(F,4) fp32 outward planes of a closed convex hull given as vertices + triangles (what trimesh.Trimesh holds for
+    Mesher.get_bound_from_frames' return value): unit normal n and offset d with n.x + d <= 0 inside; the orientation is
+    fixed by the hull's vertex centroid, so the winding of the faces does not matter."""
+    hv = np.asarray(hull_verts, dtype=np.float64); hf = np.asarray(hull_faces, dtype=np.int64)
+    a, b, c = hv[hf[:, 0]], hv[hf[:, 1]], hv[hf[:, 2]]
+    n = np.cross(b - a, c - a)
+    ln = np.linalg.norm(n, axis=1, keepdims=True)
+    ok = ln[:, 0] > 0                                                # degenerate (zero-area) hull faces carry no constraint
+    n, a = n[ok] / ln[ok], a[ok]
+    d = -(n * a).sum(axis=1)
+    flip = (n @ hv.mean(axis=0) + d) > 0
+    n[flip] *= -1; d[flip] *= -1
+    return np.concatenate([n, d[:, None]], axis=1).astype(np.float32)
+
+
+class MeshCuller:
+    """cull_mesh / cull_out_bound_mesh (src/tools/cull_mesh.py) on device-resident meshes: verts (V,3) fp32, faces (T,3)
+    int32, optional colours (V,3) uint8 -- the arrays MeshExtractor.run / vertex_colors return.  Every method returns the
+    culled (verts, faces, colors) as new device tensors, vertex and face order preserved (trimesh's update_faces +
+    remove_unreferenced_vertices); the one host read per call is the pair of output sizes."""
+
+    def __init__(self, H, W, fx, fy, cx, cy, truncation):
+        self.cam = (int(H), int(W), float(fx), float(fy), float(cx), float(cy))
+        self.truncation = float(truncation)
+        self.frames_per_cta = 0           # 0 = library default (16 depth frames in flight, L2-resident)
+
+    # ---- per-vertex tests ----
+    def seen_by_frames(self, verts: torch.Tensor, c2ws: torch.Tensor, depths: Optional[torch.Tensor], eval_rec: bool,
+                       seen: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """NOT whole_mask of cull_mesh.py:58-99, (V,) uint8.  c2ws (K,4,4): estimate_c2w_list[:idx+1] (or the ground-truth
+        poses); depths (K,H,W) fp32 sensor depth (required with eval_rec = cfg['meshing']['eval_rec']).  Pass `seen` to
+        accumulate over several calls (ranges of frames)."""
+        H, W, fx, fy, cx, cy = self.cam
+        V, K = verts.shape[0], c2ws.shape[0]
+        if seen is None:
+            seen = torch.zeros((V,), device=verts.device, dtype=torch.uint8)
+        a = L.CullFramesArgs()
+        a.verts, a.V = cptr(verts, torch.float32, V * 3, "verts (V,3)"), V
+        w2c = torch.inverse(c2ws.to(verts.device, torch.float32)).contiguous()          # cull_mesh.py:69, batched
+        a.w2c = cptr(w2c, torch.float32, K * 16, "c2ws (K,4,4)")
+        if eval_rec and depths is None:
+            raise ValueError("MeshCuller: eval_rec needs the depth frames (K,H,W)")
+        a.depths = cptr(depths, torch.float32, K * H * W, "depths (K,H,W)") if eval_rec else None
+        a.K, a.H, a.W, a.fx, a.fy, a.cx, a.cy = K, H, W, fx, fy, cx, cy
+        a.truncation, a.eval_rec, a.frames_per_cta = self.truncation, 1 if eval_rec else 0, self.frames_per_cta
+        a.seen = cptr(seen, torch.uint8, V, "seen (V,)")
+        call("usl_mesh_cull_frames", byref(a), stream())
+        return seen
+
+    @staticmethod
+    def inside_hull(verts: torch.Tensor, planes) -> torch.Tensor:
+        """mesh_bound.contains(vertices) for a convex bound given as outward planes (F,4) (see hull_planes), (V,) uint8."""
+        V = verts.shape[0]
+        pl = torch.as_tensor(planes, dtype=torch.float32).to(verts.device).contiguous()
+        inside = torch.empty((V,), device=verts.device, dtype=torch.uint8)
+        call("usl_mesh_cull_hull", cptr(verts, torch.float32, V * 3, "verts (V,3)"), V, ptr(pl), pl.shape[0], ptr(inside), stream())
+        return inside
+
+    # ---- face rule + compaction ----
+    @staticmethod
+    def filter_faces(verts, faces, colors, vmask, require_all: bool):
+        V, T = verts.shape[0], faces.shape[0]
+        dev = verts.device
+        if V == 0 or T == 0:                                      # nothing can be referenced: the empty mesh
+            return (torch.empty((0, 3), device=dev, dtype=torch.float32), torch.empty((0, 3), device=dev, dtype=torch.int32),
+                    torch.empty((0, 3), device=dev, dtype=torch.uint8) if colors is not None else None)
+        st = stream()
+        keep = torch.empty((T,), device=dev, dtype=torch.uint8); vref = torch.zeros((V,), device=dev, dtype=torch.uint8)
+        call("usl_mesh_face_keep", cptr(faces, torch.int32, T * 3, "faces (T,3)"), T, cptr(vmask, torch.uint8, V, "vertex mask (V,)"), V,
+             1 if require_all else 0, ptr(keep), ptr(vref), st)
+        nb = c_int64(0)
+        call("usl_scan_u8_blocks", max(V, T), byref(nb))
+        sums = torch.empty((max(nb.value, 1),), device=dev, dtype=torch.int32)
+        voff = torch.empty((V,), device=dev, dtype=torch.int32); foff = torch.empty((T,), device=dev, dtype=torch.int32)
+        totals = torch.zeros((2,), device=dev, dtype=torch.int32)
+        call("usl_scan_u8", ptr(vref), V, 0, ptr(voff), ptr(sums), ptr(totals[0:1]), st)
+        call("usl_scan_u8", ptr(keep), T, 0, ptr(foff), ptr(sums), ptr(totals[1:2]), st)
+        V2, T2 = [int(v) for v in totals.cpu()]
+        verts_out = torch.empty((V2, 3), device=dev, dtype=torch.float32); faces_out = torch.empty((T2, 3), device=dev, dtype=torch.int32)
+        colors_out = torch.empty((V2, 3), device=dev, dtype=torch.uint8) if colors is not None else None
+        if V2 > 0:
+            call("usl_mesh_compact", ptr(verts), cptr(colors, torch.uint8, V * 3, "colors (V,3)") if colors is not None else None, V,
+                 ptr(faces), T, ptr(keep), ptr(vref), ptr(voff), ptr(foff), ptr(verts_out), ptr(colors_out), ptr(faces_out), st)
+        return verts_out, faces_out, colors_out
+
+    def cull_by_frames(self, verts, faces, colors, c2ws, depths, eval_rec: bool):
+        """cull_mesh: faces whose three vertices are all unseen go (cull_mesh.py:101-103)."""
+        seen = self.seen_by_frames(verts, c2ws, depths, eval_rec)
+        return self.filter_faces(verts, faces, colors, seen, require_all=False)
+
+    def cull_by_hull(self, verts, faces, colors, planes):
+        """cull_out_bound_mesh: faces with all three vertices inside the bound stay (cull_mesh.py:143-146)."""
+        return self.filter_faces(verts, faces, colors, self.inside_hull(verts, planes), require_all=True)
 
 
 def weld(parts):
