@@ -1,0 +1,74 @@
+"""TEST INFRASTRUCTURE, NOT PRODUCT CODE: loader of tests/host_harness/cull_host.cpp.
+
+The harness compiles uni-slam_b200/csrc/usl_cull.cuh -- the element functions the CUDA kernels of cull.cu inline -- for the
+host with g++ (-ffp-contract=off), so that their arithmetic can be checked without a GPU and the kernels can then be held to
+it bit for bit.  Imported by tests/ (through helpers.py) and by bench.py's isolated culling leg as the checker; it imports
+nothing from oracle/ and nothing from the product package, and the product never loads it.
+"""
+import os
+
+import numpy as np
+
+_CULL_HOST = None
+
+
+def cull_host():
+    """g++ build of tests/host_harness/cull_host.cpp (it includes uni-slam_b200/csrc/usl_cull.cuh, the source the CUDA
+    kernels inline) -> tests/_build/libcull_host.so.  Test infrastructure: never loaded by the product."""
+    global _CULL_HOST
+    if _CULL_HOST is not None:
+        return _CULL_HOST
+    import ctypes
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    tests = os.path.dirname(here)
+    src = os.path.join(here, "cull_host.cpp")
+    hdr = os.path.join(os.path.dirname(tests), "uni-slam_b200", "csrc", "usl_cull.cuh")
+    out = os.path.join(tests, "_build", "libcull_host.so")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-o", out, src], check=True)
+    lib = ctypes.CDLL(out)
+    vp, i64, ci, cf = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+    lib.cull_host_frames.restype = None
+    lib.cull_host_frames.argtypes = [vp, i64, vp, vp, ci, ci, ci, cf, cf, cf, cf, cf, ci, ci, vp]
+    lib.cull_host_hull.restype = None
+    lib.cull_host_hull.argtypes = [vp, i64, vp, ci, vp]
+    lib.cull_host_compact.restype = None
+    lib.cull_host_compact.argtypes = [vp, vp, i64, vp, i64, vp, ci, vp, vp, vp, vp, vp]
+    _CULL_HOST = lib
+    return lib
+
+
+def cull_host_frames(verts, w2c, depths, cam, truncation, eval_rec, frames_per_cta=16):
+    """seen (V,) uint8 from the host harness; verts (V,3) f32, w2c (K,4,4) f32, depths (K,H,W) f32, cam = (H,W,fx,fy,cx,cy)."""
+    lib = cull_host()
+    verts = np.ascontiguousarray(verts, dtype=np.float32); w2c = np.ascontiguousarray(w2c, dtype=np.float32)
+    depths = np.ascontiguousarray(depths, dtype=np.float32)
+    seen = np.zeros(len(verts), dtype=np.uint8)
+    H, W, fx, fy, cx, cy = cam
+    lib.cull_host_frames(verts.ctypes.data, len(verts), w2c.ctypes.data, depths.ctypes.data, len(w2c), int(H), int(W), fx, fy, cx, cy,
+                         truncation, int(eval_rec), frames_per_cta, seen.ctypes.data)
+    return seen
+
+
+def cull_host_hull(verts, planes):
+    lib = cull_host()
+    verts = np.ascontiguousarray(verts, dtype=np.float32); planes = np.ascontiguousarray(planes, dtype=np.float32)
+    inside = np.zeros(len(verts), dtype=np.uint8)
+    lib.cull_host_hull(verts.ctypes.data, len(verts), planes.ctypes.data, len(planes), inside.ctypes.data)
+    return inside
+
+
+def cull_host_compact(verts, colors, faces, vmask, require_all):
+    lib = cull_host()
+    verts = np.ascontiguousarray(verts, dtype=np.float32); faces = np.ascontiguousarray(faces, dtype=np.int32)
+    vmask = np.ascontiguousarray(vmask, dtype=np.uint8)
+    colors = np.ascontiguousarray(colors, dtype=np.uint8) if colors is not None else None
+    keep = np.zeros(len(faces), dtype=np.uint8)
+    vo = np.zeros_like(verts); fo = np.zeros_like(faces); co = np.zeros_like(colors) if colors is not None else None
+    n = np.zeros(2, dtype=np.int64)
+    lib.cull_host_compact(verts.ctypes.data, colors.ctypes.data if colors is not None else None, len(verts), faces.ctypes.data, len(faces),
+                          vmask.ctypes.data, int(require_all), keep.ctypes.data, vo.ctypes.data, co.ctypes.data if co is not None else None,
+                          fo.ctypes.data, n.ctypes.data)
+    return vo[:n[0]], fo[:n[1]], (co[:n[0]] if co is not None else None), keep

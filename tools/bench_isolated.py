@@ -1,0 +1,108 @@
+"""Bench legs that run in their OWN process (bench.py starts this file as a child at N = 1 and merges the JSON it prints).
+
+Why a child: these kernels were written after the round's GPU budget was spent, so their first execution on a B200 is
+the driver's own bench run.  A fault in them must not be able to take the headline measurement down with it: the child has
+its own CUDA context, a time limit, and whatever it prints (or fails to print) only fills the `mesh_cull` key.
+
+Leg: mesh culling (src/tools/cull_mesh.py) at Replica size -- a marching-cubes mesh of the synthetic room (1.25 cm grid,
+about a million vertices) against 64 full-resolution (1200x680) depth frames of one lap of the trajectory:
+usl_mesh_cull_frames with and without the occlusion test, the convex-bound test, the face rule + compaction; the kernel's
+marks are compared with the host harness (tests/host_harness: the kernels' own element functions compiled with g++) on a
+20 000-vertex sample.  Timing: CUDA events on the launching stream, after a warm-up call.
+"""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (REPO, os.path.join(REPO, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _timed(fn, iters=3):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        out = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, out
+
+
+def leg_mesh_cull(P, dev, n_frames=64, voxel=0.0125, sample=20000):
+    syn, meshmod = P.synthetic, P.mesh
+    cfg = syn.CONFIGS["replica_room0"]
+    cam = cfg.cam
+    seq = syn.SyntheticSequence(cfg, n_frames=800, device=dev)
+    ks = [int(k) for k in np.linspace(0, 799, n_frames)]
+    depths = torch.stack([seq.frame(k)[1] for k in ks]).contiguous()
+    c2ws = torch.stack([seq.poses[k] for k in ks]).contiguous().float()
+    # the mesh: marching cubes (usl_mc_*) of the analytic SDF on a `voxel` grid over the meshing bound (+- 0.05, Mesher.py:178-193)
+    axes = []
+    for lo, hi in cfg.bound_yaml:
+        n = int(round((hi - lo + 0.1) / voxel))
+        axes.append(torch.from_numpy(np.linspace(lo - 0.05, hi + 0.05, n)).float().to(dev))
+    nx, ny, nz = [a.numel() for a in axes]
+    vol = torch.empty((ny, nx, nz), device=dev, dtype=torch.float32)
+    for y0 in range(0, ny, 16):
+        y1 = min(y0 + 16, ny)
+        gy, gx, gz = torch.meshgrid(axes[1][y0:y1], axes[0], axes[2], indexing="ij")
+        vol[y0:y1] = seq.room.sdf(torch.stack([gx, gy, gz], dim=-1))
+    verts, faces = meshmod.MeshExtractor(axes).run(vol.contiguous())
+    V, T = int(verts.shape[0]), int(faces.shape[0])
+    culler = meshmod.MeshCuller(cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy, cfg.truncation)
+    res = {"workload": f"marching-cubes mesh of the synthetic room ({voxel * 100:.2f} cm grid: {V} vertices, {T} faces) against {n_frames} "
+                       f"depth frames {cam.W}x{cam.H} ({depths.numel() * 4 / 2**20:.0f} MiB resident)", "vertices": V, "faces": T, "frames": n_frames}
+    w2c = torch.inverse(c2ws)
+    from host_harness import loader
+    pick = torch.linspace(0, V - 1, min(sample, V), device=dev).long()
+    v_host = verts[pick].cpu().numpy()
+    depths_host = depths.cpu().numpy()
+    for tag, eval_rec in (("occlusion", True), ("frustum_only", False)):
+        ms, seen = _timed(lambda: culler.seen_by_frames(verts, c2ws, depths, eval_rec))
+        ref = loader.cull_host_frames(v_host, w2c.cpu().numpy(), depths_host, (cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy),
+                                      cfg.truncation, eval_rec, 16)
+        got = seen[pick].cpu().numpy()
+        res[f"cull_frames_{tag}_ms"] = ms
+        res[f"cull_frames_{tag}_seen_fraction"] = float(seen.float().mean())
+        res[f"cull_frames_{tag}_mismatch_vs_host_harness"] = int((got != ref).sum())
+        res[f"cull_frames_{tag}_vertex_frame_tests_per_s"] = V * n_frames / (ms * 1e-3)     # upper count: early exits do fewer
+    res["harness_sample"] = int(pick.numel())
+    ms, out = _timed(lambda: culler.cull_by_frames(verts, faces, None, c2ws, depths, True))
+    res["cull_mesh_total_ms"] = ms                                       # marks + face rule + 2 scans + compaction + the size read
+    res["culled_vertices"], res["culled_faces"] = int(out[0].shape[0]), int(out[1].shape[0])
+    # convex bound: the room's box pulled in by 30 cm, as 12 triangles (what a trimesh hull holds)
+    lo = np.array([b[0] + 0.3 for b in cfg.bound_yaml]); hi = np.array([b[1] - 0.3 for b in cfg.bound_yaml])
+    hv = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
+    hf = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]])
+    planes = meshmod.hull_planes(hv, hf)
+    ms, inside = _timed(lambda: culler.inside_hull(verts, planes))
+    res["cull_hull_ms"] = ms
+    res["cull_hull_planes"] = int(planes.shape[0])
+    res["cull_hull_mismatch_vs_host_harness"] = int((inside[pick].cpu().numpy() != loader.cull_host_hull(v_host, planes)).sum())
+    inside_box = ((verts >= torch.from_numpy(lo).float().to(dev)) & (verts <= torch.from_numpy(hi).float().to(dev))).all(dim=1)
+    res["cull_hull_mismatch_vs_box_test"] = int((inside.bool() != inside_box).sum())     # differs only by rounding on the faces
+    return res
+
+
+def main():
+    t0 = time.time()
+    out = {}
+    try:
+        P = importlib.import_module("uni-slam_b200")
+        torch.cuda.set_device(0)
+        out = leg_mesh_cull(P, "cuda:0")
+        out["seconds"] = time.time() - t0
+    except Exception as e:                                    # noqa: BLE001 -- reported, never raised into the parent
+        out = {"error": f"{type(e).__name__}: {e}"[:400]}
+    print("ISOLATED_JSON " + json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
