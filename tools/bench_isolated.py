@@ -74,6 +74,13 @@ def leg_mesh_cull(P, dev, n_frames=64, voxel=0.0125, sample=20000):
         res[f"cull_frames_{tag}_mismatch_vs_host_harness"] = int((got != ref).sum())
         res[f"cull_frames_{tag}_vertex_frame_tests_per_s"] = V * n_frames / (ms * 1e-3)     # upper count: early exits do fewer
     res["harness_sample"] = int(pick.numel())
+    # frames per CTA = how many depth frames the CTAs in flight share in L2 (1: every group streams one frame past all vertices)
+    sweep = {}
+    for fpc in (1, 4, 16, 64):
+        culler.frames_per_cta = fpc
+        sweep[str(fpc)], _ = _timed(lambda: culler.seen_by_frames(verts, c2ws, depths, True), iters=2)
+    culler.frames_per_cta = 0
+    res["cull_frames_occlusion_ms_by_frames_per_cta"] = sweep
     ms, out = _timed(lambda: culler.cull_by_frames(verts, faces, None, c2ws, depths, True))
     res["cull_mesh_total_ms"] = ms                                       # marks + face rule + 2 scans + compaction + the size read
     res["culled_vertices"], res["culled_faces"] = int(out[0].shape[0]), int(out[1].shape[0])

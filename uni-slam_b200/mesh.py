@@ -148,10 +148,15 @@ class MeshCuller:
 
     # ---- face rule + compaction ----
     @staticmethod
-    def filter_faces(verts, faces, colors, vmask, require_all: bool):
+    def filter_faces(verts, faces, colors, vmask, require_all: bool, vertex_kept: Optional[list] = None):
+        """vertex_kept: pass a list to receive the (V,) uint8 mask of the vertices that survive -- any other per-vertex array
+        (the slab's edge keys for mesh.weld) is compacted with it: keys[mask.bool()].  Multi-GPU: every rank culls its own
+        slab's mesh (a vertex's mark depends on its position only, so the two copies of a seam vertex agree), then weld."""
         V, T = verts.shape[0], faces.shape[0]
         dev = verts.device
         if V == 0 or T == 0:                                      # nothing can be referenced: the empty mesh
+            if vertex_kept is not None:
+                vertex_kept.append(torch.zeros((V,), device=dev, dtype=torch.uint8))
             return (torch.empty((0, 3), device=dev, dtype=torch.float32), torch.empty((0, 3), device=dev, dtype=torch.int32),
                     torch.empty((0, 3), device=dev, dtype=torch.uint8) if colors is not None else None)
         st = stream()
@@ -166,6 +171,8 @@ class MeshCuller:
         call("usl_scan_u8", ptr(vref), V, 0, ptr(voff), ptr(sums), ptr(totals[0:1]), st)
         call("usl_scan_u8", ptr(keep), T, 0, ptr(foff), ptr(sums), ptr(totals[1:2]), st)
         V2, T2 = [int(v) for v in totals.cpu()]
+        if vertex_kept is not None:
+            vertex_kept.append(vref)
         verts_out = torch.empty((V2, 3), device=dev, dtype=torch.float32); faces_out = torch.empty((T2, 3), device=dev, dtype=torch.int32)
         colors_out = torch.empty((V2, 3), device=dev, dtype=torch.uint8) if colors is not None else None
         if V2 > 0:
