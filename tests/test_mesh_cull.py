@@ -180,3 +180,126 @@ def test_gpu_culled_meshes_match_the_reference():
     assert np.array_equal(culler.inside_hull(verts, big).cpu().numpy(), inside)
     far = culler.cull_by_hull(verts + 100.0, faces, None, planes)
     assert far[0].shape[0] == 0 and far[1].shape[0] == 0
+
+
+# ---- CPU: the glue of mesh.get_mesh (Mesher.get_mesh in one call) with host stand-ins for the launches --------------------
+def test_grid_axes_match_the_reference():
+    """mesh.grid_axes against the axes the unmodified Mesher.get_grid_uniform produced (tests/golden/mesh_*.npz)."""
+    for name in ("mesh_replica", "mesh_scannet"):
+        g = helpers.load_golden(name)
+        axes = pkg().mesh.grid_axes(g["mc_bound"], float(g["resolution"]))
+        for a, k in zip(axes, ("axis_x", "axis_y", "axis_z")):
+            assert a.dtype == torch.float32 and np.array_equal(a.numpy(), g[k].astype(np.float32))
+
+
+def test_get_mesh_glue_with_host_stand_ins(monkeypatch, tmp_path):
+    """get_mesh's order of operations (query -> marching cubes -> colours on un-scaled vertices -> / scale -> bound culling ->
+    PLY) with every launch replaced by its host counterpart of the SAME signature (oracle marching cubes, the culling
+    harness); the launches themselves are covered by the -m gpu tests."""
+    import importlib
+    import inspect
+    import types
+    from oracle import mc_ref
+    mesh = pkg().mesh
+    steps = importlib.import_module("uni-slam_b200.steps")
+
+    class Query:
+        def __init__(self, meta, sdf_table, rgb_table, dec, axes):
+            self.ax, self.ay, self.az = [a.double() for a in axes]
+            self.nx, self.ny, self.nz = [a.numel() for a in axes]
+
+        def run(self, y_begin, y_end, out=None):
+            gy, gx, gz = torch.meshgrid(self.ay[y_begin:y_end], self.ax, self.az, indexing="ij")
+            return (torch.sqrt((gx - 0.2) ** 2 + gy ** 2 + (gz + 0.1) ** 2) - 0.9).float().reshape(-1)   # a sphere: sdf < 0 inside
+
+    assert list(inspect.signature(Query.__init__).parameters) == list(inspect.signature(steps.DenseSdfQuery.__init__).parameters)
+    assert list(inspect.signature(Query.run).parameters) == list(inspect.signature(steps.DenseSdfQuery.run).parameters)
+
+    def mc_run(self, vol, y_begin=0, y_end=None, halo=False, keys=False):
+        assert vol.shape == (self.ny, self.nx, self.nz) and y_begin == 0 and not halo
+        v, f, k = mc_ref.marching_cubes(vol.numpy(), self.level, self.origin, self.spacing)
+        out = (torch.from_numpy(v), torch.from_numpy(f.astype(np.int32)), torch.from_numpy(k))
+        return out if keys else out[:2]
+
+    def colors(meta, sdf_table, rgb_table, dec, verts, bound):
+        return (verts * 40).abs().clamp(0, 255).to(torch.uint8)                 # depends on the UN-scaled position
+
+    def inside_hull(verts, planes):
+        return torch.from_numpy(helpers.cull_host_hull(verts.numpy(), planes))
+
+    def filter_faces(verts, faces, colors, vmask, require_all, vertex_kept=None):
+        v, f, c, _ = helpers.cull_host_compact(verts.numpy(), colors.numpy() if colors is not None else None, faces.numpy(), vmask.numpy(), require_all)
+        if vertex_kept is not None:
+            ref = np.zeros(len(verts), dtype=np.uint8); ref[np.unique(faces.numpy()[cull_ref.face_filter(verts.numpy(), faces.numpy(), vmask.numpy(), require_all)[3]])] = 1
+            vertex_kept.append(torch.from_numpy(ref))
+        return torch.from_numpy(v), torch.from_numpy(f), (torch.from_numpy(c) if c is not None else None)
+
+    for fake, real in ((mc_run, mesh.MeshExtractor.run), (colors, mesh.vertex_colors), (inside_hull, mesh.MeshCuller.inside_hull),
+                       (filter_faces, mesh.MeshCuller.filter_faces)):
+        assert list(inspect.signature(fake).parameters) == list(inspect.signature(real).parameters), real
+    monkeypatch.setattr(steps, "DenseSdfQuery", Query)
+    monkeypatch.setattr(mesh.MeshExtractor, "run", mc_run)
+    monkeypatch.setattr(mesh, "vertex_colors", colors)
+    monkeypatch.setattr(mesh.MeshCuller, "inside_hull", staticmethod(inside_hull))
+    monkeypatch.setattr(mesh.MeshCuller, "filter_faces", staticmethod(filter_faces))
+
+    mc_bound = np.array([[-1.2, 1.2], [-1.1, 1.3], [-1.4, 1.0]])
+    tab = torch.zeros(4)
+    scale = 2.0
+    # the bound: a box that cuts the (scaled) sphere, as 12 triangles
+    lo, hi = np.array([-0.6, -0.3, -0.6]), np.array([0.35, 0.6, 0.3])
+    hv = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
+    hf = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]])
+    ply = str(tmp_path / "m.ply")
+    v, f, c, k = mesh.get_mesh(ply, None, tab, tab, [], None, mc_bound, resolution=0.1, scale=scale, mesh_bound=types.SimpleNamespace(vertices=hv, faces=hf), keys=True)
+    # expected, step by step
+    axes = mesh.grid_axes(mc_bound, 0.1)
+    vol = Query(None, None, None, None, axes).run(0, axes[1].numel()).reshape(axes[1].numel(), axes[0].numel(), axes[2].numel())
+    ev, ef, ek = mc_ref.marching_cubes(vol.numpy(), 0.0, [float(a[0]) for a in axes], [float(a[2] - a[1]) for a in axes])
+    ec = colors(None, None, None, None, torch.from_numpy(ev), None).numpy()
+    evs = (torch.from_numpy(ev) / scale).numpy()
+    inside, _ = cull_ref.inside_hull(evs, cull_ref.hull_planes(hv, hf))
+    rv, rf, rc, keep = cull_ref.face_filter(evs, ef, inside, True, colors=ec)
+    assert 0 < len(rv) < len(ev) and 0 < len(rf) < len(ef)
+    assert np.array_equal(v.numpy(), rv) and np.array_equal(f.numpy(), rf) and np.array_equal(c.numpy(), rc)
+    ref = np.zeros(len(ev), dtype=bool); ref[np.unique(ef[keep])] = True
+    assert np.array_equal(k.numpy(), ek[ref])
+    v2, f2, c2 = mesh.read_ply(ply)
+    assert np.array_equal(v2, rv) and np.array_equal(f2, rf) and np.array_equal(c2, rc)
+    # no bound, no colours, no file; and a level set that misses the volume
+    v, f, c = mesh.get_mesh(None, None, tab, tab, [], None, mc_bound, resolution=0.1, color=False)
+    assert c is None and np.array_equal(v.numpy(), ev) and np.array_equal(f.numpy(), ef)
+    assert mesh.get_mesh(None, None, tab, tab, [], None, mc_bound, resolution=0.1, level_set=50.0) is None
+
+
+@pytest.mark.gpu
+def test_gpu_get_mesh_one_call(tmp_path):
+    """mesh.get_mesh (Mesher.get_mesh in one call) == its pieces run one by one, with and without the bound culling."""
+    import gpu_cases
+    P = pkg()
+    mesh = P.mesh
+    g = helpers.load_golden("mesh_replica")
+    meta, tabs, dec, beta = gpu_cases.cuda_field(g, 120, DEV)
+    bound = torch.from_numpy(g["bound"])
+    mc_bound = np.stack([g["bound"][:, 0] + 0.3, g["bound"][:, 1] - 0.3], axis=1)
+    ply = str(tmp_path / "a.ply")
+    res = mesh.get_mesh(ply, meta, tabs[0], tabs[1], dec, bound, mc_bound, resolution=0.2)
+    assert res is not None
+    v, f, c = res
+    axes = mesh.grid_axes(mc_bound, 0.2)
+    q = P.DenseSdfQuery(meta, tabs[0], tabs[1], dec, [a.to(DEV) for a in axes])
+    vol = q.run(0, q.ny).view(q.ny, q.nx, q.nz)
+    v0, f0 = mesh.MeshExtractor(axes).run(vol.contiguous())
+    c0 = mesh.vertex_colors(meta, tabs[0], tabs[1], dec, v0, bound)
+    assert v0.shape[0] > 100 and torch.equal(v, v0) and torch.equal(f, f0) and torch.equal(c, c0)
+    v2, f2, c2 = mesh.read_ply(ply)
+    assert np.array_equal(v2, v0.cpu().numpy()) and np.array_equal(f2, f0.cpu().numpy()) and np.array_equal(c2, c0.cpu().numpy())
+    # bound culling: six planes of a box around the middle of the mesh
+    lo = (v0.min(dim=0)[0] * 0.7 + v0.max(dim=0)[0] * 0.3).cpu().numpy(); hi = (v0.min(dim=0)[0] * 0.3 + v0.max(dim=0)[0] * 0.7).cpu().numpy()
+    planes = np.array([[1, 0, 0, -hi[0]], [-1, 0, 0, lo[0]], [0, 1, 0, -hi[1]], [0, -1, 0, lo[1]], [0, 0, 1, -hi[2]], [0, 0, -1, lo[2]]], dtype=np.float32)
+    v, f, c, k = mesh.get_mesh(None, meta, tabs[0], tabs[1], dec, bound, mc_bound, resolution=0.2, mesh_bound=planes, keys=True)
+    inside = helpers.cull_host_hull(v0.cpu().numpy(), planes)
+    rv, rf, rc, keep = cull_ref.face_filter(v0.cpu().numpy(), f0.cpu().numpy(), inside, True, colors=c0.cpu().numpy())
+    assert 0 < len(rv) < v0.shape[0]
+    assert np.array_equal(v.cpu().numpy(), rv) and np.array_equal(f.cpu().numpy(), rf) and np.array_equal(c.cpu().numpy(), rc)
+    assert k.shape[0] == len(rv) and len(torch.unique(k)) == len(rv)

@@ -190,6 +190,56 @@ class MeshCuller:
         return self.filter_faces(verts, faces, colors, self.inside_hull(verts, planes), require_all=True)
 
 
+def grid_axes(marching_cubes_bound, resolution: float, padding: float = 0.05):
+    """The per-axis coordinates of Mesher.get_grid_uniform (Mesher.py:168-195): n = round((hi - lo + 2 * padding) / resolution)
+    samples of np.linspace(lo - padding, hi + padding, n) in double, rounded to fp32 -- [x, y, z] CPU tensors.
+    marching_cubes_bound: cfg['mapping']['marching_cubes_bound'] * scale, (3,2)."""
+    b = np.asarray(marching_cubes_bound.cpu() if torch.is_tensor(marching_cubes_bound) else marching_cubes_bound, dtype=np.float64)
+    axes = []
+    for a in range(3):
+        lo, hi = b[a, 0], b[a, 1]
+        n = int(torch.tensor((hi - lo + 2 * padding) / resolution, dtype=torch.float64).round().int().item())
+        axes.append(torch.from_numpy(np.linspace(lo - padding, hi + padding, n)).float())
+    return axes
+
+
+def get_mesh(mesh_out_file: Optional[str], meta: ops.FieldMeta, sdf_table, rgb_table, dec, bound, marching_cubes_bound, *,
+             resolution: float = 0.01, level_set: float = 0.0, scale: float = 1.0, color: bool = True, mesh_bound=None,
+             y_range: Optional[Tuple[int, int]] = None, keys: bool = False):
+    """Mesher.get_mesh (Mesher.py:197-276) in one call on the device: get_grid_uniform -> eval_points over the whole grid
+    (usl_sdf_query_grid) -> marching cubes (usl_mc_*) -> vertex colours (the fused field query) -> vertices / scale ->
+    cull_out_bound_mesh against `mesh_bound` (usl_mesh_cull_hull + face rule + compaction) -> PLY.
+
+    mesh_bound: what Mesher.get_bound_from_frames returns (an object with .vertices / .faces, i.e. the trimesh hull), or an
+    (F,4) array of outward planes, or None (no bound culling: the reference's result before Mesher.py:274).
+    y_range = (begin, end): only that y-slab of the grid (multi-GPU: parallel.slab_range; a slab that is not the last one
+    queries one halo row); with keys=True the slab's vertex edge keys are returned as a fourth value for mesh.weld.
+    Returns (verts (V,3) fp32, faces (T,3) int32, colors (V,3) uint8 | None) on the device -- or None when the level set
+    does not cross the volume (the reference prints 'marching_cubes error' and returns) -- and writes mesh_out_file if given."""
+    from .steps import DenseSdfQuery
+    axes = grid_axes(marching_cubes_bound, resolution)
+    dev = sdf_table.device
+    q = DenseSdfQuery(meta, sdf_table.detach(), rgb_table.detach(), [d.detach() for d in dec], [a.to(dev) for a in axes])
+    yb, ye = (0, q.ny) if y_range is None else (int(y_range[0]), int(y_range[1]))
+    yh = min(ye + 1, q.ny)
+    vol = q.run(yb, yh).view(yh - yb, q.nx, q.nz)
+    out = MeshExtractor(axes, level_set).run(vol, yb, ye, halo=yh > ye, keys=True)
+    verts, faces, vkeys = out
+    if verts.shape[0] == 0 or faces.shape[0] == 0:
+        return None
+    cols = vertex_colors(meta, sdf_table, rgb_table, dec, verts, bound) if color else None     # on the un-scaled vertices (Mesher.py:259-267)
+    if scale != 1.0:
+        verts = verts / scale                                                                   # Mesher.py:269
+    if mesh_bound is not None:
+        planes = hull_planes(mesh_bound.vertices, mesh_bound.faces) if hasattr(mesh_bound, "vertices") else np.asarray(mesh_bound, dtype=np.float32)
+        kept = []
+        verts, faces, cols = MeshCuller.filter_faces(verts, faces, cols, MeshCuller.inside_hull(verts, planes), True, vertex_kept=kept)
+        vkeys = vkeys[kept[0].bool()]
+    if mesh_out_file is not None:
+        write_ply(mesh_out_file, verts.cpu().numpy(), faces.cpu().numpy(), cols.cpu().numpy() if cols is not None else None)
+    return (verts, faces, cols, vkeys) if keys else (verts, faces, cols)
+
+
 def weld(parts):
     """Concatenate per-slab meshes [(verts, faces, keys, colors|None), ...] and weld the vertices that neighbouring slabs both
     emitted (the x / z edges of a halo row) by their global edge key.  Host numpy; returns verts, faces, colors."""
