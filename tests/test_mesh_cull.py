@@ -143,13 +143,15 @@ def test_gpu_cull_frames_random_points(eval_rec):
     ref = helpers.cull_host_frames(pts, w2c, depths, cam, tr, eval_rec, 16)
     seen = _gpu_seen(culler, pts, c2ws, depths, eval_rec)
     assert np.array_equal(seen, ref)
-    # accumulation over ranges of frames == one call
+    seen_ref, margin = cull_ref.visibility(pts, torch.from_numpy(c2ws), torch.from_numpy(depths), *cam[2:], tr, eval_rec)
+    diff = seen.astype(bool) != seen_ref
+    assert not (diff & (margin > 1e-4)).any() and diff.sum() <= 1e-4 * len(pts)
+    # accumulation over ranges of frames == one call (the two calls invert their poses in batches of another size, which may
+    # round a matrix differently: agreement is required wherever no comparison is within 1e-4 of a tie)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
     acc = culler.seen_by_frames(t(pts), t(c2ws[:20]), t(depths[:20]), eval_rec)
     acc = culler.seen_by_frames(t(pts), t(c2ws[20:]), t(depths[20:]), eval_rec, seen=acc)
-    assert np.array_equal(acc.cpu().numpy(), ref)
-    seen_ref, margin = cull_ref.visibility(pts, torch.from_numpy(c2ws), torch.from_numpy(depths), *cam[2:], tr, eval_rec)
-    diff = seen.astype(bool) != seen_ref
+    diff = acc.cpu().numpy() != ref
     assert not (diff & (margin > 1e-4)).any() and diff.sum() <= 1e-4 * len(pts)
 
 
