@@ -415,6 +415,14 @@ USL_API int usl_mesh_compact(const float *verts, const uint8_t *colors, int64_t 
                              const uint8_t *keep, const uint8_t *vref, const uint32_t *voff, const uint32_t *foff,
                              float *verts_out, uint8_t *colors_out, int32_t *faces_out, usl_stream_t stream);
 
+/* ---- f3: per-frame metrics of eval_rendering (src/tools/eval_recon.py:278-293) over the renderer's output buffers ----------
+ * acc[0] += sum over the pixels with gt_depth > 0 of sum_c (gt_color - color)^2, acc[1] += sum |gt_depth - depth| over the same
+ * pixels, acc[2] += their number -- in double (the reference's colour is float64 and render_img returns float64 depth).
+ * mse = acc[0] / (3 acc[2]), psnr = -10 log10(mse), depth_l1 = acc[1] / acc[2].  gt_color / color [n,3], gt_depth / depth [n];
+ * acc[3] is accumulated into (the caller zero-fills it; one slot of 3 doubles per frame keeps a sequence on the device). */
+USL_API int usl_render_metrics(const float *gt_color, const float *gt_depth, const float *color, const float *depth, int64_t n,
+                               double *acc, usl_stream_t stream);
+
 /* ---- 8e: multi-GPU exchange steps of the sharded mapping iteration, over peer memory (NVLink / NVSwitch) -----------
  * The reference is single-GPU; these entry points are what its proposed `allreduce_grads` seam becomes.
  * The host layer maps every rank's buffers into every rank's address space (CUDA IPC / symmetric memory: one allocation

@@ -48,6 +48,8 @@ CASES = {
     # src/tools/cull_mesh.py: cull_mesh (frustum + occlusion test against the frames, both eval_rec settings) and
     # cull_out_bound_mesh (convex bound) on a small marching-cubes mesh of the analytic room
     "cull_replica": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, n_frames=7, voxel=0.31),
+    # src/tools/eval_recon.py:235-307 eval_rendering: render_img on every 5th frame, PSNR over the pixels with depth, depth L1
+    "evalr_replica": dict(yaml="configs/Replica/room0.yaml", H=30, W=40, s=1 / 30.0, n_img=11, ray_batch=700),
 }
 
 
@@ -630,6 +632,61 @@ def gen_cull(name, case):
           "inside hull", int(out["inside_hull"].sum()), "hull faces", len(hf))
 
 
+def gen_eval_rendering(name, case):
+    """Runs the unmodified eval_rendering over a short sequence of tiny frames with the reference's own Renderer (LPIPS and
+    MS-SSIM, third-party networks, are stand-ins that return 0).  Records, per evaluated frame, what the metrics are computed
+    from (dataset colour -- float64 as datasets.py:87-91 produces it -- and depth, rendered colour and depth), the argument
+    of its torch.log10 (the frame's mse, full precision), the outputs of its torch.abs (the depth residuals) and the result
+    line it appends to output.txt."""
+    import json
+    import tempfile
+    import src.tools.eval_recon as ER
+    from src.utils.Renderer import Renderer
+    cfg = _load_cfg(case)
+    bound, grids, dec = _build_world(cfg, 90)
+    H, W = case["H"], case["W"]
+    cam = cfg["cam"]
+    n_img = case["n_img"]
+    frames, dirs = _frames(cfg, case, n_img, seed=41)
+    fake = types.SimpleNamespace(bound=bound, device="cpu", H=H, W=W, fx=cam["fx"], fy=cam["fy"], cx=cam["cx"], cy=cam["cy"])
+    renderer = Renderer(cfg, fake, ray_batch_size=case["ray_batch"])
+    reader = [(k, frames[k][0].double(), frames[k][1], frames[k][2], dirs) for k in range(n_img)]
+    torch.manual_seed(43)
+    est = []
+    for _, _, c2w in frames:
+        c = c2w.clone(); c[:3, 3] += 0.005 * torch.randn(3); est.append(c)
+    rendered, mses, residuals = [], [], []
+    orig_render, orig_log10, orig_abs = renderer.render_img, torch.log10, torch.abs
+
+    def render(*a, **k):
+        out = orig_render(*a, **k); rendered.append([o.detach().clone() for o in out]); return out
+
+    def log10(t):
+        mses.append(t.detach().clone()); return orig_log10(t)
+
+    def tabs(t):
+        out = orig_abs(t); residuals.append(out.detach().clone()); return out
+    renderer.render_img = render; torch.log10 = log10; torch.abs = tabs
+    outdir = tempfile.mkdtemp(prefix="usl_evalr_")
+    try:
+        torch.manual_seed(3)
+        ER.eval_rendering(cfg, n_img, reader, est, renderer, ([grids[0]], [grids[1]]), dec, cfg["model"]["truncation"], outdir, "cpu")
+    finally:
+        torch.log10 = orig_log10; torch.abs = orig_abs
+    result = json.loads(open(os.path.join(outdir, "output.txt")).read().strip().splitlines()[0])
+    idxs = list(range(0, n_img, 5))
+    assert len(rendered) == len(idxs) == len(mses)
+    res = [r for r in residuals if r.dim() == 1][-len(idxs):]              # the depth residuals (1-D, after the boolean index)
+    out = {"frames": np.array(idxs), "H_W": np.array([H, W]),
+           "gt_color": np.stack([_np(reader[i][1]) for i in idxs]), "gt_depth": np.stack([_np(reader[i][2]) for i in idxs]),
+           "depth": np.stack([_np(r[0]) for r in rendered]), "color": np.stack([_np(r[1]) for r in rendered]),
+           "mse": np.array([float(m) for m in mses], dtype=np.float64), "mse_dtype": np.array(str(mses[0].dtype)),
+           "depth_l1": np.array([float(r.double().mean()) for r in res], dtype=np.float64),
+           "avg_psnr": np.array(result["avg_psnr"]), "depth_l1_render": np.array(result["depth_l1_render"])}
+    _save(name, out)
+    print(name, "frames", idxs, "mse", out["mse"], "psnr", result["avg_psnr"], "depth_l1", result["depth_l1_render"], out["mse_dtype"])
+
+
 def main():
     _setup_paths()
     torch.set_num_threads(8)
@@ -647,6 +704,8 @@ def main():
             gen_mesh_query(name, case)
         elif name.startswith("cull"):
             gen_cull(name, case)
+        elif name.startswith("evalr"):
+            gen_eval_rendering(name, case)
         else:
             gen_tracking(name, case)
 

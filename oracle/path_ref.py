@@ -582,3 +582,14 @@ def load_bound(bound_yaml, scale=1.0, bound_dividable=0.24):
     bound = torch.from_numpy(np.array(bound_yaml) * scale).float()
     bound[:, 1] = (((bound[:, 1] - bound[:, 0]) / bound_dividable).int() + 1) * bound_dividable + bound[:, 0]
     return bound
+
+
+# ---- eval_rendering's per-frame metrics (src/tools/eval_recon.py:278-293) -----------------------------------------------------
+def render_metrics(gt_color, gt_depth, color, depth):
+    """(mse, psnr, depth_l1) of one rendered frame over the pixels with sensor depth: mse_loss(gt_color[m], color[m]) with the
+    dataset's float64 colour promoting the difference to float64, psnr = -10 log10(mse), depth_l1 = mean |gt_depth[m] - depth[m]|
+    (render_img returns depth as float64)."""
+    m = gt_depth > 0
+    mse = ((gt_color[m].double() - color[m].double()) ** 2).mean()
+    l1 = (gt_depth[m].double() - depth[m].double()).abs().mean()
+    return mse, -10.0 * torch.log10(mse), l1

@@ -1,1 +1,7 @@
 
+
+
+def get_cmap(name):
+    """eval_rendering colours its uncertainty image with a colour map (visualisation only): the stand-in returns zeros (…,4)."""
+    import numpy as np
+    return lambda a: np.zeros(np.asarray(a).shape + (4,))

@@ -107,4 +107,4 @@ def img_draws_by_ray_slot(g):
 
 
 # ---- host harness of the culling kernels' element functions (tests/host_harness) ----
-from host_harness.loader import cull_host, cull_host_compact, cull_host_frames, cull_host_hull  # noqa: E402,F401
+from host_harness.loader import cull_host, cull_host_compact, cull_host_frames, cull_host_hull, metrics_host  # noqa: E402,F401

@@ -10,6 +10,36 @@ import os
 import numpy as np
 
 _CULL_HOST = None
+_METRICS_HOST = None
+
+
+def _build(src_name, hdr_name, out_name):
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    tests = os.path.dirname(here)
+    src = os.path.join(here, src_name)
+    hdr = os.path.join(os.path.dirname(tests), "uni-slam_b200", "csrc", hdr_name)
+    out = os.path.join(tests, "_build", out_name)
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-o", out, src], check=True)
+    return out
+
+
+def metrics_host(gt_color, gt_depth, color, depth):
+    """acc (3,) float64 = [sum of squared colour errors, sum |depth error|, pixel count] over the pixels with gt_depth > 0, from
+    the host build of usl_metrics.cuh (tests/host_harness/metrics_host.cpp)."""
+    global _METRICS_HOST
+    import ctypes
+    if _METRICS_HOST is None:
+        lib = ctypes.CDLL(_build("metrics_host.cpp", "usl_metrics.cuh", "libmetrics_host.so"))
+        lib.metrics_host.restype = None
+        lib.metrics_host.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_void_p]
+        _METRICS_HOST = lib
+    a = [np.ascontiguousarray(x, dtype=np.float32) for x in (gt_color, gt_depth, color, depth)]
+    acc = np.zeros(3, dtype=np.float64)
+    _METRICS_HOST.metrics_host(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, a[1].size, acc.ctypes.data)
+    return acc
 
 
 def cull_host():

@@ -305,3 +305,56 @@ def test_gpu_get_mesh_one_call(tmp_path):
     assert 0 < len(rv) < v0.shape[0]
     assert np.array_equal(v.cpu().numpy(), rv) and np.array_equal(f.cpu().numpy(), rf) and np.array_equal(c.cpu().numpy(), rc)
     assert k.shape[0] == len(rv) and len(torch.unique(k)) == len(rv)
+
+
+# ---- f3: eval_rendering's per-frame metrics (usl_render_metrics, steps.RenderMetrics) -------------------------------------------
+def test_render_metrics_oracle_and_element_function_match_the_reference():
+    """tests/golden/evalr_replica.npz comes from the unmodified eval_rendering (src/tools/eval_recon.py:235-307): the oracle,
+    the kernel's element function (host build) and RenderMetrics.finalize reproduce its per-frame mse and its result line."""
+    from oracle import path_ref
+    P = pkg()
+    g = helpers.load_golden("evalr_replica")
+    accs = []
+    for i in range(len(g["frames"])):
+        t = [torch.from_numpy(g[k][i]) for k in ("gt_color", "gt_depth", "color", "depth")]
+        mse, psnr, l1 = path_ref.render_metrics(*t)
+        assert float(mse) == g["mse"][i] and float(l1) == g["depth_l1"][i]                    # the reference's own float64 values
+        acc = helpers.metrics_host(g["gt_color"][i], g["gt_depth"][i], g["color"][i], g["depth"][i])
+        assert acc[2] == int((g["gt_depth"][i] > 0).sum())
+        assert abs(acc[0] / (3 * acc[2]) / g["mse"][i] - 1) < 1e-12 and abs(acc[1] / acc[2] / g["depth_l1"][i] - 1) < 1e-12
+        accs.append(acc)
+    res = P.RenderMetrics.finalize(torch.from_numpy(np.stack(accs)))
+    assert float(f"{res['avg_psnr']:.4f}") == float(g["avg_psnr"]) and float(f"{res['depth_l1_render']:.4f}") == float(g["depth_l1_render"])
+    assert res["frames"] == 3 and torch.isnan(P.RenderMetrics.finalize(torch.zeros(1, 3, dtype=torch.float64))["psnr"]).all()
+
+
+@pytest.mark.gpu
+def test_gpu_render_metrics():
+    P = pkg()
+    g = helpers.load_golden("evalr_replica")
+    rm = P.RenderMetrics(DEV, max_frames=8)
+    t = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    for i in range(len(g["frames"])):
+        # as eval_rendering receives them: dataset colour float64 (H,W,3), render_img's depth float64 (H,W), colour fp32
+        rm.add(t(g["color"][i]), t(g["depth"][i]), t(g["gt_color"][i]), t(g["gt_depth"][i]))
+    torch.cuda.synchronize()
+    acc = rm.acc[:rm.n].cpu().numpy()
+    for i in range(len(g["frames"])):
+        ref = helpers.metrics_host(g["gt_color"][i], g["gt_depth"][i], g["color"][i], g["depth"][i])
+        assert acc[i, 2] == ref[2] and np.allclose(acc[i, :2], ref[:2], rtol=1e-12, atol=0)   # double sums, another order
+    res = rm.result()
+    assert np.allclose(res["mse"].numpy(), g["mse"], rtol=1e-12)
+    assert float(f"{res['avg_psnr']:.4f}") == float(g["avg_psnr"]) and float(f"{res['depth_l1_render']:.4f}") == float(g["depth_l1_render"])
+    # a full-size frame (more pixels than one grid pass), partly without depth
+    rng = np.random.default_rng(3)
+    n = 680 * 1200
+    gc, c = rng.random((n, 3), dtype=np.float32), rng.random((n, 3), dtype=np.float32)
+    gd = (rng.random(n, dtype=np.float32) * 4).astype(np.float32); gd[rng.random(n) < 0.1] = 0
+    d = (gd + rng.normal(0, 0.05, n)).astype(np.float32)
+    rm2 = P.RenderMetrics(DEV, max_frames=1)
+    rm2.add(t(c), t(d), t(gc), t(gd))
+    ref = helpers.metrics_host(gc, gd, c, d)
+    got = rm2.acc[0].cpu().numpy()
+    assert got[2] == ref[2] and np.allclose(got[:2], ref[:2], rtol=1e-11, atol=0)
+    with pytest.raises(RuntimeError):
+        rm2.add(t(c), t(d), t(gc), t(gd))

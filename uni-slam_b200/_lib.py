@@ -144,6 +144,7 @@ _SIGS = {
     "usl_mc_emit": [POINTER(McArgs), _P],
     "usl_scan_u8": [_P, c_int64, c_int, _P, _P, _P, _P],
     "usl_scan_u8_blocks": [c_int64, POINTER(c_int64)],
+    "usl_render_metrics": [_P, _P, _P, _P, c_int64, _P, _P],
     "usl_mesh_cull_frames": [POINTER(CullFramesArgs), _P],
     "usl_mesh_cull_hull": [_P, c_int64, _P, c_int32, _P, _P],
     "usl_mesh_face_keep": [_P, c_int64, _P, c_int64, c_int32, _P, _P, _P],

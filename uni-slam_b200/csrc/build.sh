@@ -9,7 +9,7 @@ NAME="${USL_LIB_NAME:-libunislam_b200.so}"
 OBJ="$HERE/_obj/${NAME%.so}"
 mkdir -p "$OUT" "$OBJ"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $@"
-SRCS="encode field field_bwd field_tc sampling composite loss adam collective mesh cull"
+SRCS="encode field field_bwd field_tc sampling composite loss adam collective mesh cull metrics"
 pids=()
 for f in $SRCS; do
   nvcc $FLAGS -c "$HERE/$f.cu" -o "$OBJ/$f.o" &

@@ -452,6 +452,48 @@ class RenderImageStep(_Profiled):
         return out
 
 
+class RenderMetrics:
+    """eval_rendering's per-frame metrics (src/tools/eval_recon.py:278-307) over rendered frames where they lie on the device:
+    PSNR over the pixels with sensor depth (mse_loss(gt_color[gt_depth > 0], color[gt_depth > 0]), psnr = -10 log10) and the
+    depth L1 (mean |gt_depth - depth| over the same pixels), one usl_render_metrics launch per frame, sums in double, no host
+    read before result().  MS-SSIM and LPIPS (third-party networks) are not part of it.
+
+    add() takes RenderImageStep.run's outputs (out['color'], out['depth']) or modules.Renderer.render_img's (color, depth):
+    any shape with 3 / 1 trailing channels, fp32 or the float64 render_img returns (widened fp32, cast back exactly); the
+    dataset colour is cast to fp32 (the reference keeps it float64, datasets.py:87-91: a difference below 6e-8 per value)."""
+
+    def __init__(self, device, max_frames: int = 4096):
+        self.acc = torch.zeros((max_frames, 3), device=device, dtype=torch.float64)
+        self.n = 0
+
+    def add(self, color: torch.Tensor, depth: torch.Tensor, gt_color: torch.Tensor, gt_depth: torch.Tensor):
+        if self.n >= self.acc.shape[0]:
+            raise RuntimeError(f"RenderMetrics: sized for {self.acc.shape[0]} frames")
+        n = gt_depth.numel()
+        if depth.numel() != n or color.numel() != 3 * n or gt_color.numel() != 3 * n:
+            raise ValueError("RenderMetrics.add: color / gt_color need 3 values and depth one value per pixel of gt_depth")
+        c, d, gc, gd = [L.f32c(t).reshape(-1) for t in (color, depth, gt_color, gt_depth)]
+        for t, nm in ((c, "color"), (d, "depth"), (gc, "gt_color"), (gd, "gt_depth")):
+            cptr(t, torch.float32, None, nm)
+        call("usl_render_metrics", ptr(gc), ptr(gd), ptr(c), ptr(d), n, ptr(self.acc[self.n]), stream())
+        self.n += 1
+
+    @staticmethod
+    def finalize(acc: torch.Tensor) -> dict:
+        """acc (F,3) float64 rows [sum sq. colour error, sum |depth error|, pixel count] -> the dict eval_rendering writes (its
+        third-party entries aside) + the per-frame values.  A frame without a single pixel of depth gives NaN, as the
+        reference's mean over an empty selection does."""
+        a = acc.detach().to("cpu", torch.float64)
+        mse = a[:, 0] / (3.0 * a[:, 2])
+        psnr = -10.0 * torch.log10(mse)
+        l1 = a[:, 1] / a[:, 2]
+        return {"avg_psnr": float(psnr.mean()) if len(a) else float("nan"), "depth_l1_render": float(l1.mean()) if len(a) else float("nan"),
+                "psnr": psnr, "depth_l1": l1, "mse": mse, "frames": int(len(a))}
+
+    def result(self) -> dict:
+        return self.finalize(self.acc[:self.n])            # the one host read of the sequence
+
+
 class DenseSdfQuery:
     """Mesher.get_grid_uniform + eval_points (SDF channel) over a y-slab of the 1 cm query grid
     (src/utils/Mesher.py:134-195,219-227); points are generated in-kernel from the per-axis coordinates."""
