@@ -485,7 +485,7 @@ def run_ours(args, rank, world, local_rank):
         extra.update(dq)
         extra.update(ri)
     if rank == 0 and world == 1 and not args.no_extras and not args.quick:
-        extra["mesh_cull"] = isolated_legs()
+        extra.update(isolated_legs())                    # keys: render_metrics, mesh_cull (or isolated_legs_error)
 
     if rank == 0:
         cpu_base, parity = None, None
@@ -947,17 +947,18 @@ def bench_render_img(P, cfg, meta, tabs, dec, beta, dev, rank, world, dist=None,
 
 def isolated_legs(timeout_s=240):
     """tools/bench_isolated.py in a child process (own CUDA context, time limit): the mesh-culling kernels (f4,
-    src/tools/cull_mesh.py), first run on a B200 by this very bench; whatever happens in the child only fills this key."""
+    src/tools/cull_mesh.py) and eval_rendering's metrics (f3), first run on a B200 by this very bench; whatever happens in the
+    child only fills its own keys."""
     try:
         r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "bench_isolated.py")], capture_output=True, text=True, timeout=timeout_s)
         for ln in reversed(r.stdout.splitlines()):
             if ln.startswith("ISOLATED_JSON "):
                 return json.loads(ln[len("ISOLATED_JSON "):])
-        return {"error": f"child exited {r.returncode} without a result: {(r.stderr or '').strip()[-300:]}"}
+        return {"isolated_legs_error": f"child exited {r.returncode} without a result: {(r.stderr or '').strip()[-300:]}"}
     except subprocess.TimeoutExpired:
-        return {"error": f"child exceeded {timeout_s} s"}
+        return {"isolated_legs_error": f"child exceeded {timeout_s} s"}
     except Exception as e:                                # noqa: BLE001
-        return {"error": f"{type(e).__name__}: {e}"[:300]}
+        return {"isolated_legs_error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def cpu_baseline_leg(wl, step, tabs, dec, beta, cam_poses, dev):

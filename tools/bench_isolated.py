@@ -2,9 +2,10 @@
 
 Why a child: these kernels were written after the round's GPU budget was spent, so their first execution on a B200 is
 the driver's own bench run.  A fault in them must not be able to take the headline measurement down with it: the child has
-its own CUDA context, a time limit, and whatever it prints (or fails to print) only fills the `mesh_cull` key.
+its own CUDA context, a time limit, and whatever it prints (or fails to print) only fills the `mesh_cull` / `render_metrics` keys.
 
-Leg: mesh culling (src/tools/cull_mesh.py) at Replica size -- a marching-cubes mesh of the synthetic room (1.25 cm grid,
+Leg 1: eval_rendering's per-frame metrics (usl_render_metrics) on a full-resolution frame.
+Leg 2: mesh culling (src/tools/cull_mesh.py) at Replica size -- a marching-cubes mesh of the synthetic room (1.25 cm grid,
 about a million vertices) against 64 full-resolution (1200x680) depth frames of one lap of the trajectory:
 usl_mesh_cull_frames with and without the occlusion test, the convex-bound test, the face rule + compaction; the kernel's
 marks are compared with the host harness (tests/host_harness: the kernels' own element functions compiled with g++) on a
@@ -98,16 +99,52 @@ def leg_mesh_cull(P, dev, n_frames=64, voxel=0.0125, sample=20000):
     return res
 
 
+def leg_render_metrics(P, dev, frames=8):
+    """eval_rendering's per-frame PSNR / depth L1 (usl_render_metrics) on full-resolution frames: synthetic sensor frames
+    against a perturbed copy standing in for the rendering; sums compared with the host harness."""
+    from host_harness import loader
+    syn = P.synthetic
+    cfg = syn.CONFIGS["replica_room0"]
+    seq = syn.SyntheticSequence(cfg, n_frames=800, device=dev)
+    col, dep, _ = seq.frame(0)
+    g = torch.Generator(device=dev).manual_seed(9)
+    ren_c = (col + 0.05 * torch.randn(col.shape, device=dev, generator=g)).clamp(0, 1).contiguous()
+    ren_d = (dep + 0.02 * torch.randn(dep.shape, device=dev, generator=g)).contiguous()
+    rm = P.RenderMetrics(dev, max_frames=frames + 1)
+    rm.add(ren_c, ren_d, col, dep)                                        # warm-up, and the frame that is checked
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(frames):
+        rm.add(ren_c, ren_d, col, dep)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / frames
+    ref = loader.metrics_host(col.cpu().numpy(), dep.cpu().numpy(), ren_c.cpu().numpy(), ren_d.cpu().numpy())
+    got = rm.acc[0].cpu().numpy()
+    r = rm.result()
+    n = dep.numel()
+    return {"pixels": n, "ms_per_frame": ms, "streamed_gbs": n * 32 / (ms * 1e-3) / 1e9, "pixels_with_depth": int(got[2]),
+            "max_rel_diff_vs_host_harness": float(np.max(np.abs(got[:2] - ref[:2]) / np.abs(ref[:2]))), "count_matches": bool(got[2] == ref[2]),
+            "psnr": float(r["psnr"][0]), "depth_l1": float(r["depth_l1"][0])}
+
+
 def main():
     t0 = time.time()
     out = {}
     try:
         P = importlib.import_module("uni-slam_b200")
         torch.cuda.set_device(0)
-        out = leg_mesh_cull(P, "cuda:0")
-        out["seconds"] = time.time() - t0
     except Exception as e:                                    # noqa: BLE001 -- reported, never raised into the parent
-        out = {"error": f"{type(e).__name__}: {e}"[:400]}
+        print("ISOLATED_JSON " + json.dumps({"isolated_legs_error": f"{type(e).__name__}: {e}"[:400]}), flush=True)
+        return
+    for key, leg in (("render_metrics", leg_render_metrics), ("mesh_cull", leg_mesh_cull)):
+        t1 = time.time()
+        try:
+            out[key] = leg(P, "cuda:0")
+            out[key]["seconds"] = time.time() - t1
+        except Exception as e:                                # noqa: BLE001
+            out[key] = {"error": f"{type(e).__name__}: {e}"[:400]}
+    out["isolated_legs_seconds"] = time.time() - t0
     print("ISOLATED_JSON " + json.dumps(out), flush=True)
 
 
