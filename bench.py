@@ -758,7 +758,11 @@ def bench_slam_loop(P, cfg, dev, args):
         return {}
     r = slam.run_slam(cfg, n_frames=n, device=dev, scale_hw=1.0, pregenerate=True)
     H, W = cfg.cam.H, cfg.cam.W
-    return {"slam_workload": f"{cfg.name}: {n} frames {W}x{H}, {cfg.track_iters} tracking iterations/frame x {cfg.track_pixels} rays, mapping every "
+    try:                                                   # the reference's own ATE definition (Horn-aligned, eval_ate.py:202-236,380-445)
+        ate_aligned = slam.ate_rmse_aligned(r.est_c2w, r.gt_c2w)[0]
+    except Exception:                                      # noqa: BLE001 -- a host-side evaluation extra must not cost the line
+        ate_aligned = None
+    return {"slam_ate_rmse_aligned_m": ate_aligned, "slam_workload": f"{cfg.name}: {n} frames {W}x{H}, {cfg.track_iters} tracking iterations/frame x {cfg.track_pixels} rays, mapping every "
                              f"{cfg.map_every} frames x {cfg.map_iters} iterations (eager launches, one process)",
             "slam_frames": n, "slam_frames_per_s": r.frames_per_s, "slam_seconds": r.seconds, "slam_ate_rmse_m": r.ate_rmse,
             "slam_ate_rmse_constant_velocity_prior_m": r.ate_rmse_no_tracking, "slam_tracking_iters": r.tracking_iters,

@@ -200,3 +200,34 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     byname = dict(pairs)
     for cname, fld in last.items():
         assert int(out[f"{cname}.{fld}"]) == getattr(byname[cname], fld).offset, (cname, fld)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_aligned_ate_matches_the_reference_evaluation():
+    """slam.ate_rmse_aligned against the unmodified align() / rmse of src/tools/eval_ate.py on a noisy, rotated trajectory."""
+    import subprocess
+    import json
+    code = r"""
+import sys, os, json
+sys.path[:0] = [os.path.join(%r, "oracle", "shims"), %r, %r]
+os.chdir(%r)
+import numpy, torch
+import src.tools.eval_ate as EA
+rng = numpy.random.default_rng(4)
+n = 57
+gt = numpy.cumsum(rng.normal(0, 0.05, (n, 3)), axis=0)
+a = 0.3
+R = numpy.array([[numpy.cos(a), -numpy.sin(a), 0], [numpy.sin(a), numpy.cos(a), 0], [0, 0, 1.0]])
+est = gt @ R.T + numpy.array([0.4, -0.2, 0.1]) + rng.normal(0, 0.01, (n, 3))
+rot, trans, te = EA.align(numpy.matrix(est.T), numpy.matrix(gt.T))
+rmse = float(numpy.sqrt(numpy.dot(te, te) / len(te)))
+print("RES " + json.dumps({"gt": gt.tolist(), "est": est.tolist(), "rot": numpy.asarray(rot).tolist(), "trans": numpy.asarray(trans).ravel().tolist(), "rmse": rmse, "te": te.tolist()}))
+""" % (REPO, REF, REPO, REF)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout
+    res = json.loads([ln for ln in out.splitlines() if ln.startswith("RES ")][0][4:])
+    slam = importlib.import_module("uni-slam_b200.slam")
+    def c2w(xyz):
+        m = torch.eye(4, dtype=torch.float64).repeat(len(xyz), 1, 1); m[:, :3, 3] = torch.tensor(xyz, dtype=torch.float64); return m
+    rmse, rot, trans, te = slam.ate_rmse_aligned(c2w(res["est"]), c2w(res["gt"]))
+    assert abs(rmse - res["rmse"]) < 1e-12 and np.allclose(rot, res["rot"], atol=1e-12) and np.allclose(trans, res["trans"], atol=1e-12)
+    assert np.allclose(te, res["te"], atol=1e-12) and 0.005 < rmse < 0.03            # the 1 cm noise, not the 0.4 m offset

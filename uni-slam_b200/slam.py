@@ -39,6 +39,27 @@ class SlamResult:
     loss_last_map: float
 
 
+def ate_rmse_aligned(est_c2w: torch.Tensor, gt_c2w: torch.Tensor):
+    """The reference's ATE figure (src/tools/eval_ate.py:380-445, evaluate_ate): the estimated camera centres are aligned to
+    the ground truth by Horn's closed form (rotation + translation, eval_ate.py:202-236: SVD of the centred cross-covariance,
+    reflection fixed through the determinants), and absolute_translational_error.rmse = sqrt(mean |residual|^2) is returned
+    with the rotation, the translation and the per-frame residual norms.  Host numpy in double, like the reference."""
+    import numpy as np
+    e = est_c2w[:, :3, 3].detach().to("cpu", torch.float64).numpy().T          # model (3,n): the trajectory that is moved
+    g = gt_c2w[:, :3, 3].detach().to("cpu", torch.float64).numpy().T           # data  (3,n)
+    em, gm = e.mean(axis=1, keepdims=True), g.mean(axis=1, keepdims=True)
+    w = (e - em) @ (g - gm).T                                                   # sum of outer(model column, data column)
+    u, _, vh = np.linalg.svd(w.T)
+    s = np.eye(3)
+    if np.linalg.det(u) * np.linalg.det(vh) < 0:
+        s[2, 2] = -1.0
+    rot = u @ s @ vh
+    trans = gm - rot @ em
+    err = rot @ e + trans - g
+    te = np.sqrt((err * err).sum(axis=0))
+    return float(np.sqrt(te @ te / len(te))), rot, trans[:, 0], te
+
+
 def run_slam(cfg: syn.SceneCfg = syn.REPLICA_ROOM0, n_frames: int = 40, device="cuda:0", scale_hw: float = 0.5,
              frame_stride: int = 1, track_iters: int = None, map_iters: int = None, map_iters_first: int = 10,
              seed: int = 0, prior_noise_m: float = 0.0, verbose: bool = False, pregenerate: bool = False,
