@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CASES = ["map_replica_k7", "track_scannet", "mesh_replica", "cull_replica", "evalr_replica"]
+CASES = ["map_scannet_k23", "map_replica_k7", "track_scannet", "mesh_replica", "cull_replica", "evalr_replica"]
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (build container only)")
