@@ -23,6 +23,11 @@ timeout 200 python tools/profile_targets.py > $O/targets_plain.log 2>&1 && \
 timeout 500 ncu --set full --clock-control none -k regex:"sdf_query_grid|mc_classify|mc_emit|scan_|field_fwd_kernel|composite_fwd|depth_error" -c 14 -f -o $O/${R}_targets \
     python tools/profile_targets.py > $O/ncu_targets.log 2>&1
 ncu -i $O/${R}_targets.ncu-rep --page raw --csv > $O/${R}_targets_raw.csv 2>/dev/null
+# 4b. the culling and rendering-metrics kernels (tools/bench_isolated.py is also their bench leg)
+timeout 300 python tools/bench_isolated.py > $O/${R}_isolated.json 2>&1 && \
+timeout 500 ncu --set full --clock-control none -k regex:"mesh_cull|mesh_face_keep|mesh_compact|render_metrics" -c 12 -f -o $O/${R}_cull \
+    python tools/bench_isolated.py > $O/ncu_cull.log 2>&1
+ncu -i $O/${R}_cull.ncu-rep --page raw --csv > $O/${R}_cull_raw.csv 2>/dev/null
 timeout 300 python tools/microbench.py > $O/${R}_microbench.json 2> $O/microbench.err
 timeout 300 ncu --metrics gpu__time_duration.sum,lts__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sectors_srcunit_tex_op_red.avg.pct_of_peak_sustained_elapsed,lts__t_sectors_srcunit_tex_op_read.avg.pct_of_peak_sustained_elapsed,dram__throughput.avg.pct_of_peak_sustained_elapsed \
     --clock-control none -k regex:"bench_" --csv --log-file $O/${R}_microbench_ncu.csv python tools/microbench.py > /dev/null 2> $O/microbench_ncu.err
