@@ -231,3 +231,39 @@ print("RES " + json.dumps({"gt": gt.tolist(), "est": est.tolist(), "rot": numpy.
     rmse, rot, trans, te = slam.ate_rmse_aligned(c2w(res["est"]), c2w(res["gt"]))
     assert abs(rmse - res["rmse"]) < 1e-12 and np.allclose(rot, res["rot"], atol=1e-12) and np.allclose(trans, res["trans"], atol=1e-12)
     assert np.allclose(te, res["te"], atol=1e-12) and 0.005 < rmse < 0.03            # the 1 cm noise, not the 0.4 m offset
+
+
+def test_host_side_entry_points_and_argument_errors():
+    """Entry points that compute on the host, and the argument checks of launch wrappers that return BEFORE any CUDA call
+    (status 1 + usl_last_error, status 0 for empty work) -- callable without a GPU."""
+    from ctypes import byref, c_int64
+    L = importlib.import_module("uni-slam_b200._lib")
+    lib = L.load()
+    # slices of the sharded Adam: multiples of 4 floats that cover the buffer
+    for world in (1, 2, 3, 8):
+        for n in (4, 1024, 12913796 // 4 * 4):
+            s = c_int64(0)
+            assert lib.usl_allreduce_adam_slice_floats(world, n, byref(s)) == 0
+            assert s.value % 4 == 0 and s.value * world >= n and (s.value - 4) * world < n
+    assert lib.usl_allreduce_adam_slice_floats(9, 1024, byref(s)) == 1 and b"bad arguments" in lib.usl_last_error()
+    assert lib.usl_allreduce_adam_slice_floats(2, 1023, byref(s)) == 1
+    nb = c_int64(0)
+    assert lib.usl_scan_u8_blocks(0, byref(nb)) == 0 and nb.value == 0
+    assert lib.usl_scan_u8_blocks(1, byref(nb)) == 0 and nb.value == 1
+    assert lib.usl_scan_u8_blocks(-1, byref(nb)) == 1
+    # mesh culling / metrics: empty work is a no-op, missing buffers are refused with a message
+    a = L.CullFramesArgs()
+    assert lib.usl_mesh_cull_frames(None, None) == 1
+    assert lib.usl_mesh_cull_frames(byref(a), None) == 0                       # V = 0, K = 0
+    a.V, a.K, a.H, a.W = 10, 2, 4, 4
+    assert lib.usl_mesh_cull_frames(byref(a), None) == 1 and b"usl_mesh_cull_frames" in lib.usl_last_error()
+    assert lib.usl_mesh_cull_hull(None, 0, None, 3, None, None) == 0
+    assert lib.usl_mesh_cull_hull(None, 5, None, 3, None, None) == 1 and b"usl_mesh_cull_hull" in lib.usl_last_error()
+    assert lib.usl_mesh_face_keep(None, 0, None, 0, 0, None, None, None) == 0
+    assert lib.usl_mesh_face_keep(None, 7, None, 3, 0, None, None, None) == 1
+    assert lib.usl_mesh_compact(None, None, 0, None, 0, None, None, None, None, None, None, None, None) == 0
+    assert lib.usl_mesh_compact(None, None, 4, None, 0, None, None, None, None, None, None, None, None) == 1
+    assert lib.usl_render_metrics(None, None, None, None, 0, None, None) == 0
+    assert lib.usl_render_metrics(None, None, None, None, 9, None, None) == 1 and b"usl_render_metrics" in lib.usl_last_error()
+    with pytest.raises(RuntimeError, match="usl_render_metrics"):
+        L.call("usl_render_metrics", None, None, None, None, 9, None, None)
