@@ -957,7 +957,13 @@ def isolated_legs(timeout_s=240):
         r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "bench_isolated.py")], capture_output=True, text=True, timeout=timeout_s)
         for ln in reversed(r.stdout.splitlines()):
             if ln.startswith("ISOLATED_JSON "):
-                return json.loads(ln[len("ISOLATED_JSON "):])
+                def finite(o):                            # the bench line must stay strict JSON: no NaN / Infinity tokens
+                    if isinstance(o, dict):
+                        return {k: finite(v) for k, v in o.items()}
+                    if isinstance(o, list):
+                        return [finite(v) for v in o]
+                    return None if isinstance(o, float) and (o != o or o in (float("inf"), float("-inf"))) else o
+                return finite(json.loads(ln[len("ISOLATED_JSON "):]))
         return {"isolated_legs_error": f"child exited {r.returncode} without a result: {(r.stderr or '').strip()[-300:]}"}
     except subprocess.TimeoutExpired:
         return {"isolated_legs_error": f"child exceeded {timeout_s} s"}
