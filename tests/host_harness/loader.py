@@ -26,7 +26,7 @@ def _build(src_name, hdr_name, out_name):
     return out
 
 
-def metrics_host(gt_color, gt_depth, color, depth):
+def metrics_host(gt_color, gt_depth, color, depth, nthreads=148 * 4 * 256):
     """acc (3,) float64 = [sum of squared colour errors, sum |depth error|, pixel count] over the pixels with gt_depth > 0, from
     the host build of usl_metrics.cuh (tests/host_harness/metrics_host.cpp)."""
     global _METRICS_HOST
@@ -34,11 +34,11 @@ def metrics_host(gt_color, gt_depth, color, depth):
     if _METRICS_HOST is None:
         lib = ctypes.CDLL(_build("metrics_host.cpp", "usl_metrics.cuh", "libmetrics_host.so"))
         lib.metrics_host.restype = None
-        lib.metrics_host.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_void_p]
+        lib.metrics_host.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
         _METRICS_HOST = lib
     a = [np.ascontiguousarray(x, dtype=np.float32) for x in (gt_color, gt_depth, color, depth)]
     acc = np.zeros(3, dtype=np.float64)
-    _METRICS_HOST.metrics_host(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, a[1].size, acc.ctypes.data)
+    _METRICS_HOST.metrics_host(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data, a[1].size, int(nthreads), acc.ctypes.data)
     return acc
 
 
@@ -61,36 +61,40 @@ def cull_host():
     lib = ctypes.CDLL(out)
     vp, i64, ci, cf = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
     lib.cull_host_frames.restype = None
-    lib.cull_host_frames.argtypes = [vp, i64, vp, vp, ci, ci, ci, cf, cf, cf, cf, cf, ci, ci, vp]
+    lib.cull_host_frames.argtypes = [vp, i64, vp, vp, ci, ci, ci, cf, cf, cf, cf, cf, ci, ci, i64, vp]
     lib.cull_host_hull.restype = None
-    lib.cull_host_hull.argtypes = [vp, i64, vp, ci, vp]
+    lib.cull_host_hull.argtypes = [vp, i64, vp, ci, i64, vp]
     lib.cull_host_compact.restype = None
-    lib.cull_host_compact.argtypes = [vp, vp, i64, vp, i64, vp, ci, vp, vp, vp, vp, vp]
+    lib.cull_host_compact.argtypes = [vp, vp, i64, vp, i64, vp, ci, i64, vp, vp, vp, vp, vp]
     _CULL_HOST = lib
     return lib
 
 
-def cull_host_frames(verts, w2c, depths, cam, truncation, eval_rec, frames_per_cta=16):
-    """seen (V,) uint8 from the host harness; verts (V,3) f32, w2c (K,4,4) f32, depths (K,H,W) f32, cam = (H,W,fx,fy,cx,cy)."""
+NTHREADS = 4736 * 256         # the x extent usl_mesh_cull_frames launches on a 148-SM device when there are more tiles than that
+
+
+def cull_host_frames(verts, w2c, depths, cam, truncation, eval_rec, frames_per_cta=16, nthreads=NTHREADS):
+    """seen (V,) uint8 from the host harness; verts (V,3) f32, w2c (K,4,4) f32, depths (K,H,W) f32, cam = (H,W,fx,fy,cx,cy);
+    nthreads = simulated gridDim.x * blockDim.x."""
     lib = cull_host()
     verts = np.ascontiguousarray(verts, dtype=np.float32); w2c = np.ascontiguousarray(w2c, dtype=np.float32)
     depths = np.ascontiguousarray(depths, dtype=np.float32)
     seen = np.zeros(len(verts), dtype=np.uint8)
     H, W, fx, fy, cx, cy = cam
     lib.cull_host_frames(verts.ctypes.data, len(verts), w2c.ctypes.data, depths.ctypes.data, len(w2c), int(H), int(W), fx, fy, cx, cy,
-                         truncation, int(eval_rec), frames_per_cta, seen.ctypes.data)
+                         truncation, int(eval_rec), frames_per_cta, int(nthreads), seen.ctypes.data)
     return seen
 
 
-def cull_host_hull(verts, planes):
+def cull_host_hull(verts, planes, nthreads=NTHREADS):
     lib = cull_host()
     verts = np.ascontiguousarray(verts, dtype=np.float32); planes = np.ascontiguousarray(planes, dtype=np.float32)
     inside = np.zeros(len(verts), dtype=np.uint8)
-    lib.cull_host_hull(verts.ctypes.data, len(verts), planes.ctypes.data, len(planes), inside.ctypes.data)
+    lib.cull_host_hull(verts.ctypes.data, len(verts), planes.ctypes.data, len(planes), int(nthreads), inside.ctypes.data)
     return inside
 
 
-def cull_host_compact(verts, colors, faces, vmask, require_all):
+def cull_host_compact(verts, colors, faces, vmask, require_all, nthreads=NTHREADS):
     lib = cull_host()
     verts = np.ascontiguousarray(verts, dtype=np.float32); faces = np.ascontiguousarray(faces, dtype=np.int32)
     vmask = np.ascontiguousarray(vmask, dtype=np.uint8)
@@ -99,6 +103,6 @@ def cull_host_compact(verts, colors, faces, vmask, require_all):
     vo = np.zeros_like(verts); fo = np.zeros_like(faces); co = np.zeros_like(colors) if colors is not None else None
     n = np.zeros(2, dtype=np.int64)
     lib.cull_host_compact(verts.ctypes.data, colors.ctypes.data if colors is not None else None, len(verts), faces.ctypes.data, len(faces),
-                          vmask.ctypes.data, int(require_all), keep.ctypes.data, vo.ctypes.data, co.ctypes.data if co is not None else None,
+                          vmask.ctypes.data, int(require_all), int(nthreads), keep.ctypes.data, vo.ctypes.data, co.ctypes.data if co is not None else None,
                           fo.ctypes.data, n.ctypes.data)
     return vo[:n[0]], fo[:n[1]], (co[:n[0]] if co is not None else None), keep

@@ -67,18 +67,20 @@ def test_kernel_element_functions_reproduce_the_reference_masks(tag, eval_rec):
     grouping of the frames (the kernel's early exit / OR accumulation must not change the result)."""
     g, cam, tr = _golden()
     w2c = torch.inverse(torch.from_numpy(g["c2ws"])).numpy()
-    for fpc in (16, 3, 1):
-        seen = helpers.cull_host_frames(g["verts"], w2c, g["depths"], cam, tr, eval_rec, fpc)
-        assert np.array_equal(seen.astype(bool), g["seen_" + tag]), fpc
+    for fpc, nthreads in ((16, 256), (3, 768), (1, 1024), (64, 4736 * 256)):     # grid-stride loops of every length, one group .. one per frame
+        seen = helpers.cull_host_frames(g["verts"], w2c, g["depths"], cam, tr, eval_rec, fpc, nthreads)
+        assert np.array_equal(seen.astype(bool), g["seen_" + tag]), (fpc, nthreads)
     col = (np.arange(len(g["verts"]) * 3) % 251).astype(np.uint8).reshape(-1, 3)
-    v, f, c, keep = helpers.cull_host_compact(g["verts"], col, g["faces"], seen, require_all=0)
-    assert np.array_equal(keep.astype(bool), g["face_keep_" + tag])
-    assert np.array_equal(v, g["culled_verts_" + tag]) and np.array_equal(f, g["culled_faces_" + tag])
+    for nthreads in (256, 2304, 4736 * 256):
+        v, f, c, keep = helpers.cull_host_compact(g["verts"], col, g["faces"], seen, require_all=0, nthreads=nthreads)
+        assert np.array_equal(keep.astype(bool), g["face_keep_" + tag])
+        assert np.array_equal(v, g["culled_verts_" + tag]) and np.array_equal(f, g["culled_faces_" + tag])
     _, _, c_ref, _ = cull_ref.face_filter(g["verts"], g["faces"], seen.astype(bool), False, colors=col)
     assert np.array_equal(c, c_ref)
     planes = pkg().mesh.hull_planes(g["hull_verts"], g["hull_faces"])
-    inside = helpers.cull_host_hull(g["verts"], planes)
-    assert np.array_equal(inside.astype(bool), g["inside_hull"])
+    for nthreads in (256, 1280, 4736 * 256):
+        inside = helpers.cull_host_hull(g["verts"], planes, nthreads)
+        assert np.array_equal(inside.astype(bool), g["inside_hull"])
     v, f, _, _ = helpers.cull_host_compact(g["verts"], None, g["faces"], inside, require_all=1)
     assert np.array_equal(v, g["culled_verts_hull"]) and np.array_equal(f, g["culled_faces_hull"])
 

@@ -3,19 +3,21 @@
 //   usl_mesh_cull_frames   cull_mesh (cull_mesh.py:58-99): a vertex is "seen" when some frame has it inside its frustum, in
 //                          front of the camera and (eval_rec) not behind the sensor depth + truncation.  The reference walks
 //                          the frames on the host: per frame ~20 torch launches over all vertices, a grid_sample, a D2H copy of
-//                          the mask and a numpy AND.  Here: thread = vertex, blockIdx.y = a group of consecutive frames whose
-//                          camera rows sit in shared memory; a vertex leaves at the first frame that sees it, and a vertex
-//                          that an earlier group already marked is skipped at entry, so the work is dominated by the vertices
-//                          no frame sees.  Frame groups are the slow grid dimension: the CTAs in flight work on the same few
-//                          depth frames (16 x 3.3 MB at 1200x680), which therefore stay in L2 while all vertex tiles pass over
-//                          them; with 180 GB of HBM the whole sequence's depth frames (2000 x 3.3 MB = 6.5 GB) stay resident.
+//                          the mask and a numpy AND.  Here: thread = vertex, blockIdx.y = a group of consecutive frames; a vertex
+//                          leaves at the first frame that sees it, and a vertex that an earlier group already marked is skipped
+//                          at entry, so the work is dominated by the vertices no frame sees.  Frame groups are the slow grid
+//                          dimension: the CTAs in flight work on the same few depth frames (16 x 3.3 MB at 1200x680), which
+//                          therefore stay in L2 while all vertex tiles pass over them; with 180 GB of HBM the whole sequence's
+//                          depth frames (2000 x 3.3 MB = 6.5 GB) stay resident.  The camera rows are read at warp-uniform
+//                          addresses (one broadcast transaction per load, L1-resident).
 //   usl_mesh_cull_hull     cull_out_bound_mesh (cull_mesh.py:136-142): vertex inside the closed convex bound = on the inner side
-//                          of every hull plane; planes staged through shared memory, warp-uniform early exit.
+//                          of every hull plane (warp-uniform plane reads, a thread leaves at the first plane it is outside of)
 //   usl_mesh_face_keep     the face rule of either culling (cull_mesh.py:101-102 / :143-144) + the referenced-vertex marks
 //   usl_mesh_compact       update_faces + remove_unreferenced_vertices (order-preserving) from the exclusive scans of the keep
 //                          flags and the vertex marks (usl_scan_u8 of mesh.cu)
 //
-// The per-element arithmetic lives in usl_cull.cuh (shared with the host-side test harness).
+// The kernels are trampolines: what a thread does lives in usl_cull.cuh, which also compiles for the host -- the test harness
+// (tests/host_harness) runs those thread functions over a simulated grid, and the -m gpu tests hold the kernels to it bit for bit.
 #include "usl_device.cuh"
 #include "usl_cull.cuh"
 
@@ -23,98 +25,30 @@ namespace usl {
 
 constexpr int CULL_THREADS = 256;
 constexpr int CULL_MAX_FRAMES_PER_CTA = 64;
-constexpr int CULL_PLANES_PER_TILE = 256;
 
-struct CullFramesArgs {
-    const float *verts;
-    int64_t V;
-    const float *w2c;
-    const float *depths;
-    int K, frames_per_cta;
-    CullCam cam;
-    uint8_t *seen;
-};
+#define USL_CULL_TID ((int64_t)blockIdx.x * CULL_THREADS + threadIdx.x)
+#define USL_CULL_NTHREADS ((int64_t)gridDim.x * CULL_THREADS)
 
 __global__ void __launch_bounds__(CULL_THREADS) mesh_cull_frames_kernel(const __grid_constant__ CullFramesArgs A) {
-    __shared__ float s_w2c[CULL_MAX_FRAMES_PER_CTA * 12];
-    const int k0 = blockIdx.y * A.frames_per_cta;
-    const int nk = min(A.frames_per_cta, A.K - k0);
-    for (int i = threadIdx.x; i < nk * 12; i += CULL_THREADS) s_w2c[i] = A.w2c[(int64_t)(k0 + i / 12) * 16 + (i % 12)];
-    __syncthreads();
-    const int64_t frame_px = (int64_t)A.cam.H * A.cam.W;
-    for (int64_t v = (int64_t)blockIdx.x * CULL_THREADS + threadIdx.x; v < A.V; v += (int64_t)gridDim.x * CULL_THREADS) {
-        if (A.seen[v]) continue;                          // marked by an earlier frame group (or not yet visible: still correct)
-        const float px = A.verts[v * 3], py = A.verts[v * 3 + 1], pz = A.verts[v * 3 + 2];
-        bool s = false;
-        for (int k = 0; k < nk && !s; ++k)
-            s = cull_seen_in_frame(px, py, pz, s_w2c + k * 12, A.depths ? A.depths + (int64_t)(k0 + k) * frame_px : nullptr, A.cam);
-        if (s) A.seen[v] = 1;                             // every writer stores the same value
-    }
+    cull_frames_thread(A, USL_CULL_TID, USL_CULL_NTHREADS, (int)blockIdx.y);
 }
 
 __global__ void __launch_bounds__(CULL_THREADS) mesh_cull_hull_kernel(const float *__restrict__ verts, int64_t V, const float *__restrict__ planes,
                                                                       int F, uint8_t *__restrict__ inside) {
-    __shared__ float s_pl[CULL_PLANES_PER_TILE * 4];
-    const int64_t v = (int64_t)blockIdx.x * CULL_THREADS + threadIdx.x;
-    const bool live = v < V;
-    float px = 0.f, py = 0.f, pz = 0.f;
-    if (live) { px = verts[v * 3]; py = verts[v * 3 + 1]; pz = verts[v * 3 + 2]; }
-    bool in = live;
-    for (int f0 = 0; f0 < F; f0 += CULL_PLANES_PER_TILE) {
-        const int nf = min(CULL_PLANES_PER_TILE, F - f0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < nf * 4; i += CULL_THREADS) s_pl[i] = planes[(int64_t)f0 * 4 + i];
-        __syncthreads();
-        if (__any_sync(0xffffffffu, in)) {                // a warp whose vertices are all outside already has nothing left to test
-            for (int f = 0; f < nf; ++f) in = in && (cull_plane_side(px, py, pz, s_pl + f * 4) <= 0.f);
-        }
-    }
-    if (live) inside[v] = in ? 1 : 0;
+    cull_hull_thread(verts, V, planes, F, inside, USL_CULL_TID, USL_CULL_NTHREADS);
 }
 
 __global__ void __launch_bounds__(CULL_THREADS) mesh_face_keep_kernel(const int32_t *__restrict__ faces, int64_t T, const uint8_t *__restrict__ vmask,
                                                                       int64_t V, int require_all, uint8_t *__restrict__ keep,
                                                                       uint8_t *__restrict__ vref) {
-    for (int64_t t = (int64_t)blockIdx.x * CULL_THREADS + threadIdx.x; t < T; t += (int64_t)gridDim.x * CULL_THREADS) {
-        const int32_t a = faces[t * 3], b = faces[t * 3 + 1], c = faces[t * 3 + 2];
-        bool k = false;
-        if (a >= 0 && a < V && b >= 0 && b < V && c >= 0 && c < V) {      // a face with an index outside the vertex array is dropped
-            k = cull_face_keep(vmask[a], vmask[b], vmask[c], require_all);
-            if (k) { vref[a] = 1; vref[b] = 1; vref[c] = 1; }
-        }
-        keep[t] = k ? 1 : 0;
-    }
+    cull_face_keep_thread(faces, T, vmask, V, require_all, keep, vref, USL_CULL_TID, USL_CULL_NTHREADS);
 }
-
-struct CompactArgs {
-    const float *verts;
-    const uint8_t *colors;
-    int64_t V;
-    const int32_t *faces;
-    int64_t T;
-    const uint8_t *keep, *vref;
-    const uint32_t *voff, *foff;
-    float *verts_out;
-    uint8_t *colors_out;
-    int32_t *faces_out;
-};
 
 __global__ void __launch_bounds__(CULL_THREADS) mesh_compact_kernel(const __grid_constant__ CompactArgs A) {
-    const int64_t stride = (int64_t)gridDim.x * CULL_THREADS;
-    for (int64_t v = (int64_t)blockIdx.x * CULL_THREADS + threadIdx.x; v < A.V; v += stride) {
-        if (!A.vref[v]) continue;
-        const int64_t o = A.voff[v];
-        for (int d = 0; d < 3; ++d) A.verts_out[o * 3 + d] = A.verts[v * 3 + d];
-        if (A.colors && A.colors_out)
-            for (int d = 0; d < 3; ++d) A.colors_out[o * 3 + d] = A.colors[v * 3 + d];
-    }
-    for (int64_t t = (int64_t)blockIdx.x * CULL_THREADS + threadIdx.x; t < A.T; t += stride) {
-        if (!A.keep[t]) continue;
-        const int64_t o = A.foff[t];
-        for (int d = 0; d < 3; ++d) A.faces_out[o * 3 + d] = (int32_t)A.voff[A.faces[t * 3 + d]];
-    }
+    cull_compact_thread(A, USL_CULL_TID, USL_CULL_NTHREADS);
 }
 
+// grid-stride launches: every tile of 256 items, capped at ctas_per_sm CTAs per SM of this device
 static unsigned cull_grid(int64_t n, int ctas_per_sm) {
     int dev = 0, n_sm = 0;
     cudaGetDevice(&dev);
@@ -145,8 +79,8 @@ int usl_mesh_cull_frames(const usl_cull_frames_args_t *a, usl_stream_t stream) {
     A.cam.H = a->H; A.cam.W = a->W; A.cam.fx = a->fx; A.cam.fy = a->fy; A.cam.cx = a->cx; A.cam.cy = a->cy;
     A.cam.truncation = a->truncation; A.cam.eval_rec = a->eval_rec ? 1 : 0;
     A.seen = a->seen;
-    // x extent: every vertex tile, capped at 32 CTAs per SM worth of tiles (grid-stride beyond), so that one frame group's CTAs
-    // drain before the next group's depth frames are pulled into L2
+    // x extent capped at 32 CTAs per SM worth of vertex tiles (grid-stride beyond), so that one frame group's CTAs drain before
+    // the next group's depth frames are pulled into L2
     dim3 grid(cull_grid(a->V, 32), (unsigned)groups);
     mesh_cull_frames_kernel<<<grid, CULL_THREADS, 0, (cudaStream_t)stream>>>(A);
     return check_launch("usl_mesh_cull_frames");
@@ -155,7 +89,7 @@ int usl_mesh_cull_frames(const usl_cull_frames_args_t *a, usl_stream_t stream) {
 int usl_mesh_cull_hull(const float *verts, int64_t V, const float *planes, int32_t F, uint8_t *inside, usl_stream_t stream) {
     if (V <= 0) return 0;
     if (!verts || !inside || F < 0 || (F > 0 && !planes)) { set_error("usl_mesh_cull_hull: bad arguments"); return 1; }
-    mesh_cull_hull_kernel<<<(unsigned)((V + CULL_THREADS - 1) / CULL_THREADS), CULL_THREADS, 0, (cudaStream_t)stream>>>(verts, V, planes, F, inside);
+    mesh_cull_hull_kernel<<<cull_grid(V, 32), CULL_THREADS, 0, (cudaStream_t)stream>>>(verts, V, planes, F, inside);
     return check_launch("usl_mesh_cull_hull");
 }
 

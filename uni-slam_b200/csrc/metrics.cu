@@ -14,11 +14,8 @@ constexpr int METRICS_THREADS = 256;
 __global__ void __launch_bounds__(METRICS_THREADS) render_metrics_kernel(const float *__restrict__ gt_color, const float *__restrict__ gt_depth,
                                                                          const float *__restrict__ color, const float *__restrict__ depth,
                                                                          int64_t n, double *__restrict__ acc) {
-    double se = 0.0, ad = 0.0, cnt = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * METRICS_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * METRICS_THREADS) {
-        double s, a;
-        if (metrics_pixel(gt_color + i * 3, color + i * 3, gt_depth[i], depth[i], s, a)) { se += s; ad += a; cnt += 1.0; }
-    }
+    double se, ad, cnt;
+    metrics_thread(gt_color, gt_depth, color, depth, n, (int64_t)blockIdx.x * METRICS_THREADS + threadIdx.x, (int64_t)gridDim.x * METRICS_THREADS, se, ad, cnt);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         se += __shfl_down_sync(0xffffffffu, se, o);

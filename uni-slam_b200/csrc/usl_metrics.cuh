@@ -1,4 +1,5 @@
-// Element function of usl_render_metrics (metrics.cu): eval_rendering's per-pixel terms (src/tools/eval_recon.py:278-293).
+// Element and thread functions of usl_render_metrics (metrics.cu): eval_rendering's per-pixel terms (src/tools/eval_recon.py:278-293)
+// and a thread's grid-stride partial sums.
 // Like usl_cull.cuh it also compiles with plain g++ for the host-side test harness (tests/host_harness); the library never
 // runs it on the CPU.
 #pragma once
@@ -26,6 +27,16 @@ USLM_HD bool metrics_pixel(const float *gt_color, const float *color, float gt_d
     se = s;
     ad = fabs((double)gt_depth - (double)depth);
     return true;
+}
+
+// One thread of render_metrics_kernel: its grid-stride partial sums (thread `tid` of `nthreads`).
+USLM_HD void metrics_thread(const float *gt_color, const float *gt_depth, const float *color, const float *depth, int64_t n, int64_t tid,
+                            int64_t nthreads, double &se, double &ad, double &cnt) {
+    se = 0.0; ad = 0.0; cnt = 0.0;
+    for (int64_t i = tid; i < n; i += nthreads) {
+        double s, a;
+        if (metrics_pixel(gt_color + i * 3, color + i * 3, gt_depth[i], depth[i], s, a)) { se += s; ad += a; cnt += 1.0; }
+    }
 }
 
 }  // namespace usl
