@@ -106,5 +106,5 @@ def img_draws_by_ray_slot(g):
     return t_rand, t_uni, u_pdf
 
 
-# ---- host harness of the culling kernels' element functions (tests/host_harness) ----
+# ---- host harness of the culling kernels' thread functions (tests/host_harness) ----
 from host_harness.loader import cull_host, cull_host_compact, cull_host_frames, cull_host_hull, metrics_host  # noqa: E402,F401

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE, NOT PRODUCT CODE: loader of tests/host_harness/cull_host.cpp.
 
-The harness compiles uni-slam_b200/csrc/usl_cull.cuh -- the element functions the CUDA kernels of cull.cu inline -- for the
+The harness compiles uni-slam_b200/csrc/usl_cull.cuh -- the thread functions the CUDA kernels of cull.cu inline -- for the
 host with g++ (-ffp-contract=off), so that their arithmetic can be checked without a GPU and the kernels can then be held to
 it bit for bit.  Imported by tests/ (through helpers.py) and by bench.py's isolated culling leg as the checker; it imports
 nothing from oracle/ and nothing from the product package, and the product never loads it.

@@ -3,7 +3,7 @@
 Chain of evidence:
   unmodified cull_mesh / cull_out_bound_mesh (run by oracle/gen_golden.py) -> tests/golden/cull_replica.npz
   oracle/cull_ref.py == golden                                                    (CPU)
-  element functions of the kernels (csrc/usl_cull.cuh, compiled for the host by tests/host_harness) == golden, and == oracle on
+  thread functions of the kernels (csrc/usl_cull.cuh, compiled for the host by tests/host_harness) == golden, and == oracle on
       200 k random points wherever the decision is not within rounding of a tie  (CPU)
   CUDA kernels == host harness bit for bit, == golden, end-to-end culled meshes   (-m gpu)
 """
@@ -312,7 +312,7 @@ def test_gpu_get_mesh_one_call(tmp_path):
 # ---- f3: eval_rendering's per-frame metrics (usl_render_metrics, steps.RenderMetrics) -------------------------------------------
 def test_render_metrics_oracle_and_element_function_match_the_reference():
     """tests/golden/evalr_replica.npz comes from the unmodified eval_rendering (src/tools/eval_recon.py:235-307): the oracle,
-    the kernel's element function (host build) and RenderMetrics.finalize reproduce its per-frame mse and its result line."""
+    the kernel's thread function (host build) and RenderMetrics.finalize reproduce its per-frame mse and its result line."""
     from oracle import path_ref
     P = pkg()
     g = helpers.load_golden("evalr_replica")

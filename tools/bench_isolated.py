@@ -8,7 +8,7 @@ Leg 1: eval_rendering's per-frame metrics (usl_render_metrics) on a full-resolut
 Leg 2: mesh culling (src/tools/cull_mesh.py) at Replica size -- a marching-cubes mesh of the synthetic room (1.25 cm grid,
 about a million vertices) against 64 full-resolution (1200x680) depth frames of one lap of the trajectory:
 usl_mesh_cull_frames with and without the occlusion test, the convex-bound test, the face rule + compaction; the kernel's
-marks are compared with the host harness (tests/host_harness: the kernels' own element functions compiled with g++) on a
+marks are compared with the host harness (tests/host_harness: the kernels' own thread functions compiled with g++) on a
 20 000-vertex sample.  Timing: CUDA events on the launching stream, after a warm-up call.
 """
 import importlib
