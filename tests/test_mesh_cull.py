@@ -360,3 +360,28 @@ def test_gpu_render_metrics():
     assert got[2] == ref[2] and np.allclose(got[:2], ref[:2], rtol=1e-11, atol=0)
     with pytest.raises(RuntimeError):
         rm2.add(t(c), t(d), t(gc), t(gd))
+
+
+def test_cull_thread_functions_on_degenerate_vertices_and_empty_inputs():
+    """Vertices where the projection degenerates (camera centre, z = 0 plane, NaN / inf coordinates, far away) and empty
+    meshes / frame lists: the kernels' thread functions decide like the oracle (torch semantics: comparisons with NaN are false)."""
+    g, cam, tr = _golden()
+    c2w = g["c2ws"][:2]
+    ctr = c2w[0][:3, 3]
+    fwd = -c2w[0][:3, 2]                                   # the camera looks along -z of its frame
+    special = np.stack([ctr, ctr + 1e-5 * fwd, ctr - 1e-5 * fwd, ctr + 1.0 * fwd, ctr - 1.0 * fwd, ctr + 1e6 * fwd,
+                        np.array([np.nan, 0, 0]), np.array([np.inf, 0, 0]), np.array([0, -np.inf, 0]), np.zeros(3)]).astype(np.float32)
+    w2c = torch.inverse(torch.from_numpy(c2w)).numpy()
+    for eval_rec in (True, False):
+        ref, _ = cull_ref.visibility(special, torch.from_numpy(c2w), torch.from_numpy(g["depths"][:2]), *cam[2:], tr, eval_rec)
+        got = helpers.cull_host_frames(special, w2c, g["depths"][:2], cam, tr, eval_rec, 16, 256)
+        assert np.array_equal(got.astype(bool), ref), (eval_rec, got, ref)
+        assert not got[6:9].any() and not got[0]            # NaN / inf vertices and the camera centre are never seen
+    # on the optical axis one metre ahead: inside the frustum, seen without the occlusion test
+    assert helpers.cull_host_frames(special[3:4], w2c, g["depths"][:2], cam, tr, False, 16, 256)[0] == 1
+    # empty vertex list / no frames / no planes / no faces
+    assert helpers.cull_host_frames(np.zeros((0, 3), np.float32), w2c, g["depths"][:2], cam, tr, True, 16, 256).shape == (0,)
+    assert not helpers.cull_host_frames(special, w2c[:0], g["depths"][:0], cam, tr, True, 16, 256).any()
+    assert helpers.cull_host_hull(special[:6], np.zeros((0, 4), np.float32), 256).all()          # no plane: everything is inside
+    nanv = helpers.cull_host_hull(special[6:9], np.array([[1, 0, 0, -1.0]], np.float32), 256)
+    assert not nanv[0]                                                                          # NaN is outside (side <= 0 is false)
