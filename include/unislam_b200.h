@@ -400,11 +400,11 @@ typedef struct usl_cull_frames_args {
     uint8_t *seen;                    /* [V] in/out */
 } usl_cull_frames_args_t;
 USL_API int usl_mesh_cull_frames(const usl_cull_frames_args_t *a, usl_stream_t stream);
-/* cull_out_bound_mesh's mesh_bound.contains(vertices) (cull_mesh.py:136-142) for a closed CONVEX bound (the reference's bound is
+/* cull_out_bound_mesh's mesh_bound.contains(vertices) (cull_mesh.py:137-143) for a closed CONVEX bound (the reference's bound is
  * the convex hull Mesher.get_bound_from_frames returns): inside[v] = all_f (planes[f,0:3] . p + planes[f,3] <= 0); planes[F,4]
  * outward, on the device. */
 USL_API int usl_mesh_cull_hull(const float *verts, int64_t V, const float *planes, int32_t F, uint8_t *inside, usl_stream_t stream);
-/* The face rule + trimesh's update_faces / remove_unreferenced_vertices (cull_mesh.py:101-104, 143-146), order-preserving:
+/* The face rule + trimesh's update_faces / remove_unreferenced_vertices (cull_mesh.py:100-103, 144-146), order-preserving:
  *   usl_mesh_face_keep: keep[t] = any (require_all = 0, cull_mesh: vmask = seen) / all (require_all = 1, bound: vmask = inside) of
  *                       the face's three vertex flags; vref[v] = 1 for every vertex of a kept face (caller zero-fills vref)
  *   usl_scan_u8(keep) -> foff, T';  usl_scan_u8(vref) -> voff, V'   (popcount = 0)
@@ -415,7 +415,7 @@ USL_API int usl_mesh_compact(const float *verts, const uint8_t *colors, int64_t 
                              const uint8_t *keep, const uint8_t *vref, const uint32_t *voff, const uint32_t *foff,
                              float *verts_out, uint8_t *colors_out, int32_t *faces_out, usl_stream_t stream);
 
-/* ---- f3: per-frame metrics of eval_rendering (src/tools/eval_recon.py:278-293) over the renderer's output buffers ----------
+/* ---- f3: per-frame metrics of eval_rendering (src/tools/eval_recon.py:276-286) over the renderer's output buffers ----------
  * acc[0] += sum over the pixels with gt_depth > 0 of sum_c (gt_color - color)^2, acc[1] += sum |gt_depth - depth| over the same
  * pixels, acc[2] += their number -- in double (the reference's colour is float64 and render_img returns float64 depth).
  * mse = acc[0] / (3 acc[2]), psnr = -10 log10(mse), depth_l1 = acc[1] / acc[2].  gt_color / color [n,3], gt_depth / depth [n];

@@ -6,9 +6,9 @@ CPU restatement of the mesh culling the reference applies after marching cubes (
                       pinhole matrix (x flipped, z + 1e-5), sample the sensor depth bilinearly (F.grid_sample, align_corners,
                       zero padding, on the reference's u/W, v/H normalisation), and mark the vertex seen when it lies in the
                       frustum in front of the camera (and, with eval_rec, not further than depth + truncation).
-* ``face_filter``     cull_mesh.py:101-104 / :143-146: the faces trimesh's update_faces keeps and the vertex compaction of
+* ``face_filter``     cull_mesh.py:100-103 / :144-146: the faces trimesh's update_faces keeps and the vertex compaction of
                       remove_unreferenced_vertices (order-preserving).
-* ``hull_planes`` / ``inside_hull``  the point-in-convex-hull test behind ``mesh_bound.contains`` (cull_mesh.py:136-142).
+* ``hull_planes`` / ``inside_hull``  the point-in-convex-hull test behind ``mesh_bound.contains`` (cull_mesh.py:137-143).
                       trimesh is absent from this image: for a closed convex hull its ray test equals the half-space test
                       up to points ON the hull (parity unpinned for those).
 
@@ -69,7 +69,7 @@ def visibility(verts, c2ws, depths, fx, fy, cx, cy, truncation, eval_rec, edge=0
 
 
 def face_filter(verts, faces, vmask, require_all, colors=None):
-    """update_faces(keep) + remove_unreferenced_vertices (cull_mesh.py:101-104, 143-146).
+    """update_faces(keep) + remove_unreferenced_vertices (cull_mesh.py:100-103, 144-146).
     require_all=False: keep a face when ANY of its vertices has vmask (cull_mesh: drop faces whose three vertices are all
     unseen); require_all=True: keep when ALL have it (cull_out_bound_mesh).  Order-preserving.  Returns verts, faces, colors, keep."""
     faces = np.asarray(faces)

@@ -584,7 +584,7 @@ def load_bound(bound_yaml, scale=1.0, bound_dividable=0.24):
     return bound
 
 
-# ---- eval_rendering's per-frame metrics (src/tools/eval_recon.py:278-293) -----------------------------------------------------
+# ---- eval_rendering's per-frame metrics (src/tools/eval_recon.py:276-286) -----------------------------------------------------
 def render_metrics(gt_color, gt_depth, color, depth):
     """(mse, psnr, depth_l1) of one rendered frame over the pixels with sensor depth: mse_loss(gt_color[m], color[m]) with the
     dataset's float64 colour promoting the difference to float64, psnr = -10 log10(mse), depth_l1 = mean |gt_depth[m] - depth[m]|

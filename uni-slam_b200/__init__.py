@@ -10,7 +10,7 @@ Public surface (mirrors the reference's operator API for the path, SURVEY.md sec
   MappingStep, TrackingStep fused per-iteration drivers            (B5, B6 + a-3 .. a-10)
   DenseSdfQuery             dense SDF query for meshing            (a-11)
   RenderImageStep           forward-only whole-frame renderer      (f3, Renderer.render_img)
-  RenderMetrics             eval_rendering's per-frame PSNR / depth L1 on the device (f3, tools/eval_recon.py:278-307)
+  RenderMetrics             eval_rendering's per-frame PSNR / depth L1 on the device (f3, tools/eval_recon.py:276-299)
   FusedAdam                 one-launch torch.optim.Adam equivalent (a-12 / f1)
   KeyframeStore             device-resident keyframe subsets + window views (f2, Mapper.py:315-356,528-541)
   mesh                      marching cubes on the device-resident volume, vertex colours, frame / bound culling, PLY

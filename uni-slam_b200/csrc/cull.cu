@@ -10,9 +10,9 @@
 //                          therefore stay in L2 while all vertex tiles pass over them; with 180 GB of HBM the whole sequence's
 //                          depth frames (2000 x 3.3 MB = 6.5 GB) stay resident.  The camera rows are read at warp-uniform
 //                          addresses (one broadcast transaction per load, L1-resident).
-//   usl_mesh_cull_hull     cull_out_bound_mesh (cull_mesh.py:136-142): vertex inside the closed convex bound = on the inner side
+//   usl_mesh_cull_hull     cull_out_bound_mesh (cull_mesh.py:137-143): vertex inside the closed convex bound = on the inner side
 //                          of every hull plane (warp-uniform plane reads, a thread leaves at the first plane it is outside of)
-//   usl_mesh_face_keep     the face rule of either culling (cull_mesh.py:101-102 / :143-144) + the referenced-vertex marks
+//   usl_mesh_face_keep     the face rule of either culling (cull_mesh.py:100-101 / :144-145) + the referenced-vertex marks
 //   usl_mesh_compact       update_faces + remove_unreferenced_vertices (order-preserving) from the exclusive scans of the keep
 //                          flags and the vertex marks (usl_scan_u8 of mesh.cu)
 //

@@ -107,7 +107,7 @@ USL_HD void cull_frames_thread(const CullFramesArgs &A, int64_t tid, int64_t nth
     }
 }
 
-// One thread of mesh_cull_hull_kernel.  mesh_bound.contains for a closed convex hull (cull_mesh.py:136-142): inside = on the
+// One thread of mesh_cull_hull_kernel.  mesh_bound.contains for a closed convex hull (cull_mesh.py:137-143): inside = on the
 // inner side (n . p + d <= 0) of every outward plane; planes[F,4] are read at warp-uniform addresses.
 USL_HD void cull_hull_thread(const float *verts, int64_t V, const float *planes, int F, uint8_t *inside, int64_t tid, int64_t nthreads) {
     for (int64_t v = tid; v < V; v += nthreads) {
@@ -122,8 +122,8 @@ USL_HD void cull_hull_thread(const float *verts, int64_t V, const float *planes,
     }
 }
 
-// One thread of mesh_face_keep_kernel.  cull_mesh.py:101-102 (require_all = 0: a face goes when all three vertices are unseen,
-// i.e. stays when any is seen) and :143-144 (require_all = 1: a face stays when all three vertices are inside the bound);
+// One thread of mesh_face_keep_kernel.  cull_mesh.py:100-101 (require_all = 0: a face goes when all three vertices are unseen,
+// i.e. stays when any is seen) and :144-145 (require_all = 1: a face stays when all three vertices are inside the bound);
 // the vertices of a kept face are marked referenced.  A face with an index outside the vertex array is dropped.
 USL_HD void cull_face_keep_thread(const int32_t *faces, int64_t T, const uint8_t *vmask, int64_t V, int require_all, uint8_t *keep,
                                   uint8_t *vref, int64_t tid, int64_t nthreads) {

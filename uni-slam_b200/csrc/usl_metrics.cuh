@@ -1,4 +1,4 @@
-// Element and thread functions of usl_render_metrics (metrics.cu): eval_rendering's per-pixel terms (src/tools/eval_recon.py:278-293)
+// Element and thread functions of usl_render_metrics (metrics.cu): eval_rendering's per-pixel terms (src/tools/eval_recon.py:276-286)
 // and a thread's grid-stride partial sums.
 // Like usl_cull.cuh it also compiles with plain g++ for the host-side test harness (tests/host_harness); the library never
 // runs it on the CPU.

@@ -181,12 +181,12 @@ class MeshCuller:
         return verts_out, faces_out, colors_out
 
     def cull_by_frames(self, verts, faces, colors, c2ws, depths, eval_rec: bool):
-        """cull_mesh: faces whose three vertices are all unseen go (cull_mesh.py:101-103)."""
+        """cull_mesh: faces whose three vertices are all unseen go (cull_mesh.py:100-102)."""
         seen = self.seen_by_frames(verts, c2ws, depths, eval_rec)
         return self.filter_faces(verts, faces, colors, seen, require_all=False)
 
     def cull_by_hull(self, verts, faces, colors, planes):
-        """cull_out_bound_mesh: faces with all three vertices inside the bound stay (cull_mesh.py:143-146)."""
+        """cull_out_bound_mesh: faces with all three vertices inside the bound stay (cull_mesh.py:144-146)."""
         return self.filter_faces(verts, faces, colors, self.inside_hull(verts, planes), require_all=True)
 
 

@@ -453,7 +453,7 @@ class RenderImageStep(_Profiled):
 
 
 class RenderMetrics:
-    """eval_rendering's per-frame metrics (src/tools/eval_recon.py:278-307) over rendered frames where they lie on the device:
+    """eval_rendering's per-frame metrics (src/tools/eval_recon.py:276-299) over rendered frames where they lie on the device:
     PSNR over the pixels with sensor depth (mse_loss(gt_color[gt_depth > 0], color[gt_depth > 0]), psnr = -10 log10) and the
     depth L1 (mean |gt_depth - depth| over the same pixels), one usl_render_metrics launch per frame, sums in double, no host
     read before result().  MS-SSIM and LPIPS (third-party networks) are not part of it.
