@@ -229,7 +229,7 @@ def get_mesh(mesh_out_file: Optional[str], meta: ops.FieldMeta, sdf_table, rgb_t
         return None
     cols = vertex_colors(meta, sdf_table, rgb_table, dec, verts, bound) if color else None     # on the un-scaled vertices (Mesher.py:259-267)
     if scale != 1.0:
-        verts = verts / scale                                                                   # Mesher.py:269
+        verts = verts / scale                                                                   # Mesher.py:271
     if mesh_bound is not None:
         planes = hull_planes(mesh_bound.vertices, mesh_bound.faces) if hasattr(mesh_bound, "vertices") else np.asarray(mesh_bound, dtype=np.float32)
         kept = []
@@ -264,7 +264,7 @@ def cull_by_bound(verts: np.ndarray, faces: np.ndarray, colors, lo, hi):
 
 
 def write_ply(path: str, verts: np.ndarray, faces: np.ndarray, colors: Optional[np.ndarray] = None, scale: float = 1.0):
-    """Binary little-endian PLY as trimesh.Trimesh(vertices / scale, faces, vertex_colors).export writes it (Mesher.py:269-276)."""
+    """Binary little-endian PLY as trimesh.Trimesh(vertices / scale, faces, vertex_colors).export writes it (Mesher.py:271-276)."""
     v = (np.asarray(verts, dtype=np.float64) / scale).astype("<f4")
     f = np.asarray(faces, dtype="<i4")
     hdr = ["ply", "format binary_little_endian 1.0", f"element vertex {len(v)}", "property float x", "property float y", "property float z"]
