@@ -1,0 +1,103 @@
+"""CPU, build container only: the oracle's building blocks against the UNMODIFIED reference functions called directly on
+adversarial inputs -- the corners the tiny golden scenes may not reach (unnormalised pdf with
+u beyond cdf[-1], flat cdf segments, empty loss masks -> NaN, un-normalised / negative-real quaternions, strict
+inequalities on mask thresholds).  Runs in a subprocess with oracle/shims + the reference tree first on sys.path; skipped
+where /root/reference is absent (the GPU box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+CODE = r'''
+import os, sys, types
+sys.path[:0] = [os.path.join(%(repo)r, "oracle", "shims"), %(ref)r, %(repo)r]
+os.chdir(%(ref)r)
+import numpy as np, torch
+import src.common as C
+from src.Mapper import Mapper
+from src.utils.Renderer import Renderer
+from oracle import path_ref as O
+
+def same(a, b, what):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    assert a.shape == b.shape and a.dtype == b.dtype, (what, a.shape, b.shape, a.dtype, b.dtype)
+    assert torch.equal(torch.nan_to_num(a, nan=12345.0), torch.nan_to_num(b, nan=12345.0)) and torch.equal(torch.isnan(a), torch.isnan(b)), what
+
+g = torch.Generator().manual_seed(0)
+# ---- sample_pdf (common.py:49-85): the draw is torch.rand inside the reference -> feed the same u through a patched torch.rand
+R, nb, ns = 64, 32, 8
+bins = torch.sort(torch.rand(R, nb + 1, generator=g) * 3, -1)[0]
+w = torch.rand(R, nb, generator=g)
+w[3] = 0                                    # a ray whose weights are all zero: every cdf step below 1e-5 -> denom 1
+w[5, 10:20] = 0                             # a flat stretch inside the cdf
+w[7] *= 1e-7                                # total mass far below 1: every u lands beyond cdf[-1]
+w[9] *= 40                                  # total mass far above 1: every u lands in the first bins
+u = torch.rand(R, ns, generator=g)
+u[11, 0] = 0.0
+u[12] = 0.999999
+orig = torch.rand
+torch.rand = lambda *a, **k: u.clone()
+try:
+    ref = C.sample_pdf(bins, w, ns, det=False, device="cpu")
+finally:
+    torch.rand = orig
+got, inds = O.sample_pdf(bins, w, u)
+same(got, ref, "sample_pdf")
+assert inds.dtype == torch.int64 and int(inds.max()) <= nb + 1
+
+# ---- perturbation / sdf2alpha (Renderer.py:42-57,154-158)
+ren = object.__new__(Renderer)
+z = torch.sort(torch.rand(17, 40, generator=g) * 4, -1)[0]
+t = torch.rand(17, 40, generator=g)
+torch.rand = lambda *a, **k: t.clone()
+try:
+    ref = ren.perturbation(z)
+finally:
+    torch.rand = orig
+same(O.perturb(z, t), ref, "perturbation")
+sdf = torch.cat([torch.linspace(-1, 1, 101), torch.tensor([-40.0, 40.0, 0.0, float("nan")])])
+for beta in (10.0, 0.5, 37.0):
+    same(O.sdf2alpha(sdf, torch.tensor(beta)), ren.sdf2alpha(sdf, torch.tensor(beta)), "sdf2alpha")
+
+# ---- sdf_losses (Mapper.py:141-175): thresholds hit exactly, empty masks -> NaN
+m = object.__new__(Mapper)
+tr = 0.06
+m.truncation = tr; m.w_sdf_fs, m.w_sdf_center, m.w_sdf_tail = 5.0, 200.0, 10.0
+gt = torch.tensor([1.0, 2.0, 0.5, 3.0])
+zz = torch.stack([gt[0] + torch.tensor([-tr, -0.4 * tr, 0.0, 0.4 * tr, tr, 2 * tr]),          # samples ON every threshold
+                  gt[1] + torch.linspace(-0.2, 0.2, 6), gt[2] + torch.linspace(-0.02, 0.02, 6), gt[3] + torch.linspace(0.5, 1.0, 6)])
+ss = torch.tanh((gt[:, None] - zz) * 7)
+same(O.sdf_losses(ss, zz, gt, tr, O.MAP_WEIGHTS), m.sdf_losses(ss, zz, gt), "sdf_losses")
+only_back = gt[3:4, None] + torch.linspace(0.5, 1.0, 6)[None]                                 # nothing in front / centre / tail
+ref = m.sdf_losses(torch.zeros(1, 6), only_back, gt[3:4])
+assert torch.isnan(ref)
+same(O.sdf_losses(torch.zeros(1, 6), only_back, gt[3:4], tr, O.MAP_WEIGHTS), ref, "sdf_losses on empty masks")
+same(O.sdf_losses(ss[:0], zz[:0], gt[:0], tr, O.MAP_WEIGHTS), m.sdf_losses(ss[:0], zz[:0], gt[:0]), "sdf_losses on no rays")
+
+# ---- pose helpers (common.py:182-208 over pytorch3d): un-normalised, negative-real and axis-aligned quaternions
+q = torch.randn(40, 4, generator=g)
+q[0] = torch.tensor([1.0, 0, 0, 0]); q[1] = torch.tensor([-2.0, 0, 0, 0]); q[2] = torch.tensor([0.0, 3, 0, 0]); q[3] = torch.tensor([0.0, 0, 0, -1])
+q[4] = torch.tensor([1e-3, 1, 1, 1])
+poses = torch.cat([q, torch.randn(40, 3, generator=g)], -1)
+Mref = C.cam_pose_to_matrix(poses)
+same(O.cam_pose_to_matrix(poses), Mref, "cam_pose_to_matrix")
+same(O.matrix_to_cam_pose(Mref), C.matrix_to_cam_pose(Mref), "matrix_to_cam_pose")
+
+# ---- rays (common.py:35-46, 210-228) and the [-1,1] normalisation (common.py:231-245)
+H, W, fx, fy, cx, cy = 7, 9, 5.5, 6.5, 4.2, 3.1
+same(O.camera_dirs(H, W, fx, fy, cx, cy), C.get_camera_rays(H, W, fx, fy, cx, cy), "get_camera_rays")
+ro, rd = C.get_rays(H, W, fx, fy, cx, cy, Mref[6], "cpu")
+o2, d2 = O.full_image_rays(H, W, fx, fy, cx, cy, Mref[6])
+same(o2.reshape(ro.shape), ro, "get_rays origins"); same(d2.reshape(rd.shape), rd, "get_rays directions")
+print("ok")
+''' % dict(repo=REPO, ref=REF)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src")), reason="reference tree only exists in the build container")
+def test_oracle_building_blocks_equal_the_unmodified_reference_on_adversarial_inputs():
+    out = subprocess.run([sys.executable, "-c", CODE], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), (out.stdout[-500:], out.stderr[-3000:])
