@@ -93,6 +93,24 @@ same(O.camera_dirs(H, W, fx, fy, cx, cy), C.get_camera_rays(H, W, fx, fy, cx, cy
 ro, rd = C.get_rays(H, W, fx, fy, cx, cy, Mref[6], "cpu")
 o2, d2 = O.full_image_rays(H, W, fx, fy, cx, cy, Mref[6])
 same(o2.reshape(ro.shape), ro, "get_rays origins"); same(d2.reshape(rd.shape), rd, "get_rays directions")
+
+# ---- Decoders.forward / get_raw_sdf, nn.Linear variant (decoders.py:72-84,91-205) on points at and beyond the clamp
+sys.path.insert(0, os.path.join(%(repo)r, "tests"))
+from oracle import gen_golden as GG
+import helpers
+case = GG.CASES["map_scannet_k23"]
+cfg = GG._load_cfg(case)
+bound, grids, dec = GG._build_world(cfg, 0)
+gg = {"variant": np.array("A"), "log2_hash": np.array([cfg["grid"]["hash_size_sdf"], cfg["grid"]["hash_size_color"]]),
+      "per_level_scale": np.array([grids[0].spec.per_level_scale, grids[1].spec.per_level_scale]), "bound": bound.numpy()}
+field = helpers.golden_field(gg, 0, requires_grad=False)
+pts = torch.rand(300, 3, generator=g)
+pts[:8] = torch.tensor([[0, 0, 0], [1, 1, 1], [-0.5, 0.5, 0.5], [1.5, 0.2, 0.9], [0.5, -1e-7, 1 + 1e-7], [0, 1, 0.5], [1e-8, 0.999999, 0.5], [0.25, 0.5, 0.75]])
+with torch.no_grad():
+    ref = dec(pts.reshape(30, 10, 3), ([grids[0]], [grids[1]]))
+    got = O.decoders_forward(field, pts.reshape(30, 10, 3))
+    same(got, ref, "Decoders.forward (variant A)")
+    same(O.raw_sdf(field, pts), dec.get_raw_sdf(pts, ([grids[0]], [grids[1]])), "get_raw_sdf (variant A)")
 print("ok")
 ''' % dict(repo=REPO, ref=REF)
 
