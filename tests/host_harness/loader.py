@@ -37,6 +37,30 @@ def _build(src_name, hdr_name, out_name):
     return out
 
 
+def gpu_check_binary():
+    """tests/_build/cull_gpu_check: the torch-free C-ABI consumer of cull_gpu_check.cu (nvcc, linked against the product library
+    with an rpath relative to the binary).  Returns its path."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    tests = os.path.dirname(here)
+    repo = os.path.dirname(tests)
+    src = os.path.join(here, "cull_gpu_check.cu")
+    deps = [src] + [os.path.join(repo, "uni-slam_b200", "csrc", h) for h in ("usl_cull.cuh", "usl_metrics.cuh")] + [os.path.join(repo, "include", "unislam_b200.h")]
+    out = os.path.join(tests, "_build", "cull_gpu_check")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        tmp = f"{out}.{os.getpid()}.tmp"
+        try:
+            subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-cudart", "shared", "-Xcompiler", "-ffp-contract=off", "-o", tmp, src,
+                            "-I" + os.path.join(repo, "include"), "-L" + os.path.join(repo, "uni-slam_b200", "lib"), "-lunislam_b200",
+                            "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../uni-slam_b200/lib"], check=True)
+            os.replace(tmp, out)
+        except (OSError, subprocess.CalledProcessError):
+            if not os.path.exists(out):
+                raise
+    return out
+
+
 def metrics_host(gt_color, gt_depth, color, depth, nthreads=148 * 4 * 256):
     """acc (3,) float64 = [sum of squared colour errors, sum |depth error|, pixel count] over the pixels with gt_depth > 0, from
     the host build of usl_metrics.cuh (tests/host_harness/metrics_host.cpp)."""

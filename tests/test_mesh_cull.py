@@ -385,3 +385,29 @@ def test_cull_thread_functions_on_degenerate_vertices_and_empty_inputs():
     assert helpers.cull_host_hull(special[:6], np.zeros((0, 4), np.float32), 256).all()          # no plane: everything is inside
     nanv = helpers.cull_host_hull(special[6:9], np.array([[1, 0, 0, -1.0]], np.float32), 256)
     assert not nanv[0]                                                                          # NaN is outside (side <= 0 is false)
+
+
+# ---- the C-ABI from a plain C++ program (no Python, no torch) ------------------------------------------------------------------
+def test_abi_consumer_builds_and_its_problem_is_not_trivial():
+    """tests/host_harness/cull_gpu_check.cu links against the library through include/unislam_b200.h alone; its synthetic
+    problem (host-only mode: the thread functions, no GPU) sees / culls a real fraction of the vertices."""
+    import subprocess
+    from host_harness import loader
+    exe = loader.gpu_check_binary()
+    out = subprocess.run([exe, "20000", "8", "host"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    counts = [int(ln.split()[-3]) for ln in out.stdout.strip().splitlines()]
+    assert len(counts) == 3 and all(0.05 * 20000 < c < 0.95 * 20000 for c in counts), out.stdout
+
+
+@pytest.mark.gpu
+def test_gpu_abi_consumer_matches_the_host_thread_functions():
+    """The same program on the GPU: every culling entry point equals the host build of its thread functions bit for bit, the
+    metrics sums agree to 1e-12 (exit code 0), called with cudaMalloc'd pointers from plain C++."""
+    import json
+    import subprocess
+    from host_harness import loader
+    out = subprocess.run([loader.gpu_check_binary(), "200000", "24"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["all_equal_host"] is True and res["cull_frames_occlusion"]["mismatch_vs_host"] == 0 and res["render_metrics"]["ok"] is True
