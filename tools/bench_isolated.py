@@ -1,7 +1,7 @@
 """Bench legs that run in their OWN process (bench.py starts this file as a child at N = 1 and merges the JSON it prints).
 
-Why a child: these kernels were written after the round's GPU budget was spent, so their first execution on a B200 is
-the driver's own bench run.  A fault in them must not be able to take the headline measurement down with it: the child has
+Why a child: these kernels were written when the round's GPU budget was all but spent (one 3.7 s run of the torch-free
+checker, profiles/r02_cull_gpu_check.json, is all they saw of a B200), so this leg's first execution is the driver's own bench run.  A fault in them must not be able to take the headline measurement down with it: the child has
 its own CUDA context, a time limit, and whatever it prints (or fails to print) only fills the `mesh_cull` / `render_metrics` keys.
 
 Leg 1: eval_rendering's per-frame metrics (usl_render_metrics) on a full-resolution frame.
