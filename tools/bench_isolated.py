@@ -60,13 +60,13 @@ def leg_mesh_cull(P, dev, n_frames=64, voxel=0.0125, sample=20000):
     culler = meshmod.MeshCuller(cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy, cfg.truncation)
     res = {"workload": f"marching-cubes mesh of the synthetic room ({voxel * 100:.2f} cm grid: {V} vertices, {T} faces) against {n_frames} "
                        f"depth frames {cam.W}x{cam.H} ({depths.numel() * 4 / 2**20:.0f} MiB resident)", "vertices": V, "faces": T, "frames": n_frames}
-    w2c = torch.inverse(c2ws)
+    w2c = torch.inverse(c2ws).contiguous()
     from host_harness import loader
     pick = torch.linspace(0, V - 1, min(sample, V), device=dev).long()
     v_host = verts[pick].cpu().numpy()
     depths_host = depths.cpu().numpy()
     for tag, eval_rec in (("occlusion", True), ("frustum_only", False)):
-        ms, seen = _timed(lambda: culler.seen_by_frames(verts, c2ws, depths, eval_rec))
+        ms, seen = _timed(lambda: culler.seen_by_frames(verts, c2ws, depths, eval_rec, w2c=w2c))       # zero-fill of the marks + the launch
         ref = loader.cull_host_frames(v_host, w2c.cpu().numpy(), depths_host, (cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy),
                                       cfg.truncation, eval_rec, 16)
         got = seen[pick].cpu().numpy()
@@ -79,7 +79,7 @@ def leg_mesh_cull(P, dev, n_frames=64, voxel=0.0125, sample=20000):
     sweep = {}
     for fpc in (1, 4, 16, 64):
         culler.frames_per_cta = fpc
-        sweep[str(fpc)], _ = _timed(lambda: culler.seen_by_frames(verts, c2ws, depths, True), iters=2)
+        sweep[str(fpc)], _ = _timed(lambda: culler.seen_by_frames(verts, c2ws, depths, True, w2c=w2c), iters=2)
     culler.frames_per_cta = 0
     res["cull_frames_occlusion_ms_by_frames_per_cta"] = sweep
     ms, out = _timed(lambda: culler.cull_by_frames(verts, faces, None, c2ws, depths, True))

@@ -116,17 +116,18 @@ class MeshCuller:
 
     # ---- per-vertex tests ----
     def seen_by_frames(self, verts: torch.Tensor, c2ws: torch.Tensor, depths: Optional[torch.Tensor], eval_rec: bool,
-                       seen: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       seen: Optional[torch.Tensor] = None, w2c: Optional[torch.Tensor] = None) -> torch.Tensor:
         """NOT whole_mask of cull_mesh.py:58-99, (V,) uint8.  c2ws (K,4,4): estimate_c2w_list[:idx+1] (or the ground-truth
         poses); depths (K,H,W) fp32 sensor depth (required with eval_rec = cfg['meshing']['eval_rec']).  Pass `seen` to
-        accumulate over several calls (ranges of frames)."""
+        accumulate over several calls (ranges of frames); pass `w2c` (K,4,4) = torch.inverse(c2ws) when it is already at hand."""
         H, W, fx, fy, cx, cy = self.cam
         V, K = verts.shape[0], c2ws.shape[0]
         if seen is None:
             seen = torch.zeros((V,), device=verts.device, dtype=torch.uint8)
         a = L.CullFramesArgs()
         a.verts, a.V = cptr(verts, torch.float32, V * 3, "verts (V,3)"), V
-        w2c = torch.inverse(c2ws.to(verts.device, torch.float32)).contiguous()          # cull_mesh.py:69, batched
+        if w2c is None:
+            w2c = torch.inverse(c2ws.to(verts.device, torch.float32)).contiguous()      # cull_mesh.py:69, batched
         a.w2c = cptr(w2c, torch.float32, K * 16, "c2ws (K,4,4)")
         if eval_rec and depths is None:
             raise ValueError("MeshCuller: eval_rec needs the depth frames (K,H,W)")
